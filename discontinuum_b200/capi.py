@@ -1,0 +1,279 @@
+"""ctypes binding of libdgp.so (include/dgp.h) -- the only way Python reaches the CUDA engine.
+
+There is no fallback: if the shared library is missing or no B200 is visible, loading / creating
+an engine raises.  Arrays cross the boundary as raw pointers: numpy float64 arrays (host) or
+torch CUDA float64 tensors (device).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+MAX_TERMS, MAX_FACTORS, MAX_FDIMS, MAX_COLS, MAX_THETA = 8, 3, 4, 8, 48
+ABI_VERSION = 1
+
+RBF, MATERN32, MATERN52, PERIODIC = 0, 1, 2, 3
+GATE_NONE, GATE_SIGMOID, GATE_INV_SIGMOID = 0, 1, 2
+COL_COPY, COL_LOG, COL_GATE = 0, 1, 2
+MEAN_ZERO, MEAN_CONST, MEAN_POWERLAW = 0, 1, 2
+
+
+class DgpCol(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("src", C.c_int32), ("theta", C.c_int32), ("pad_", C.c_int32), ("aux", C.c_double)]
+
+
+class DgpFactor(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ndims", C.c_int32), ("col", C.c_int32 * MAX_FDIMS), ("ls", C.c_int32 * MAX_FDIMS),
+                ("period", C.c_int32), ("pad_", C.c_int32)]
+
+
+class DgpTerm(C.Structure):
+    _fields_ = [("scale", C.c_int32), ("gate", C.c_int32), ("gate_col", C.c_int32), ("nfactors", C.c_int32),
+                ("factor", DgpFactor * MAX_FACTORS)]
+
+
+class DgpSpec(C.Structure):
+    _fields_ = [("abi", C.c_int32), ("ndim", C.c_int32), ("ncols", C.c_int32), ("nterms", C.c_int32),
+                ("ntheta", C.c_int32), ("noise_theta", C.c_int32), ("mean_kind", C.c_int32), ("mean_col", C.c_int32),
+                ("mean_theta", C.c_int32 * 4), ("col", DgpCol * MAX_COLS), ("term", DgpTerm * MAX_TERMS)]
+
+
+# every symbol include/dgp.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+_SIGNATURES = [
+    ("dgp_create", C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, _P]),
+    ("dgp_destroy", C.c_int, [_P]),
+    ("dgp_last_error", C.c_char_p, [_P]),
+    ("dgp_abi_version", C.c_int, []),
+    ("dgp_workspace_bytes", C.c_size_t, [C.c_int, C.c_int]),
+    ("dgp_set_train", C.c_int, [_P, C.POINTER(DgpSpec), _P, _P, _P, C.c_int, C.c_int]),
+    ("dgp_covmat", C.c_int, [_P, _P, _P, C.c_int]),
+    ("dgp_cross_covmat", C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, C.c_int]),
+    ("dgp_nlml", C.c_int, [_P, _P, C.c_double, _P]),
+    ("dgp_nlml_grad", C.c_int, [_P, _P, C.c_double, _P, _P]),
+    ("dgp_nlml_grad_launch", C.c_int, [_P, _P, C.c_double]),
+    ("dgp_nlml_grad_wait", C.c_int, [_P, _P, _P]),
+    ("dgp_factorize", C.c_int, [_P, _P, C.c_double, _P]),
+    ("dgp_predict", C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    ("dgp_sample", C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_double, _P, C.c_int]),
+    ("dgp_get_alpha", C.c_int, [_P, _P, C.c_int]),
+    ("dgp_get_chol", C.c_int, [_P, _P, C.c_int]),
+    ("dgp_set_debug_kinv", C.c_int, [_P, C.c_int]),
+    ("dgp_get_kinv", C.c_int, [_P, _P, C.c_int]),
+    ("dgp_launch_count", C.c_longlong, [_P]),
+    ("dgp_last_timing", C.c_int, [_P, _P]),
+    ("dgp_set_timing", C.c_int, [_P, C.c_int]),
+]
+EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
+
+_LIB: Optional[C.CDLL] = None
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdgp.so")
+
+
+def load_library() -> C.CDLL:
+    """dlopen libdgp.so and bind every declared symbol; raises if the library was not built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build the CUDA engine first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "discontinuum_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, res, args in _SIGNATURES:
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dgp_abi_version() != ABI_VERSION:
+        raise RuntimeError("libdgp.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+class DgpError(RuntimeError):
+    pass
+
+
+def _ptr(a) -> Tuple[int, int]:
+    """(address, on_device) of a numpy array or a torch tensor."""
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+            raise TypeError("expected a C-contiguous float64 array")
+        return a.ctypes.data, 0
+    import torch
+
+    if isinstance(a, torch.Tensor):
+        if a.dtype != torch.float64 or not a.is_contiguous():
+            raise TypeError("expected a contiguous float64 tensor")
+        return a.data_ptr(), 1 if a.is_cuda else 0
+    raise TypeError(type(a))
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+class Engine:
+    """One libdgp handle: the resident training set of one site and its factorisation workspace."""
+
+    def __init__(self, max_n: int, max_m: int = 2048, device: int = 0, stream: int = 0):
+        self.lib = load_library()
+        self._h = _P()
+        rc = self.lib.dgp_create(C.byref(self._h), int(device), int(max_n), int(max_m), _P(stream) if stream else None)
+        if rc != 0:
+            msg = self.lib.dgp_last_error(None)
+            self._h = _P()
+            raise DgpError(f"dgp_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.max_n, self.max_m, self.device = int(max_n), int(max_m), int(device)
+        self.n = 0
+        self.ntheta = 0
+        self._keep = None
+
+    # -- plumbing
+    def _check(self, rc: int, what: str) -> int:
+        if rc < 0:
+            msg = self.lib.dgp_last_error(self._h)
+            raise DgpError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.dgp_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # -- data
+    def set_train(self, spec: DgpSpec, X, y, noise):
+        if isinstance(X, np.ndarray) or not hasattr(X, "data_ptr"):
+            X, y, noise = _f64(X), _f64(y), _f64(noise)
+        n = int(X.shape[0])
+        if X.ndim != 2 or X.shape[1] != spec.ndim or y.shape[0] != n or noise.shape[0] != n:
+            raise ValueError("set_train: X[n, ndim], y[n], noise[n] expected")
+        (px, dx), (py, dy), (pn, dn) = _ptr(X), _ptr(y), _ptr(noise)
+        if not (dx == dy == dn):
+            raise ValueError("set_train: X, y, noise must live on the same side")
+        self._check(self.lib.dgp_set_train(self._h, C.byref(spec), px, py, pn, n, dx), "dgp_set_train")
+        self.n, self.ntheta, self.ndim = n, int(spec.ntheta), int(spec.ndim)
+        self._keep = spec
+
+    def _theta(self, theta) -> np.ndarray:
+        th = _f64(theta).reshape(-1)
+        if th.shape[0] != self.ntheta:
+            raise ValueError(f"theta has {th.shape[0]} entries, spec.ntheta = {self.ntheta}")
+        return th
+
+    # -- hot path
+    def nlml(self, theta, jitter: float = 0.0) -> Tuple[float, int]:
+        th = self._theta(theta)
+        out = C.c_double(0.0)
+        info = self._check(self.lib.dgp_nlml(self._h, th.ctypes.data, float(jitter), C.addressof(out)), "dgp_nlml")
+        return out.value, info
+
+    def nlml_grad(self, theta, jitter: float = 0.0) -> Tuple[float, np.ndarray, int]:
+        th = self._theta(theta)
+        out = C.c_double(0.0)
+        grad = np.zeros(self.ntheta)
+        info = self._check(self.lib.dgp_nlml_grad(self._h, th.ctypes.data, float(jitter), C.addressof(out), grad.ctypes.data),
+                           "dgp_nlml_grad")
+        return out.value, grad, info
+
+    def nlml_grad_launch(self, theta, jitter: float = 0.0):
+        th = self._theta(theta)
+        self._check(self.lib.dgp_nlml_grad_launch(self._h, th.ctypes.data, float(jitter)), "dgp_nlml_grad_launch")
+
+    def nlml_grad_wait(self) -> Tuple[float, np.ndarray, int]:
+        out = C.c_double(0.0)
+        grad = np.zeros(self.ntheta)
+        info = self._check(self.lib.dgp_nlml_grad_wait(self._h, C.addressof(out), grad.ctypes.data), "dgp_nlml_grad_wait")
+        return out.value, grad, info
+
+    def factorize(self, theta, jitter: float = 0.0) -> Tuple[float, int]:
+        th = self._theta(theta)
+        out = C.c_double(0.0)
+        info = self._check(self.lib.dgp_factorize(self._h, th.ctypes.data, float(jitter), C.addressof(out)), "dgp_factorize")
+        return out.value, info
+
+    def predict(self, Xs, want_var: bool = True):
+        on_dev = hasattr(Xs, "data_ptr") and Xs.is_cuda
+        if not on_dev:
+            Xs = _f64(Xs)
+        m = int(Xs.shape[0])
+        if Xs.ndim != 2 or Xs.shape[1] != self.ndim:
+            raise ValueError("predict: Xs[m, ndim] expected")
+        if on_dev:
+            import torch
+
+            mu = torch.empty(m, dtype=torch.float64, device=Xs.device)
+            var = torch.empty(m, dtype=torch.float64, device=Xs.device) if want_var else None
+        else:
+            mu = np.empty(m)
+            var = np.empty(m) if want_var else None
+        self._check(self.lib.dgp_predict(self._h, _ptr(Xs)[0], m, 1 if on_dev else 0, _ptr(mu)[0],
+                                         _ptr(var)[0] if want_var else None), "dgp_predict")
+        return mu, var
+
+    def sample(self, Xs, Z, jitter: float = 0.0) -> np.ndarray:
+        Xs, Z = _f64(Xs), _f64(Z)
+        S, m = Z.shape
+        if Xs.shape[0] != m:
+            raise ValueError("sample: Z[S, m] and Xs[m, ndim] expected")
+        out = np.empty((S, m))
+        self._check(self.lib.dgp_sample(self._h, Xs.ctypes.data, m, Z.ctypes.data, S, float(jitter), out.ctypes.data, 0),
+                    "dgp_sample")
+        return out
+
+    # -- parity / debug
+    def covmat(self, theta) -> np.ndarray:
+        th = self._theta(theta)
+        K = np.empty((self.n, self.n))
+        self._check(self.lib.dgp_covmat(self._h, th.ctypes.data, K.ctypes.data, 0), "dgp_covmat")
+        return K
+
+    def cross_covmat(self, theta, Xs) -> np.ndarray:
+        th, Xs = self._theta(theta), _f64(Xs)
+        K = np.empty((Xs.shape[0], self.n))
+        self._check(self.lib.dgp_cross_covmat(self._h, th.ctypes.data, Xs.ctypes.data, Xs.shape[0], 0, K.ctypes.data, 0),
+                    "dgp_cross_covmat")
+        return K
+
+    def alpha(self) -> np.ndarray:
+        a = np.empty(self.n)
+        self._check(self.lib.dgp_get_alpha(self._h, a.ctypes.data, 0), "dgp_get_alpha")
+        return a
+
+    def chol(self) -> np.ndarray:
+        L = np.empty((self.n, self.n))
+        self._check(self.lib.dgp_get_chol(self._h, L.ctypes.data, 0), "dgp_get_chol")
+        return L
+
+    def set_debug_kinv(self, on: bool):
+        self._check(self.lib.dgp_set_debug_kinv(self._h, 1 if on else 0), "dgp_set_debug_kinv")
+
+    def kinv(self) -> np.ndarray:
+        Ki = np.empty((self.n, self.n))
+        self._check(self.lib.dgp_get_kinv(self._h, Ki.ctypes.data, 0), "dgp_get_kinv")
+        return Ki
+
+    def set_timing(self, on: bool):
+        self._check(self.lib.dgp_set_timing(self._h, 1 if on else 0), "dgp_set_timing")
+
+    def last_timing(self) -> Sequence[float]:
+        ms = (C.c_double * 4)()
+        self.lib.dgp_last_timing(self._h, ms)
+        return list(ms)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.dgp_launch_count(self._h))

@@ -1,0 +1,566 @@
+// libdgp.so -- C ABI (include/dgp.h) and host-side schedule of the B200 exact-GP engine.
+//
+// Per evaluation the schedule is a chain of launches on one stream:
+//   features/residual -> [block-column 0 covariance panel] ->
+//   for s: potf2(s) -> TRSM(s) -> forward-substitution(s) -> trailing update(s)     (n^3/3, DMMA)
+//   for s: TRI_FINAL(s) -> TRI_UPDATE(s)                                            (U = L^-T, n^3/3, DMMA)
+//   alpha = U z ;  LAUUM fused with the W (.) dK/dtheta contraction                 (n^3/3, DMMA)
+//   deterministic reductions -> {nlml, info, grad} -> pinned host buffer.
+// Three padded n x n panels: bufA (work matrix, later the partial sums of U, later T = L^-1),
+// bufL (L, lower), bufU (U = L^-T, upper).  The covariance matrix itself is never stored: tiles are
+// generated in registers as accumulator initial values at their first trailing update.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/dgp.h"
+#include "dgp_cov.cuh"
+#include "dgp_gemm.cuh"
+#include "dgp_panel.cuh"
+
+using namespace dgp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct dgp_handle_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int max_n = 0, max_pad = 0, max_m = 0;
+  int n = 0, npad = 0, nb = 0;
+  bool have_train = false, factorized = false, have_T = false, debug_kinv = false, timing = false;
+  dgp_spec spec;
+  // device buffers
+  double *bufA = nullptr, *bufL = nullptr, *bufU = nullptr, *DI = nullptr;
+  double *X = nullptr, *y = nullptr, *noise = nullptr, *Xw = nullptr, *r = nullptr, *z = nullptr, *alpha = nullptr;
+  double *theta = nullptr, *scal = nullptr, *gpart = nullptr;
+  // prediction chunk
+  double *Kx = nullptr, *Xs = nullptr, *Xws = nullptr, *means = nullptr, *dot = nullptr, *vpart = nullptr;
+  double *mu = nullptr, *var = nullptr;
+  // pinned host staging
+  double *h_theta = nullptr, *h_scal = nullptr;
+  CUtensorMap tmA, tmL, tmU, tmDI, tmKx;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double last_ms[4] = {0, 0, 0, 0};
+  bool pending = false;
+  int pending_grad = 0;
+  long long launches = 0;
+  std::string err;
+};
+
+#define DGP_FAIL(h, code, ...)                                   \
+  do {                                                           \
+    char buf_[512];                                              \
+    snprintf(buf_, sizeof(buf_), __VA_ARGS__);                   \
+    if (h) (h)->err = buf_; else g_create_error = buf_;          \
+    return (code);                                               \
+  } while (0)
+
+#define CK(h, call)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) DGP_FAIL(h, -2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static int make_map(dgp_handle h, CUtensorMap* m, double* base, int rows, int cols, long long ld) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) DGP_FAIL(h, -3, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {BK, 64};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DGP_FAIL(h, -3, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%lld", (int)r, rows, cols, ld);
+  return 0;
+}
+
+template <int INIT, int EPI>
+static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g) {
+  if (g.ntiles <= 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(h, cudaFuncSetAttribute(k_gemm<INIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    attr_set = true;
+  }
+  k_gemm<INIT, EPI><<<g.ntiles, GEMM_THREADS, SM_TOTAL, h->stream>>>(a, b, h->spec, g);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int dgp_abi_version(void) { return DGP_ABI_VERSION; }
+
+size_t dgp_workspace_bytes(int max_n, int max_m) {
+  const size_t np = round_up(max_n > 0 ? max_n : 128, 128);
+  const size_t mc = round_up(max_m > 0 ? max_m : 2048, 128);
+  const size_t nb = np / 128;
+  size_t b = 3 * np * np * 8 + np * 128 * 8;
+  b += nb * (nb + 1) * DGP_MAX_THETA * 8;
+  b += mc * np * 8 + (nb + 2 * nb) * mc * 8;
+  return b;
+}
+
+const char* dgp_last_error(dgp_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) {
+  if (!out || max_n <= 0) DGP_FAIL((dgp_handle) nullptr, -1, "dgp_create: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    DGP_FAIL((dgp_handle) nullptr, -2, "dgp_create: no CUDA device (this engine has no CPU fallback)");
+  dgp_handle h = new dgp_handle_s();
+  h->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete h; return -2; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = "dgp_create: libdgp is built for sm_100a (B200) only";
+    delete h; return -2;
+  }
+  h->max_n = max_n;
+  h->max_pad = round_up(max_n, 128);
+  h->max_m = round_up(max_m > 0 ? max_m : 2048, 128);
+  if (stream) { h->stream = (cudaStream_t)stream; }
+  else { cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking); h->own_stream = true; }
+  const size_t np = h->max_pad, mc = h->max_m, nbm = np / 128;
+  auto A = [&](double** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(double)); };
+  cudaError_t r = cudaSuccess;
+  auto acc = [&](cudaError_t x) { if (r == cudaSuccess) r = x; };
+  acc(A(&h->bufA, np * np)); acc(A(&h->bufL, np * np)); acc(A(&h->bufU, np * np)); acc(A(&h->DI, np * 128));
+  acc(A(&h->X, np * DGP_MAX_COLS)); acc(A(&h->y, np)); acc(A(&h->noise, np)); acc(A(&h->Xw, np * DGP_XS));
+  acc(A(&h->r, np)); acc(A(&h->z, np)); acc(A(&h->alpha, np));
+  acc(A(&h->theta, DGP_MAX_THETA)); acc(A(&h->scal, SC_SIZE)); acc(A(&h->gpart, nbm * (nbm + 1) * DGP_MAX_THETA));
+  acc(A(&h->Kx, mc * np)); acc(A(&h->Xs, mc * DGP_MAX_COLS)); acc(A(&h->Xws, mc * DGP_XS)); acc(A(&h->means, mc));
+  acc(A(&h->dot, nbm * mc)); acc(A(&h->vpart, 2 * nbm * mc)); acc(A(&h->mu, mc)); acc(A(&h->var, mc));
+  acc(cudaMallocHost((void**)&h->h_theta, DGP_MAX_THETA * sizeof(double)));
+  acc(cudaMallocHost((void**)&h->h_scal, SC_SIZE * sizeof(double)));
+  for (int i = 0; i < 5; i++) acc(cudaEventCreate(&h->ev[i]));
+  if (r != cudaSuccess) {
+    g_create_error = std::string("dgp_create: allocation failed: ") + cudaGetErrorString(r);
+    dgp_destroy(h);
+    return -2;
+  }
+  cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM);
+  *out = h;
+  return 0;
+}
+
+int dgp_destroy(dgp_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  double* bufs[] = {h->bufA, h->bufL, h->bufU, h->DI, h->X, h->y, h->noise, h->Xw, h->r, h->z, h->alpha, h->theta,
+                    h->scal, h->gpart, h->Kx, h->Xs, h->Xws, h->means, h->dot, h->vpart, h->mu, h->var};
+  for (double* p : bufs) if (p) cudaFree(p);
+  if (h->h_theta) cudaFreeHost(h->h_theta);
+  if (h->h_scal) cudaFreeHost(h->h_scal);
+  for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+static int check_spec(dgp_handle h, const dgp_spec* sp) {
+  if (sp->abi != DGP_ABI_VERSION) DGP_FAIL(h, -1, "spec abi %d != %d", sp->abi, DGP_ABI_VERSION);
+  if (sp->ndim < 1 || sp->ndim > DGP_MAX_COLS || sp->ncols < 1 || sp->ncols > DGP_MAX_COLS)
+    DGP_FAIL(h, -1, "spec: ndim/ncols out of range");
+  if (sp->nterms < 1 || sp->nterms > DGP_MAX_TERMS) DGP_FAIL(h, -1, "spec: nterms out of range");
+  if (sp->ntheta < 1 || sp->ntheta > DGP_MAX_THETA) DGP_FAIL(h, -1, "spec: ntheta out of range");
+  auto bad = [&](int idx) { return idx < -1 || idx >= sp->ntheta; };
+  if (bad(sp->noise_theta)) DGP_FAIL(h, -1, "spec: noise_theta out of range");
+  for (int c = 0; c < sp->ncols; c++) {
+    const dgp_col& k = sp->col[c];
+    if (k.src < 0 || k.src >= sp->ndim) DGP_FAIL(h, -1, "spec: col %d src out of range", c);
+    if (k.kind == DGP_COL_GATE && (k.theta < 0 || k.theta >= sp->ntheta)) DGP_FAIL(h, -1, "spec: gate col %d theta", c);
+  }
+  for (int t = 0; t < sp->nterms; t++) {
+    const dgp_term& tm = sp->term[t];
+    if (bad(tm.scale) || tm.nfactors < 0 || tm.nfactors > DGP_MAX_FACTORS) DGP_FAIL(h, -1, "spec: term %d", t);
+    if (tm.gate != DGP_GATE_NONE && (tm.gate_col < 0 || tm.gate_col >= sp->ncols || sp->col[tm.gate_col].kind != DGP_COL_GATE))
+      DGP_FAIL(h, -1, "spec: term %d gate column", t);
+    for (int f = 0; f < tm.nfactors; f++) {
+      const dgp_factor& fa = tm.factor[f];
+      if (fa.kind < DGP_RBF || fa.kind > DGP_PERIODIC || fa.ndims < 1 || fa.ndims > DGP_MAX_FDIMS)
+        DGP_FAIL(h, -1, "spec: term %d factor %d kind/ndims", t, f);
+      for (int d = 0; d < fa.ndims; d++)
+        if (fa.col[d] < 0 || fa.col[d] >= sp->ncols || fa.ls[d] < 0 || fa.ls[d] >= sp->ntheta)
+          DGP_FAIL(h, -1, "spec: term %d factor %d dim %d", t, f, d);
+      if (fa.kind == DGP_PERIODIC && (fa.ndims != 1 || fa.period < 0 || fa.period >= sp->ntheta))
+        DGP_FAIL(h, -1, "spec: term %d factor %d periodic", t, f);
+    }
+  }
+  if (sp->mean_kind == DGP_MEAN_CONST && (sp->mean_theta[0] < 0 || sp->mean_theta[0] >= sp->ntheta))
+    DGP_FAIL(h, -1, "spec: mean theta");
+  if (sp->mean_kind == DGP_MEAN_POWERLAW)
+    for (int k = 0; k < 3; k++)
+      if (sp->mean_theta[k] < 0 || sp->mean_theta[k] >= sp->ntheta || sp->mean_col < 0 || sp->mean_col >= sp->ndim)
+        DGP_FAIL(h, -1, "spec: power-law mean");
+  return 0;
+}
+
+int dgp_set_train(dgp_handle h, const dgp_spec* spec, const double* X, const double* y, const double* noise, int n,
+                  int on_device) {
+  if (!h) return -1;
+  if (!spec || !X || !y || !noise || n < 1 || n > h->max_n) DGP_FAIL(h, -1, "dgp_set_train: bad arguments (n=%d, max_n=%d)", n, h->max_n);
+  int rc = check_spec(h, spec);
+  if (rc) return rc;
+  CK(h, cudaSetDevice(h->device));
+  h->spec = *spec;
+  h->n = n;
+  h->npad = round_up(n, 128);
+  h->nb = h->npad / 128;
+  h->factorized = false;
+  h->have_T = false;
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CK(h, cudaMemsetAsync(h->noise, 0, (size_t)h->npad * 8, h->stream));
+  CK(h, cudaMemcpyAsync(h->X, X, (size_t)n * spec->ndim * 8, kind, h->stream));
+  CK(h, cudaMemcpyAsync(h->y, y, (size_t)n * 8, kind, h->stream));
+  CK(h, cudaMemcpyAsync(h->noise, noise, (size_t)n * 8, kind, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  const long long ld = h->npad;
+  if ((rc = make_map(h, &h->tmA, h->bufA, h->npad, h->npad, ld))) return rc;
+  if ((rc = make_map(h, &h->tmL, h->bufL, h->npad, h->npad, ld))) return rc;
+  if ((rc = make_map(h, &h->tmU, h->bufU, h->npad, h->npad, ld))) return rc;
+  if ((rc = make_map(h, &h->tmDI, h->DI, h->npad, 128, 128))) return rc;
+  if ((rc = make_map(h, &h->tmKx, h->Kx, h->max_m, h->npad, ld))) return rc;
+  h->have_train = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------ schedule pieces
+static int upload_theta(dgp_handle h, const double* theta) {
+  memcpy(h->h_theta, theta, sizeof(double) * h->spec.ntheta);
+  CK(h, cudaMemcpyAsync(h->theta, h->h_theta, sizeof(double) * h->spec.ntheta, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+static GemmArgs base_args(dgp_handle h, int mode, int step) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.mode = mode; g.step = step; g.nb = h->nb; g.n = h->n;
+  g.ldc = h->npad; g.sign = 1.0;
+  g.Xw = h->Xw; g.noise = h->noise; g.theta = h->theta; g.alpha = h->alpha; g.part = h->gpart;
+  return g;
+}
+
+static int run_features(dgp_handle h) {
+  k_features<<<(h->npad + 255) / 256, 256, 0, h->stream>>>(h->spec, h->theta, h->X, h->y, h->Xw, h->r, nullptr, h->n,
+                                                        h->npad, h->scal);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  return 0;
+}
+
+static int run_potrf(dgp_handle h, double jitter) {
+  const int nb = h->nb, npad = h->npad;
+  const long long ld = npad;
+  int rc;
+  // block column 0 of Ky
+  k_cov_rect<<<dim3(npad / 32, 1), 256, 0, h->stream>>>(h->spec, h->theta, h->Xw, h->Xw, h->noise, jitter, h->bufA, ld,
+                                                       h->n, h->n, 1, 1, nullptr, nullptr, 0);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  for (int s = 0; s < nb; s++) {
+    const size_t off = (size_t)s * 128 * ld + (size_t)s * 128;
+    k_potf2<<<1, PF_THREADS, PF_SMEM, h->stream>>>(h->bufA + off, h->bufL + off, h->bufU + off, ld,
+                                                   h->DI + (size_t)s * 128 * 128, h->scal, s * 128);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    const int m = nb - s - 1;
+    if (m > 0) {
+      GemmArgs g = base_args(h, M_TRSM, s);
+      g.C = h->bufL; g.ntiles = 2 * m;
+      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmA, h->tmDI, g))) return rc;
+    }
+    k_fwd_step<<<nb - s, 256, 0, h->stream>>>(h->bufL, ld, h->DI, h->r, h->z, s);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    if (m > 0) {
+      GemmArgs g = base_args(h, M_TRAIL, s);
+      g.C = h->bufA; g.ntiles = m * (m + 1); g.sign = -1.0; g.jitter = jitter;
+      if (s == 0) rc = launch_gemm<INIT_COV, EPI_STORE>(h, h->tmL, h->tmL, g);
+      else rc = launch_gemm<INIT_LOAD, EPI_STORE>(h, h->tmL, h->tmL, g);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+static int run_trtri(dgp_handle h) {
+  const int nb = h->nb;
+  int rc;
+  for (int s = 0; s < nb; s++) {
+    if (s >= 1) {
+      GemmArgs g = base_args(h, M_TRI_FINAL, s);
+      g.C = h->bufU; g.ntiles = 2 * s; g.sign = -1.0;
+      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmA, h->tmDI, g))) return rc;
+    }
+    if (s < nb - 1) {
+      GemmArgs g = base_args(h, M_TRI_UPDATE, s);
+      g.C = h->bufA; g.ntiles = (s + 1) * 2 * (nb - s - 1);
+      if ((rc = launch_gemm<INIT_LOAD, EPI_STORE>(h, h->tmU, h->tmL, g))) return rc;
+    }
+  }
+  k_upper_gemv<<<h->npad / 8, 256, 0, h->stream>>>(h->bufU, h->npad, h->z, h->alpha, h->npad);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  return 0;
+}
+
+static int run_lauum_grad(dgp_handle h) {
+  GemmArgs g = base_args(h, M_LAUUM, 0);
+  g.C = h->bufA; g.ntiles = h->nb * (h->nb + 1);
+  g.Kinv = h->debug_kinv ? h->bufA : nullptr;
+  return launch_gemm<INIT_ZERO, EPI_GRAD>(h, h->tmU, h->tmU, g);
+}
+
+static int run_finish(dgp_handle h, int want_grad) {
+  k_finish<<<h->spec.ntheta + 1, 256, 0, h->stream>>>(h->spec, h->theta, h->gpart, h->nb * (h->nb + 1), h->z, h->alpha,
+                                                     h->X, h->n, h->npad, h->scal, want_grad);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(h->h_scal, h->scal, SC_SIZE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
+static int evaluate_launch(dgp_handle h, const double* theta, double jitter, int level) {
+  // level 0: nlml ; 1: nlml + grad ; 2: factorize for prediction (L, U, alpha, T)
+  if (!h) return -1;
+  if (!h->have_train) DGP_FAIL(h, -1, "no training data: call dgp_set_train first");
+  if (!theta) DGP_FAIL(h, -1, "theta is NULL");
+  CK(h, cudaSetDevice(h->device));
+  int rc;
+  h->factorized = false; h->have_T = false;
+  if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
+  if ((rc = upload_theta(h, theta))) return rc;
+  if ((rc = run_features(h))) return rc;
+  if ((rc = run_potrf(h, jitter))) return rc;
+  if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
+  if (level >= 1) {
+    if ((rc = run_trtri(h))) return rc;
+    if (h->timing) CK(h, cudaEventRecord(h->ev[2], h->stream));
+    if (level == 1) {
+      if ((rc = run_lauum_grad(h))) return rc;
+    } else {
+      dim3 grid(h->npad / 32, h->npad / 32);
+      k_transpose_upper<<<grid, 256, 0, h->stream>>>(h->bufU, h->bufA, h->npad);
+      h->launches++;
+      CK(h, cudaGetLastError());
+    }
+    if (h->timing) CK(h, cudaEventRecord(h->ev[3], h->stream));
+  }
+  if ((rc = run_finish(h, level == 1))) return rc;
+  if (h->timing) CK(h, cudaEventRecord(h->ev[4], h->stream));
+  h->pending = true;
+  h->pending_grad = level;
+  return 0;
+}
+
+static int evaluate_wait(dgp_handle h, double* nlml_out, double* grad_out) {
+  if (!h) return -1;
+  if (!h->pending) DGP_FAIL(h, -1, "no evaluation in flight");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->pending = false;
+  const int level = h->pending_grad;
+  if (h->timing) {
+    float ms;
+    for (int i = 0; i < 4; i++) h->last_ms[i] = 0.0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->last_ms[0] = ms;
+    if (level >= 1) {
+      cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->last_ms[1] = ms;
+      cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->last_ms[2] = ms;
+      cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->last_ms[3] = ms;
+    } else {
+      cudaEventElapsedTime(&ms, h->ev[1], h->ev[4]); h->last_ms[3] = ms;
+    }
+  }
+  if (nlml_out) *nlml_out = h->h_scal[SC_NLML];
+  if (grad_out && level == 1) memcpy(grad_out, h->h_scal + SC_GRAD, sizeof(double) * h->spec.ntheta);
+  const int info = (int)h->h_scal[SC_INFO];
+  h->factorized = (info == 0);
+  h->have_T = (info == 0 && level == 2);
+  return info;
+}
+
+int dgp_nlml(dgp_handle h, const double* theta, double jitter, double* nlml_out) {
+  int rc = evaluate_launch(h, theta, jitter, 0);
+  if (rc) return rc;
+  return evaluate_wait(h, nlml_out, nullptr);
+}
+
+int dgp_nlml_grad(dgp_handle h, const double* theta, double jitter, double* nlml_out, double* grad_out) {
+  int rc = evaluate_launch(h, theta, jitter, 1);
+  if (rc) return rc;
+  return evaluate_wait(h, nlml_out, grad_out);
+}
+
+int dgp_nlml_grad_launch(dgp_handle h, const double* theta, double jitter) { return evaluate_launch(h, theta, jitter, 1); }
+int dgp_nlml_grad_wait(dgp_handle h, double* nlml_out, double* grad_out) { return evaluate_wait(h, nlml_out, grad_out); }
+
+int dgp_factorize(dgp_handle h, const double* theta, double jitter, double* nlml_out) {
+  int rc = evaluate_launch(h, theta, jitter, 2);
+  if (rc) return rc;
+  return evaluate_wait(h, nlml_out, nullptr);
+}
+
+// ------------------------------------------------------------------ dense covariance (parity entries)
+static int copy_out(dgp_handle h, double* dst, const double* src_dev, size_t rows, size_t cols, size_t ld, int on_device) {
+  CK(h, cudaMemcpy2DAsync(dst, cols * 8, src_dev, ld * 8, cols * 8, rows,
+                          on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dgp_covmat(dgp_handle h, const double* theta, double* K_out, int out_on_device) {
+  if (!h) return -1;
+  if (!h->have_train || !theta || !K_out) DGP_FAIL(h, -1, "dgp_covmat: bad arguments");
+  CK(h, cudaSetDevice(h->device));
+  int rc;
+  h->factorized = false; h->have_T = false;
+  if ((rc = upload_theta(h, theta))) return rc;
+  if ((rc = run_features(h))) return rc;
+  k_cov_rect<<<dim3(h->npad / 32, h->nb), 256, 0, h->stream>>>(h->spec, h->theta, h->Xw, h->Xw, h->noise, 0.0, h->bufA,
+                                                               h->npad, h->n, h->n, 0, 0, nullptr, nullptr, 0);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  return copy_out(h, K_out, h->bufA, h->n, h->n, h->npad, out_on_device);
+}
+
+static int stage_xs(dgp_handle h, const double* Xs, int m0, int mc, int on_device) {
+  CK(h, cudaMemcpyAsync(h->Xs, Xs + (size_t)m0 * h->spec.ndim, (size_t)mc * h->spec.ndim * 8,
+                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  const int mpad = round_up(mc, 128);
+  k_features<<<(mpad + 255) / 256, 256, 0, h->stream>>>(h->spec, h->theta, h->Xs, nullptr, h->Xws, nullptr, h->means, mc,
+                                                     mpad, nullptr);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  return 0;
+}
+
+int dgp_cross_covmat(dgp_handle h, const double* theta, const double* Xs, int m, int xs_on_device, double* K_out,
+                     int out_on_device) {
+  if (!h) return -1;
+  if (!h->have_train || !theta || !Xs || !K_out || m < 1) DGP_FAIL(h, -1, "dgp_cross_covmat: bad arguments");
+  CK(h, cudaSetDevice(h->device));
+  int rc;
+  h->factorized = false; h->have_T = false;
+  if ((rc = upload_theta(h, theta))) return rc;
+  if ((rc = run_features(h))) return rc;
+  for (int m0 = 0; m0 < m; m0 += h->max_m) {
+    const int mc = (m - m0 < h->max_m) ? m - m0 : h->max_m;
+    if ((rc = stage_xs(h, Xs, m0, mc, xs_on_device))) return rc;
+    const int mpad = round_up(mc, 128);
+    k_cov_rect<<<dim3(mpad / 32, h->nb), 256, 0, h->stream>>>(h->spec, h->theta, h->Xws, h->Xw, h->noise, 0.0, h->Kx,
+                                                             h->npad, mc, h->n, 0, 0, nullptr, nullptr, 0);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    if ((rc = copy_out(h, K_out + (size_t)m0 * h->n, h->Kx, mc, h->n, h->npad, out_on_device))) return rc;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ prediction
+int dgp_predict(dgp_handle h, const double* Xs, int m, int on_device, double* mu_out, double* var_out) {
+  if (!h) return -1;
+  if (!Xs || !mu_out || m < 1) DGP_FAIL(h, -1, "dgp_predict: bad arguments");
+  if (!h->factorized || !h->have_T) DGP_FAIL(h, -1, "dgp_predict: call dgp_factorize first");
+  CK(h, cudaSetDevice(h->device));
+  int rc;
+  const cudaMemcpyKind okind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  for (int m0 = 0; m0 < m; m0 += h->max_m) {
+    const int mc = (m - m0 < h->max_m) ? m - m0 : h->max_m;
+    const int mpad = round_up(mc, 128);
+    if ((rc = stage_xs(h, Xs, m0, mc, on_device))) return rc;
+    // cross covariance chunk (kept for the variance GEMM) fused with the mean partial dot products
+    k_cov_rect<<<dim3(mpad / 32, h->nb), 256, 0, h->stream>>>(h->spec, h->theta, h->Xws, h->Xw, h->noise, 0.0, h->Kx,
+                                                             h->npad, mc, h->n, 0, 0, h->alpha, h->dot, h->max_m);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    if (var_out) {
+      GemmArgs g = base_args(h, M_PREDVAR, 0);
+      g.aux0 = mpad / 128; g.aux1 = h->max_m; g.part = h->vpart;
+      g.ntiles = (mpad / 128) * 2 * h->nb;
+      if ((rc = launch_gemm<INIT_ZERO, EPI_SUMSQ>(h, h->tmKx, h->tmA, g))) return rc;
+    }
+    k_pred_finish<<<(mc + 255) / 256, 256, 0, h->stream>>>(h->spec, h->theta, h->Xws, h->means, h->dot, h->nb, h->vpart,
+                                                          2 * h->nb, h->max_m, mc, h->mu, var_out ? h->var : nullptr);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(mu_out + m0, h->mu, (size_t)mc * 8, okind, h->stream));
+    if (var_out) CK(h, cudaMemcpyAsync(var_out + m0, h->var, (size_t)mc * 8, okind, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, double jitter, double* out, int on_device) {
+  (void)Xs; (void)m; (void)Z; (void)S; (void)jitter; (void)out; (void)on_device;
+  if (!h) return -1;
+  DGP_FAIL(h, -100, "dgp_sample: not implemented yet");
+}
+
+// ------------------------------------------------------------------ accessors
+int dgp_get_alpha(dgp_handle h, double* alpha_out, int out_on_device) {
+  if (!h) return -1;
+  if (!h->factorized || !alpha_out) DGP_FAIL(h, -1, "dgp_get_alpha: no factorisation (needs dgp_nlml_grad or dgp_factorize)");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemcpyAsync(alpha_out, h->alpha, (size_t)h->n * 8, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dgp_get_chol(dgp_handle h, double* L_out, int out_on_device) {
+  if (!h) return -1;
+  if (!h->factorized || !L_out) DGP_FAIL(h, -1, "dgp_get_chol: no factorisation");
+  CK(h, cudaSetDevice(h->device));
+  return copy_out(h, L_out, h->bufL, h->n, h->n, h->npad, out_on_device);
+}
+
+int dgp_set_debug_kinv(dgp_handle h, int enable) { if (!h) return -1; h->debug_kinv = enable != 0; return 0; }
+
+int dgp_get_kinv(dgp_handle h, double* Kinv_out, int out_on_device) {
+  if (!h) return -1;
+  if (!h->factorized || !h->debug_kinv || h->pending_grad != 1 || !Kinv_out)
+    DGP_FAIL(h, -1, "dgp_get_kinv: needs dgp_set_debug_kinv(1) + dgp_nlml_grad");
+  CK(h, cudaSetDevice(h->device));
+  return copy_out(h, Kinv_out, h->bufA, h->n, h->n, h->npad, out_on_device);
+}
+
+long long dgp_launch_count(dgp_handle h) { return h ? h->launches : 0; }
+int dgp_set_timing(dgp_handle h, int enable) { if (!h) return -1; h->timing = enable != 0; return 0; }
+int dgp_last_timing(dgp_handle h, double* ms4) {
+  if (!h || !ms4) return -1;
+  for (int i = 0; i < 4; i++) ms4[i] = h->last_ms[i];
+  return 0;
+}
+
+}  // extern "C"

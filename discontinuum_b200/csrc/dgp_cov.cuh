@@ -1,0 +1,245 @@
+// Covariance-tile generator: device functions that evaluate the composite kernels of
+// loadest-gp / rating-gp (reference: src/loadest_gp/models/gpytorch.py:61-128,
+// src/rating_gp/models/gpytorch.py:205-372, src/rating_gp/models/kernels.py:242-382) and their
+// derivatives w.r.t. the natural hyper-parameters one matrix entry at a time,
+// from per-point feature rows held in shared memory.  Nothing here touches global memory except
+// cov_compile(), which folds theta into a shared-memory parameter block once per CTA.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dgp.h"
+
+#define DGP_XS 8  // doubles per feature-table row (64 B)
+
+namespace dgp {
+
+struct FactorC {
+  int kind, ndims;
+  int col[DGP_MAX_FDIMS];
+  int ls_idx[DGP_MAX_FDIMS];
+  int period_idx, pad_;
+  double inv_ls[DGP_MAX_FDIMS];
+  double w;        // periodic: pi / period
+  double inv_lam;  // periodic: 1 / lengthscale
+  double inv_p;    // periodic: 1 / period
+};
+
+struct TermC {
+  double scale;
+  double gate_a;
+  int scale_idx, gate, gate_col, gate_theta, nf, pad_;
+  FactorC f[DGP_MAX_FACTORS];
+};
+
+struct CovC {
+  int nterms, ntheta, noise_idx, pad_;
+  double extra_noise;  // theta[noise_theta] (0 when absent) + jitter
+  TermC t[DGP_MAX_TERMS];
+};
+
+// slots of the per-term derivative accumulator
+constexpr int SLOT_SCALE = 0;
+constexpr int SLOT_GATE = 1;
+constexpr int SLOT_F0 = 2;                       // + f * SLOT_PER_F + d  (d < 4: lengthscale d; d == 4: period)
+constexpr int SLOT_PER_F = DGP_MAX_FDIMS + 1;
+constexpr int NSLOT = SLOT_F0 + DGP_MAX_FACTORS * SLOT_PER_F;  // 17
+
+// Fold (spec, theta) into shared memory.  Call with all threads of the CTA; ends with a barrier
+// only if `sync` is set (callers that have their own barrier pass false).
+__device__ __forceinline__ void cov_compile(CovC* cc, const dgp_spec& sp, const double* __restrict__ theta,
+                                            double jitter, int tid, int nthreads) {
+  for (int t = tid; t < DGP_MAX_TERMS; t += nthreads) {
+    TermC& tc = cc->t[t];
+    if (t < sp.nterms) {
+      const dgp_term& st = sp.term[t];
+      tc.scale_idx = st.scale;
+      tc.scale = st.scale >= 0 ? theta[st.scale] : 1.0;
+      tc.gate = st.gate;
+      tc.gate_col = st.gate_col;
+      tc.gate_theta = -1;
+      tc.gate_a = 0.0;
+      if (st.gate != DGP_GATE_NONE) {
+        tc.gate_theta = sp.col[st.gate_col].theta;
+        tc.gate_a = sp.col[st.gate_col].aux;
+      }
+      tc.nf = st.nfactors;
+      for (int f = 0; f < DGP_MAX_FACTORS; f++) {
+        FactorC& fc = tc.f[f];
+        const dgp_factor& sf = st.factor[f];
+        fc.kind = sf.kind;
+        fc.ndims = f < st.nfactors ? sf.ndims : 0;
+        fc.period_idx = -1;
+        fc.w = 0.0; fc.inv_lam = 0.0; fc.inv_p = 0.0;
+        for (int d = 0; d < DGP_MAX_FDIMS; d++) {
+          fc.col[d] = 0; fc.ls_idx[d] = -1; fc.inv_ls[d] = 0.0;
+          if (d < fc.ndims) {
+            fc.col[d] = sf.col[d];
+            fc.ls_idx[d] = sf.ls[d];
+            fc.inv_ls[d] = 1.0 / theta[sf.ls[d]];
+          }
+        }
+        if (f < st.nfactors && sf.kind == DGP_PERIODIC) {
+          fc.period_idx = sf.period;
+          fc.inv_p = 1.0 / theta[sf.period];
+          fc.w = 3.14159265358979323846 * fc.inv_p;
+          fc.inv_lam = fc.inv_ls[0];
+        }
+      }
+    } else {
+      tc.nf = 0; tc.scale = 0.0; tc.scale_idx = -1; tc.gate = 0;
+    }
+  }
+  if (tid == 0) {
+    cc->nterms = sp.nterms;
+    cc->ntheta = sp.ntheta;
+    cc->noise_idx = sp.noise_theta;
+    cc->extra_noise = (sp.noise_theta >= 0 ? theta[sp.noise_theta] : 0.0) + jitter;
+  }
+}
+
+// value of one stationary factor
+__device__ __forceinline__ double factor_val(const FactorC& f, const double* xi, const double* xj) {
+  if (f.kind == DGP_PERIODIC) {
+    const double u = (xi[f.col[0]] - xj[f.col[0]]) * f.w;
+    const double s = sin(u);
+    return exp(-2.0 * s * s * f.inv_lam);
+  }
+  double d2 = 0.0;
+  for (int d = 0; d < f.ndims; d++) {
+    const double z = (xi[f.col[d]] - xj[f.col[d]]) * f.inv_ls[d];
+    d2 = fma(z, z, d2);
+  }
+  if (f.kind == DGP_RBF) return exp(-0.5 * d2);
+  const double r = sqrt(d2);
+  if (f.kind == DGP_MATERN32) {
+    const double a = 1.7320508075688772 * r;
+    return (1.0 + a) * exp(-a);
+  }
+  const double a = 2.23606797749979 * r;  // MATERN52
+  return (1.0 + a + a * a * (1.0 / 3.0)) * exp(-a);
+}
+
+// value of one covariance entry (no noise)
+__device__ __forceinline__ double cov_entry(const CovC* cc, const double* xi, const double* xj) {
+  double k = 0.0;
+  for (int t = 0; t < cc->nterms; t++) {
+    const TermC& tc = cc->t[t];
+    double v = tc.scale;
+    if (tc.gate != DGP_GATE_NONE) {
+      double gi = xi[tc.gate_col], gj = xj[tc.gate_col];
+      if (tc.gate == DGP_GATE_INV_SIGMOID) { gi = 1.0 - gi; gj = 1.0 - gj; }
+      v *= gi * gj;
+    }
+    for (int f = 0; f < tc.nf; f++) v *= factor_val(tc.f[f], xi, xj);
+    k += v;
+  }
+  return k;
+}
+
+// value of factor f and d(value)/d(param) for its parameters: dls[d] (lengthscales), dper (period)
+__device__ __forceinline__ double factor_val_grad(const FactorC& f, const double* xi, const double* xj,
+                                                  double (&dls)[DGP_MAX_FDIMS], double& dper) {
+  dper = 0.0;
+#pragma unroll
+  for (int d = 0; d < DGP_MAX_FDIMS; d++) dls[d] = 0.0;
+  if (f.kind == DGP_PERIODIC) {
+    const double u = (xi[f.col[0]] - xj[f.col[0]]) * f.w;
+    double s, c;
+    sincos(u, &s, &c);
+    const double val = exp(-2.0 * s * s * f.inv_lam);
+    dls[0] = val * 2.0 * s * s * f.inv_lam * f.inv_lam;            // d/d lam
+    dper = val * (4.0 * f.inv_lam) * s * c * u * f.inv_p;         // d/d period = val*(2/lam)*sin(2u)*u/p
+    return val;
+  }
+  double d2 = 0.0;
+  double z2[DGP_MAX_FDIMS];
+#pragma unroll
+  for (int d = 0; d < DGP_MAX_FDIMS; d++) {
+    z2[d] = 0.0;
+    if (d < f.ndims) {
+      const double z = (xi[f.col[d]] - xj[f.col[d]]) * f.inv_ls[d];
+      z2[d] = z * z;
+      d2 += z2[d];
+    }
+  }
+  double val, common;  // d val / d ls_d = common * z_d^2 / ls_d
+  if (f.kind == DGP_RBF) {
+    val = exp(-0.5 * d2);
+    common = val;
+  } else {
+    const double r = sqrt(d2);
+    if (f.kind == DGP_MATERN32) {
+      const double a = 1.7320508075688772 * r;
+      const double e = exp(-a);
+      val = (1.0 + a) * e;
+      common = 3.0 * e;
+    } else {
+      const double a = 2.23606797749979 * r;
+      const double e = exp(-a);
+      val = (1.0 + a + a * a * (1.0 / 3.0)) * e;
+      common = (5.0 / 3.0) * (1.0 + a) * e;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < DGP_MAX_FDIMS; d++)
+    if (d < f.ndims) dls[d] = common * z2[d] * f.inv_ls[d];
+  return val;
+}
+
+// Accumulate w * d(term)/d(param) into acc[NSLOT] for one entry.  Returns nothing; the caller
+// reduces acc over the tile and scatters slots to theta indices with term_scatter().
+__device__ __forceinline__ void term_grad_accum(const TermC& tc, const double* xi, const double* xj, double w,
+                                                double (&acc)[NSLOT]) {
+  double G = 1.0, dG = 0.0;
+  if (tc.gate != DGP_GATE_NONE) {
+    double gi = xi[tc.gate_col], gj = xj[tc.gate_col];
+    double sgn = tc.gate_a;
+    if (tc.gate == DGP_GATE_INV_SIGMOID) { gi = 1.0 - gi; gj = 1.0 - gj; sgn = -sgn; }
+    G = gi * gj;
+    dG = sgn * G * (2.0 - gi - gj);
+  }
+  double fv[DGP_MAX_FACTORS];
+  double dls[DGP_MAX_FACTORS][DGP_MAX_FDIMS];
+  double dper[DGP_MAX_FACTORS];
+  double F = 1.0;
+#pragma unroll
+  for (int f = 0; f < DGP_MAX_FACTORS; f++) {
+    fv[f] = 1.0; dper[f] = 0.0;
+#pragma unroll
+    for (int d = 0; d < DGP_MAX_FDIMS; d++) dls[f][d] = 0.0;
+    if (f < tc.nf) {
+      fv[f] = factor_val_grad(tc.f[f], xi, xj, dls[f], dper[f]);
+      F *= fv[f];
+    }
+  }
+  acc[SLOT_SCALE] = fma(w, G * F, acc[SLOT_SCALE]);
+  const double ws = w * tc.scale;
+  acc[SLOT_GATE] = fma(ws, dG * F, acc[SLOT_GATE]);
+  const double wsg = ws * G;
+#pragma unroll
+  for (int f = 0; f < DGP_MAX_FACTORS; f++) {
+    if (f < tc.nf) {
+      double others = 1.0;
+#pragma unroll
+      for (int g = 0; g < DGP_MAX_FACTORS; g++)
+        if (g != f) others *= fv[g];
+      const double wo = wsg * others;
+#pragma unroll
+      for (int d = 0; d < DGP_MAX_FDIMS; d++)
+        acc[SLOT_F0 + f * SLOT_PER_F + d] = fma(wo, dls[f][d], acc[SLOT_F0 + f * SLOT_PER_F + d]);
+      acc[SLOT_F0 + f * SLOT_PER_F + DGP_MAX_FDIMS] = fma(wo, dper[f], acc[SLOT_F0 + f * SLOT_PER_F + DGP_MAX_FDIMS]);
+    }
+  }
+}
+
+// theta index of a slot of term tc (-1: unused)
+__device__ __forceinline__ int term_slot_theta(const TermC& tc, int slot) {
+  if (slot == SLOT_SCALE) return tc.scale_idx;
+  if (slot == SLOT_GATE) return tc.gate != DGP_GATE_NONE ? tc.gate_theta : -1;
+  const int f = (slot - SLOT_F0) / SLOT_PER_F, d = (slot - SLOT_F0) % SLOT_PER_F;
+  if (f >= tc.nf) return -1;
+  if (d == DGP_MAX_FDIMS) return tc.f[f].period_idx;
+  return d < tc.f[f].ndims ? tc.f[f].ls_idx[d] : -1;
+}
+
+}  // namespace dgp

@@ -1,0 +1,417 @@
+// FP64 tensor-pipe tile engine: C(128x64 tile) = init -/+ sum_k A[rows, k] * B[rows', k]^T  ("NT" form,
+// both operands K-contiguous), DMMA.8x8x4 (mma.sync.m8n8k4.f64) fed from a TMA + mbarrier ring.
+//
+// One CTA = one 128x64 output tile: warps 0-3 are DMMA consumers (2x2, 64x32 per warp, 128 accumulator
+// registers), warp 4 is the TMA producer.  Two CTAs are co-resident per SM so that one CTA's tile
+// prologue/epilogue overlaps the other's main loop.  Operand tiles are 64-row x 16-col (128 B) TMA boxes
+// with the 128-byte swizzle; the k-index permutation kperm() makes every fragment load conflict free.
+//
+// The same kernel runs every O(n^3) phase of the marginal-likelihood evaluation; `mode` selects how a
+// tile index maps to operand panels (decode_job) and the template flags select the accumulator
+// initialisation (zero / load C / generate covariance tile) and the epilogue (store / fused
+// W (.) dK/dtheta contraction / row sum of squares).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "dgp_cov.cuh"
+
+namespace dgp {
+
+constexpr int BM = 128, BN = 64, BK = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 8;   // 16 KB
+constexpr int B_BYTES = BN * BK * 8;   //  8 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 160;      // 4 consumer warps + 1 producer warp
+constexpr int WS = BN + 1;             // padded row stride of the W tile in the grad epilogue
+
+enum { M_TRSM = 0, M_TRAIL = 1, M_TRI_FINAL = 2, M_TRI_UPDATE = 3, M_LAUUM = 4, M_PREDVAR = 5, M_GENERIC = 6 };
+enum { INIT_ZERO = 0, INIT_LOAD = 1, INIT_COV = 2 };
+enum { EPI_STORE = 0, EPI_GRAD = 1, EPI_SUMSQ = 2 };
+
+struct GemmArgs {
+  int mode, step, nb, n;        // nb = npad / 128, n = valid points
+  int ntiles, aux0, aux1, aux2; // mode dependent (M_PREDVAR: aux0 = row blocks of the chunk; M_GENERIC: see decode)
+  double* C; long long ldc;     // in/out matrix of the tile
+  double sign;                  // EPI_STORE: C = sign * acc  (INIT_LOAD loads sign * C)
+  const double* Xw;             // feature table [npad][DGP_XS]          (INIT_COV, EPI_GRAD)
+  const double* noise;          // fixed noise [npad]                    (INIT_COV)
+  const double* theta;          // natural parameters on device          (INIT_COV, EPI_GRAD)
+  const double* alpha;          // [npad]                                (EPI_GRAD)
+  double* part;                 // EPI_GRAD: [ntiles][DGP_MAX_THETA]; EPI_SUMSQ: [2 nb][rows]
+  double* Kinv;                 // optional dense Ky^-1 output (EPI_GRAD, debug), ld = ldc
+  double jitter;
+};
+
+struct Job {
+  int rowA, kA, rowB, kB, nk;   // operand panel origins (elements) and number of 16-wide k steps
+  int crow, ccol;               // output tile origin
+  int init;                     // INIT_* actually used by this tile
+};
+
+__device__ __forceinline__ int isqrt_floor(int x) {
+  int r = (int)sqrt((double)x);
+  while (r * r > x) --r;
+  while ((r + 1) * (r + 1) <= x) ++r;
+  return r;
+}
+
+__device__ __forceinline__ Job decode_job(const GemmArgs& g, int tile, int init_default) {
+  Job j;
+  j.init = init_default;
+  const int s = g.step;
+  switch (g.mode) {
+    case M_TRSM: {  // L[i, s] = A[i, s] * Linv_s^T            A: work panel, B: diagonal-inverse table
+      const int i = s + 1 + (tile >> 1), h = tile & 1;
+      j.rowA = i * 128; j.kA = s * 128;
+      j.rowB = s * 128 + h * 64; j.kB = 0;
+      j.nk = h ? 8 : 4;
+      j.crow = i * 128; j.ccol = s * 128 + h * 64;
+    } break;
+    case M_TRAIL: {  // A[i, c] -= L[i, s] L[c, s]^T  for s < c-block <= i
+      const int ip = (isqrt_floor(4 * tile + 1) - 1) >> 1;
+      const int cp = tile - ip * (ip + 1);
+      const int i = s + 1 + ip, c = 2 * (s + 1) + cp;
+      j.rowA = i * 128; j.kA = s * 128;
+      j.rowB = c * 64; j.kB = s * 128;
+      j.nk = 8;
+      j.crow = i * 128; j.ccol = c * 64;
+      j.init = (s == 0) ? INIT_COV : INIT_LOAD;
+    } break;
+    case M_TRI_FINAL: {  // U[i, s] = -S[i, s] * Linv_s^T   for i < s
+      const int i = tile >> 1, h = tile & 1;
+      j.rowA = i * 128; j.kA = s * 128;
+      j.rowB = s * 128 + h * 64; j.kB = 0;
+      j.nk = h ? 8 : 4;
+      j.crow = i * 128; j.ccol = s * 128 + h * 64;
+    } break;
+    case M_TRI_UPDATE: {  // S[i, c] += U[i, s] L[c, s]^T  for i <= s < c-block
+      const int ncb = 2 * (g.nb - s - 1);
+      const int i = tile / ncb, c = 2 * (s + 1) + tile % ncb;
+      j.rowA = i * 128; j.kA = s * 128;
+      j.rowB = c * 64; j.kB = s * 128;
+      j.nk = 8;
+      j.crow = i * 128; j.ccol = c * 64;
+      j.init = (i == s) ? INIT_ZERO : INIT_LOAD;
+    } break;
+    case M_LAUUM: {  // Kinv[i, c] = sum_{k >= i} U[i, k] U[c, k]^T  (lower tiles, longest K first)
+      const int i = (isqrt_floor(4 * tile + 1) - 1) >> 1;
+      const int c = tile - i * (i + 1);
+      j.rowA = i * 128; j.kA = i * 128;
+      j.rowB = c * 64; j.kB = i * 128;
+      j.nk = (g.nb - i) * 8;
+      j.crow = i * 128; j.ccol = c * 64;
+    } break;
+    case M_PREDVAR: {  // V^T[i*, c] = sum_{k < (c+1)64} Kx[i*, k] T[c, k]   (T = L^-1), longest K first
+      const int rb = g.aux0;
+      const int c = 2 * g.nb - 1 - tile / rb, i = tile % rb;
+      j.rowA = i * 128; j.kA = 0;
+      j.rowB = c * 64; j.kB = 0;
+      j.nk = (c + 1) * 4;
+      j.crow = i * 128; j.ccol = c * 64;
+    } break;
+    default: {  // M_GENERIC: C[i, c] (+)= A[i, :] B[c, :]^T, aux0 = col blocks(64), aux1 = k steps,
+                // aux2 = 1: lower-triangular B (k <= row), 2: lower tiles only (SYRK), 0: dense
+      const int ncb = g.aux0;
+      int i = tile / ncb, c = tile % ncb;
+      if (g.aux2 == 2) {
+        i = (isqrt_floor(4 * tile + 1) - 1) >> 1;
+        c = tile - i * (i + 1);
+      }
+      j.rowA = i * 128; j.kA = 0;
+      j.rowB = c * 64; j.kB = 0;
+      j.nk = g.aux1;
+      if (g.aux2 == 1) j.nk = min(g.aux1, (c + 1) * 4);
+      j.crow = i * 128; j.ccol = c * 64;
+    } break;
+  }
+  return j;
+}
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// dynamic shared memory map (bytes from a 1024-aligned base)
+constexpr int SM_STAGES = 0;
+constexpr int SM_XS = STAGES * STAGE_BYTES;                 // 192 feature rows (INIT_COV)
+constexpr int SM_COVC = SM_XS + (BM + BN) * DGP_XS * 8;     // CovC
+constexpr int SM_BAR = SM_COVC + ((sizeof(CovC) + 15) / 16) * 16;
+constexpr int SM_TOTAL = SM_BAR + 2 * STAGES * 8 + 1024;    // + alignment slack
+// grad epilogue carve-out inside the (then idle) stage ring
+constexpr int SMG_W = 0;                                    // W tile [128][WS]
+constexpr int SMG_XS = SMG_W + BM * WS * 8;                 // feature rows
+constexpr int SMG_AL = SMG_XS + (BM + BN) * DGP_XS * 8;     // alpha_i[128], alpha_j[64]
+constexpr int SMG_PART = SMG_AL + (BM + BN) * 8;            // [4 warps][8 terms][NSLOT] + noise[4]
+constexpr int SMG_END = SMG_PART + (4 * DGP_MAX_TERMS * NSLOT + 4) * 8;
+static_assert(SMG_END <= STAGES * STAGE_BYTES, "grad epilogue does not fit the stage ring");
+
+template <int INIT, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+       const __grid_constant__ dgp_spec spec, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + SM_BAR);
+  uint64_t* empty = full + STAGES;
+  CovC* cc = (CovC*)(smem + SM_COVC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Job job = decode_job(g, blockIdx.x, INIT);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < job.nk; it++) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
+        uint8_t* st = smem + SM_STAGES + s * STAGE_BYTES;
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        tma_load_2d(st, &tmA, &full[s], job.kA + it * BK, job.rowA);
+        tma_load_2d(st + 64 * BK * 8, &tmA, &full[s], job.kA + it * BK, job.rowA + 64);
+        tma_load_2d(st + A_BYTES, &tmB, &full[s], job.kB + it * BK, job.rowB);
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- DMMA consumers
+  const int g8 = lane >> 2, q = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  double acc[8][4][2];
+
+  // ---- accumulator initialisation
+  if (INIT == INIT_COV && job.init == INIT_COV) {
+    double* xs = (double*)(smem + SM_XS);
+    const int t = threadIdx.x;  // 0..127
+    cov_compile(cc, spec, g.theta, g.jitter, t, 128);
+    for (int e = t; e < (BM + BN) * DGP_XS; e += 128) {
+      const int r = e / DGP_XS, c = e % DGP_XS;
+      const int gr = (r < BM) ? job.crow + r : job.ccol + (r - BM);
+      xs[e] = g.Xw[(size_t)gr * DGP_XS + c];
+    }
+    consumer_bar();
+#pragma unroll 1
+    for (int mi = 0; mi < 8; mi++) {
+      const int lr = 64 * wm + 8 * mi + g8, gr = job.crow + lr;
+      const double* xi = xs + lr * DGP_XS;
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int lc = 32 * wn + 8 * ni + 2 * q + e, gc = job.ccol + lc;
+          double v;
+          if (gr < g.n && gc < g.n) {
+            v = cov_entry(cc, xi, xs + (BM + lc) * DGP_XS);
+            if (gr == gc) v += g.noise[gr] + cc->extra_noise;
+          } else {
+            v = (gr == gc) ? 1.0 : 0.0;
+          }
+          acc[mi][ni][e] = g.sign * v;
+        }
+      }
+    }
+  } else if ((INIT == INIT_LOAD || INIT == INIT_COV) && job.init == INIT_LOAD) {
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++) {
+      const double* crow = g.C + (size_t)(job.crow + 64 * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+        const double2 v = *reinterpret_cast<const double2*>(crow + 8 * ni);
+        acc[mi][ni][0] = g.sign * v.x;
+        acc[mi][ni][1] = g.sign * v.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+  }
+
+  // ---- main loop.  Fragment addressing: row r of a 64-row box sits at r*128 B; logical 16-byte chunk
+  // ch of that row is stored at chunk (ch ^ (r & 7)) (TMA 128B swizzle).  Lane (g8, q) takes, for the
+  // s-th k4 step of a stage, k = (q>>1)*8 + 2s + (q&1), i.e. chunk (q>>1)*4 + s, word q&1: the 16
+  // lanes of each half warp then hit 16 distinct 8-byte bank pairs.
+  const uint32_t a_off = (uint32_t)((64 * wm + g8) * 128 + (q & 1) * 8);
+  const uint32_t b_off = (uint32_t)(A_BYTES + (32 * wn + g8) * 128 + (q & 1) * 8);
+  const uint32_t chq = (uint32_t)((q >> 1) * 4);
+  const uint32_t sbase = smem_u32(smem + SM_STAGES);
+  for (int it = 0; it < job.nk; it++) {
+    const int s = it % STAGES;
+    mbar_wait(&full[s], (it / STAGES) & 1);
+    const uint32_t st = sbase + s * STAGE_BYTES;
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const uint32_t sw = ((chq + ks) ^ (uint32_t)g8) << 4;
+      double a[8], b[4];
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++)
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[mi]) : "r"(st + a_off + mi * 1024 + sw));
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++)
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[ni]) : "r"(st + b_off + ni * 1024 + sw));
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni], a[mi], b[ni]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ---- epilogue
+  if (EPI == EPI_STORE) {
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++) {
+      double* crow = g.C + (size_t)(job.crow + 64 * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+        double2 v;
+        v.x = g.sign * acc[mi][ni][0];
+        v.y = g.sign * acc[mi][ni][1];
+        *reinterpret_cast<double2*>(crow + 8 * ni) = v;
+      }
+    }
+  } else if (EPI == EPI_SUMSQ) {
+    // row sums of squares of the tile -> part[cblock][row]
+    const int cb = job.ccol / 64;
+    double rs[8];
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++) {
+      double s = 0.0;
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) s += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      rs[mi] = s;
+    }
+    // two warps (wn = 0, 1) share a row: combine through the (now idle) stage ring
+    double* red = (double*)(smem + SM_STAGES);
+    consumer_bar();
+    if (q == 0 && wn == 1) {
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) red[64 * wm + 8 * mi + g8] = rs[mi];
+    }
+    consumer_bar();
+    if (q == 0 && wn == 0) {
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) {
+        const int lr = 64 * wm + 8 * mi + g8;
+        g.part[(size_t)cb * g.aux1 + job.crow + lr] = rs[mi] + red[lr];
+      }
+    }
+  } else {  // EPI_GRAD: W = alpha_i alpha_j' - Kinv, contracted with regenerated dK/dtheta tiles
+    consumer_bar();  // every warp is done reading the ring
+    double* W = (double*)(smem + SM_STAGES + SMG_W);
+    double* xs = (double*)(smem + SM_STAGES + SMG_XS);
+    double* al = (double*)(smem + SM_STAGES + SMG_AL);
+    double* part = (double*)(smem + SM_STAGES + SMG_PART);
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++) {
+      const int lr = 64 * wm + 8 * mi + g8;
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+        const int lc = 32 * wn + 8 * ni + 2 * q;
+        W[lr * WS + lc] = acc[mi][ni][0];
+        W[lr * WS + lc + 1] = acc[mi][ni][1];
+        if (g.Kinv != nullptr) {
+          double2 v; v.x = acc[mi][ni][0]; v.y = acc[mi][ni][1];
+          *reinterpret_cast<double2*>(g.Kinv + (size_t)(job.crow + lr) * g.ldc + job.ccol + lc) = v;
+        }
+      }
+    }
+    cov_compile(cc, spec, g.theta, 0.0, t, 128);
+    for (int e = t; e < (BM + BN) * DGP_XS; e += 128) {
+      const int r = e / DGP_XS, c = e % DGP_XS;
+      const int gr = (r < BM) ? job.crow + r : job.ccol + (r - BM);
+      xs[e] = g.Xw[(size_t)gr * DGP_XS + c];
+    }
+    for (int e = t; e < BM + BN; e += 128) al[e] = g.alpha[(e < BM) ? job.crow + e : job.ccol + (e - BM)];
+    consumer_bar();
+
+    // thread t owns row t of the tile
+    const int grow = job.crow + t;
+    double xi[DGP_XS];
+#pragma unroll
+    for (int c = 0; c < DGP_XS; c++) xi[c] = xs[t * DGP_XS + c];
+    const double ai = al[t];
+    double trw = 0.0;
+    for (int term = 0; term < cc->nterms; term++) {
+      double sl[NSLOT];
+#pragma unroll
+      for (int k = 0; k < NSLOT; k++) sl[k] = 0.0;
+      const TermC& tc = cc->t[term];
+#pragma unroll 1
+      for (int c = 0; c < BN; c++) {
+        const int gcol = job.ccol + c;
+        if (grow < g.n && gcol <= grow) {
+          const double wgt = (gcol == grow) ? 1.0 : 2.0;
+          const double w = wgt * (ai * al[BM + c] - W[t * WS + c]);
+          term_grad_accum(tc, xi, xs + (BM + c) * DGP_XS, w, sl);
+          if (term == 0 && gcol == grow) trw += w;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NSLOT; k++) {
+        double v = sl[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) part[(warp * DGP_MAX_TERMS + term) * NSLOT + k] = v;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) trw += __shfl_xor_sync(0xffffffffu, trw, o);
+    if (lane == 0) part[4 * DGP_MAX_TERMS * NSLOT + warp] = trw;
+    consumer_bar();
+    if (t < cc->ntheta) {
+      double s = 0.0;
+      for (int term = 0; term < cc->nterms; term++)
+        for (int k = 0; k < NSLOT; k++)
+          if (term_slot_theta(cc->t[term], k) == t)
+            for (int w4 = 0; w4 < 4; w4++) s += part[(w4 * DGP_MAX_TERMS + term) * NSLOT + k];
+      if (t == cc->noise_idx)
+        for (int w4 = 0; w4 < 4; w4++) s += part[4 * DGP_MAX_TERMS * NSLOT + w4];
+      g.part[(size_t)blockIdx.x * DGP_MAX_THETA + t] = -0.5 * s;
+    }
+  }
+}
+
+}  // namespace dgp

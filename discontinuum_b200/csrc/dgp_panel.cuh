@@ -1,0 +1,381 @@
+// Latency-bound and memory-bound companions of the DMMA tile engine: diagonal-block factorisation
+// (with the triangular inverse produced by the same elimination), feature-table / residual
+// preparation, covariance panels and rectangles, blocked forward substitution, triangular GEMV,
+// transposition and the deterministic final reductions.
+#pragma once
+#include "dgp_cov.cuh"
+
+namespace dgp {
+
+// device scalar block written by the kernels below and copied back to the host
+enum { SC_LOGDET = 0, SC_INFO = 1, SC_QUAD = 2, SC_NLML = 3, SC_GRAD = 8 };  // grad at [SC_GRAD, SC_GRAD + ntheta)
+constexpr int SC_SIZE = SC_GRAD + DGP_MAX_THETA;
+
+// ------------------------------------------------------------------ features, residual, scalars
+// Xw[i] = feature row of point i (copy / log-warp / gate columns, src/rating_gp/models/kernels.py:307-382),
+// mean[i] = m(x_i) (ConstantMean, or PowerLawTransform src/rating_gp/models/gpytorch.py:28-40),
+// r[i] = y[i] - mean[i] when y != nullptr.  Rows >= n are zero.
+__global__ void k_features(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta,
+                           const double* __restrict__ X, const double* __restrict__ y, double* __restrict__ Xw,
+                           double* __restrict__ r, double* __restrict__ mean_out, int n, int npad,
+                           double* __restrict__ scal) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (scal != nullptr && i < SC_SIZE) scal[i] = 0.0;
+  if (i >= npad) return;
+  double row[DGP_XS];
+#pragma unroll
+  for (int c = 0; c < DGP_XS; c++) row[c] = 0.0;
+  double m = 0.0;
+  if (i < n) {
+    const double* x = X + (size_t)i * spec.ndim;
+    for (int c = 0; c < spec.ncols; c++) {
+      const dgp_col& sc = spec.col[c];
+      const double v = x[sc.src];
+      if (sc.kind == DGP_COL_COPY) row[c] = v;
+      else if (sc.kind == DGP_COL_LOG) row[c] = log(v + sc.aux);
+      else row[c] = 1.0 / (1.0 + exp(sc.aux * (v - theta[sc.theta])));
+    }
+    if (spec.mean_kind == DGP_MEAN_CONST) m = theta[spec.mean_theta[0]];
+    else if (spec.mean_kind == DGP_MEAN_POWERLAW)
+      m = theta[spec.mean_theta[0]] + theta[spec.mean_theta[1]] * log(x[spec.mean_col] - theta[spec.mean_theta[2]]);
+  }
+#pragma unroll
+  for (int c = 0; c < DGP_XS; c++) Xw[(size_t)i * DGP_XS + c] = row[c];
+  if (mean_out != nullptr) mean_out[i] = m;
+  if (r != nullptr) r[i] = (i < n && y != nullptr) ? y[i] - m : 0.0;
+}
+
+// ------------------------------------------------------------------ covariance rectangle
+// out[i, j] = k(xa_i, xb_j) (+ noise on the global diagonal when `diag_noise`), i < ra_pad, j in this
+// CTA's 128-column block.  Entries outside (na, nb_) are identity padding when `ident_pad`, else 0.
+// Optionally accumulates dot[cblock][i] = sum_j out[i, j] * vec[j] (posterior mean partials).
+// grid = (ra_pad / 32, ncol_blocks), block = 256 threads, each thread 16 entries.
+__global__ void __launch_bounds__(256)
+k_cov_rect(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta,
+           const double* __restrict__ XwA, const double* __restrict__ XwB, const double* __restrict__ noise,
+           double jitter, double* __restrict__ out, long long ld, int na, int nb_, int diag_noise, int ident_pad,
+           const double* __restrict__ vec, double* __restrict__ dot, int dot_ld) {
+  __shared__ CovC cc;
+  __shared__ double xa[32 * DGP_XS];
+  __shared__ double xb[128 * DGP_XS];
+  __shared__ double red[32][9];
+  const int t = threadIdx.x;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+  cov_compile(&cc, spec, theta, jitter, t, 256);
+  for (int e = t; e < 32 * DGP_XS; e += 256) xa[e] = XwA[(size_t)r0 * DGP_XS + e];
+  for (int e = t; e < 128 * DGP_XS; e += 256) xb[e] = XwB[(size_t)c0 * DGP_XS + e];
+  __syncthreads();
+  const int lc = t & 127, half = t >> 7;  // thread: column lc, rows half*16 .. +16
+  const int gc = c0 + lc;
+  const double vj = (vec != nullptr) ? vec[gc] : 0.0;
+  for (int rr = 0; rr < 16; rr++) {
+    const int lr = half * 16 + rr, gr = r0 + lr;
+    double v;
+    if (gr < na && gc < nb_) {
+      v = cov_entry(&cc, xa + lr * DGP_XS, xb + lc * DGP_XS);
+      if (diag_noise && gr == gc) v += noise[gr] + cc.extra_noise;
+    } else {
+      v = (ident_pad && gr == gc) ? 1.0 : 0.0;
+    }
+    if (out != nullptr) out[(size_t)gr * ld + gc] = v;
+    if (dot != nullptr) {
+      double s = v * vj;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if ((t & 31) == 0) red[lr][(t >> 5) & 3] = s;
+    }
+  }
+  if (dot != nullptr) {
+    __syncthreads();
+    if (t < 32) dot[(size_t)blockIdx.y * dot_ld + r0 + t] = (red[t][0] + red[t][1]) + (red[t][2] + red[t][3]);
+  }
+}
+
+// ------------------------------------------------------------------ diagonal block: L, L^-1, L^-T
+// One CTA factors the 128x128 diagonal block A_ss = L L^T and, by running the same right-looking
+// elimination on the identity ("augmented rows"), obtains Y = L^-T: rows of Y are forward-substituted
+// exactly like the rows below the diagonal block.  L lives in the lower triangle of As, Y in its strict
+// upper triangle, diag(Y) = 1 / diag(L) in rd.  Outputs: L -> Lblk (zeros above the diagonal),
+// Y -> Ublk (upper), Y^T = L^-1 -> DIblk (lower).  logdet += sum log L_ii; first bad pivot -> info.
+constexpr int PF_THREADS = 256;
+constexpr int PF_AS = 129;  // row stride of As
+constexpr int PF_PN = 33;   // row stride of the 32-column panel scratch
+constexpr int PF_SMEM = (128 * PF_AS + 256 * PF_PN + 128) * 8;
+
+template <int REM>
+__device__ __forceinline__ void potf2_trailing(double* As, const double* Pn, int o, int tid) {
+  constexpr int NC = REM / 8;  // columns per thread
+  const int rg = tid >> 3, cg = tid & 7;
+  double acc[4][NC];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < NC; b++) acc[a][b] = 0.0;
+  int vrow[4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int row = rg + 32 * a;
+    vrow[a] = (row < o + 32) ? 128 + row : row;
+  }
+#pragma unroll 4
+  for (int k = 0; k < 32; k++) {
+    double rv[4], cv[NC];
+#pragma unroll
+    for (int a = 0; a < 4; a++) rv[a] = Pn[vrow[a] * PF_PN + k];
+#pragma unroll
+    for (int b = 0; b < NC; b++) cv[b] = Pn[(o + 32 + cg + 8 * b) * PF_PN + k];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < NC; b++) acc[a][b] = fma(rv[a], cv[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int row = rg + 32 * a;
+#pragma unroll
+    for (int b = 0; b < NC; b++) {
+      const int j = o + 32 + cg + 8 * b;
+      if (row < o + 32 || j <= row) As[row * PF_AS + j] -= acc[a][b];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 1)
+k_potf2(const double* __restrict__ Ablk, double* __restrict__ Lblk, double* __restrict__ Ublk, long long ld,
+        double* __restrict__ DIblk, double* __restrict__ scal, int base) {
+  extern __shared__ double pf_smem[];
+  double* As = pf_smem;
+  double* Pn = As + 128 * PF_AS;
+  double* rd = Pn + 256 * PF_PN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int e = tid; e < 128 * 128; e += PF_THREADS) {
+    const int r = e >> 7, c = e & 127;
+    As[r * PF_AS + c] = (c <= r) ? Ablk[(size_t)r * ld + c] : 0.0;
+  }
+  __syncthreads();
+
+  for (int kb = 0; kb < 4; kb++) {
+    const int o = 32 * kb;
+    // (1) 32x32 diagonal sub-block, one warp, rows in registers
+    if (warp == 0) {
+      double a[32];
+#pragma unroll
+      for (int c = 0; c < 32; c++) a[c] = As[(o + lane) * PF_AS + o + c];
+      double myinv = 0.0;
+#pragma unroll
+      for (int c = 0; c < 32; c++) {
+        const double d = __shfl_sync(0xffffffffu, a[c], c);
+        if (!(d > 0.0) && lane == 0 && scal[SC_INFO] == 0.0) scal[SC_INFO] = (double)(base + o + c + 1);
+        const double l = sqrt(d);
+        const double inv = 1.0 / l;
+        if (lane == c) { a[c] = l; myinv = inv; }
+        if (lane > c) a[c] *= inv;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 32; c2++) {
+          const double v = __shfl_sync(0xffffffffu, a[c], c2);
+          a[c2] = fma(-a[c], v, a[c2]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; c++)
+        if (c <= lane) As[(o + lane) * PF_AS + o + c] = a[c];
+      rd[o + lane] = myinv;
+    }
+    __syncthreads();
+    // (2) forward substitution of the 32-column panel: thread t owns row t, which is either a row of A
+    // below the diagonal block (t >= o + 32) or a row of Y = L^-T (t < o + 32)
+    if (tid < 128) {
+      const int t = tid;
+      double x[32];
+      if (t >= o + 32 || t < o) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) x[c] = As[t * PF_AS + o + c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c++) x[c] = (c == t - o) ? 1.0 : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < 32; c++) {
+        x[c] *= rd[o + c];
+#pragma unroll
+        for (int c2 = c + 1; c2 < 32; c2++) x[c2] = fma(-x[c], As[(o + c2) * PF_AS + o + c], x[c2]);
+      }
+      const int v = (t >= o + 32) ? t : 128 + t;
+#pragma unroll
+      for (int c = 0; c < 32; c++) {
+        Pn[v * PF_PN + c] = x[c];
+        if (t >= o + 32 || o + c > t) As[t * PF_AS + o + c] = x[c];
+      }
+    }
+    __syncthreads();
+    // (3) rank-32 update of the remaining columns, rows of A (lower part) and rows of Y alike
+    if (kb == 0) potf2_trailing<96>(As, Pn, o, tid);
+    else if (kb == 1) potf2_trailing<64>(As, Pn, o, tid);
+    else if (kb == 2) potf2_trailing<32>(As, Pn, o, tid);
+    __syncthreads();
+  }
+
+  for (int e = tid; e < 128 * 128; e += PF_THREADS) {
+    const int r = e >> 7, c = e & 127;
+    const double lv = As[r * PF_AS + c];
+    Lblk[(size_t)r * ld + c] = (c <= r) ? lv : 0.0;
+    Ublk[(size_t)r * ld + c] = (c > r) ? lv : (c == r ? rd[r] : 0.0);
+    DIblk[r * 128 + c] = (c < r) ? As[c * PF_AS + r] : (c == r ? rd[r] : 0.0);
+  }
+  if (warp == 0) {
+    double s = 0.0;
+    for (int i = lane; i < 128; i += 32) s += log(As[i * PF_AS + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) scal[SC_LOGDET] += s;
+  }
+}
+
+// ------------------------------------------------------------------ forward substitution step
+// z_s = Linv_s r_s ; r_i -= L[i, s] z_s for block rows i > s.  grid = nb - s, block = 256.
+__global__ void __launch_bounds__(256)
+k_fwd_step(const double* __restrict__ L, long long ld, const double* __restrict__ DI, double* __restrict__ r,
+           double* __restrict__ z, int s) {
+  __shared__ double rs[128];
+  __shared__ double zs[128];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 128) rs[tid] = r[s * 128 + tid];
+  __syncthreads();
+  const double* D = DI + (size_t)s * 128 * 128;
+  for (int row = warp; row < 128; row += 8) {
+    double acc = 0.0;
+    for (int k = lane; k <= row; k += 32) acc = fma(D[row * 128 + k], rs[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) zs[row] = acc;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (tid < 128) z[s * 128 + tid] = zs[tid];
+    return;
+  }
+  const int i = s + blockIdx.x;
+  for (int row = warp; row < 128; row += 8) {
+    const double* lp = L + (size_t)(i * 128 + row) * ld + s * 128;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = lane; k < 128; k += 32) acc = fma(lp[k], zs[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) r[i * 128 + row] -= acc;
+  }
+}
+
+// ------------------------------------------------------------------ alpha = U z  (U = L^-T upper triangular)
+// one warp per row, grid = npad / 8, block = 256
+__global__ void __launch_bounds__(256)
+k_upper_gemv(const double* __restrict__ U, long long ld, const double* __restrict__ z, double* __restrict__ out, int npad) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= npad) return;
+  const double* up = U + (size_t)row * ld;
+  double a0 = 0.0, a1 = 0.0;
+  int k = (row & ~31) + lane;
+  for (; k + 32 < npad; k += 64) {
+    a0 = fma(up[k], z[k], a0);
+    a1 = fma(up[k + 32], z[k + 32], a1);
+  }
+  if (k < npad) a0 = fma(up[k], z[k], a0);
+  double acc = a0 + a1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = acc;
+}
+
+// ------------------------------------------------------------------ T = U^T (lower), 32x32 tiles through smem
+// grid = (npad/32, npad/32).  Source tiles on/above the diagonal (bx >= by) are transposed into the lower
+// triangle of T; T tiles above the diagonal but inside a diagonal 128-block are zeroed, because the
+// variance GEMM reads whole 64-column k-blocks of T.
+__global__ void __launch_bounds__(256)
+k_transpose_upper(const double* __restrict__ U, double* __restrict__ T, long long ld) {
+  __shared__ double tile[32][33];
+  const int bx = blockIdx.x, by = blockIdx.y;  // source tile (row block by, col block bx)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (bx < by) {
+    if ((bx >> 2) == (by >> 2))
+      for (int r = ty; r < 32; r += 8) T[(size_t)(bx * 32 + r) * ld + by * 32 + tx] = 0.0;
+    return;
+  }
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = U[(size_t)(by * 32 + r) * ld + bx * 32 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) T[(size_t)(bx * 32 + r) * ld + by * 32 + tx] = tile[tx][r];
+}
+
+// ------------------------------------------------------------------ final reductions (deterministic order)
+// block b < ntheta: grad[b] = sum_tiles part[tile][b] (+ mean-parameter terms -J' alpha)
+// block ntheta:     quad = z'z ; nlml = 1/2 quad + logdet + n/2 log 2 pi
+__global__ void __launch_bounds__(256)
+k_finish(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta, const double* __restrict__ part,
+         int ntiles, const double* __restrict__ z, const double* __restrict__ alpha, const double* __restrict__ X,
+         int n, int npad, double* __restrict__ scal, int want_grad) {
+  __shared__ double red[256];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  double s = 0.0;
+  if (b == spec.ntheta) {
+    for (int i = tid; i < npad; i += 256) s = fma(z[i], z[i], s);
+  } else if (want_grad) {
+    for (int t = tid; t < ntiles; t += 256) s += part[(size_t)t * DGP_MAX_THETA + b];
+    int mk = -1;
+    for (int k = 0; k < 3; k++)
+      if ((spec.mean_kind == DGP_MEAN_CONST && k == 0 && spec.mean_theta[0] == b) ||
+          (spec.mean_kind == DGP_MEAN_POWERLAW && spec.mean_theta[k] == b)) mk = k;
+    if (mk >= 0) {
+      double pb = 0.0, pc = 0.0;
+      if (spec.mean_kind == DGP_MEAN_POWERLAW) { pb = theta[spec.mean_theta[1]]; pc = theta[spec.mean_theta[2]]; }
+      for (int i = tid; i < n; i += 256) {
+        double j = 1.0;  // d mean / d param
+        if (spec.mean_kind == DGP_MEAN_POWERLAW && mk > 0) {
+          const double u = X[(size_t)i * spec.ndim + spec.mean_col] - pc;
+          j = (mk == 1) ? log(u) : -pb / u;
+        }
+        s = fma(-alpha[i], j, s);
+      }
+    }
+  }
+  red[tid] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (b == spec.ntheta) {
+      scal[SC_QUAD] = red[0];
+      scal[SC_NLML] = 0.5 * red[0] + scal[SC_LOGDET] + 0.5 * (double)n * 1.8378770664093453;
+    } else {
+      scal[SC_GRAD + b] = want_grad ? red[0] : 0.0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ prediction reductions
+// mu[i] = mean[i] + sum_cb dot[cb][i] ;  var[i] = k(x*_i, x*_i) - sum_cb vpart[cb][i]
+__global__ void __launch_bounds__(256)
+k_pred_finish(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta,
+              const double* __restrict__ Xws, const double* __restrict__ mean, const double* __restrict__ dot,
+              int ndot, const double* __restrict__ vpart, int nvpart, int ldp, int m, double* __restrict__ mu,
+              double* __restrict__ var) {
+  __shared__ CovC cc;
+  cov_compile(&cc, spec, theta, 0.0, threadIdx.x, 256);
+  __syncthreads();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  double s = mean[i];
+  for (int b = 0; b < ndot; b++) s += dot[(size_t)b * ldp + i];
+  mu[i] = s;
+  if (var != nullptr) {
+    double xi[DGP_XS];
+#pragma unroll
+    for (int c = 0; c < DGP_XS; c++) xi[c] = Xws[(size_t)i * DGP_XS + c];
+    double v = 0.0;
+    for (int b = 0; b < nvpart; b++) v += vpart[(size_t)b * ldp + i];
+    var[i] = cov_entry(&cc, xi, xi) - v;
+  }
+}
+
+}  // namespace dgp

@@ -1,0 +1,94 @@
+"""Covariance / mean / likelihood definitions of the reference's two model packages, restated as
+CovSpec trees for the CUDA tile generator.
+
+  loadest_spec  <- src/loadest_gp/models/gpytorch.py:48-128  (ExactGPModel: seasonal + covariates + residual,
+                   ConstantMean, fixed noise 0.1**2, no learned noise; cov_trend is defined there but unused)
+  rating_spec   <- src/rating_gp/models/gpytorch.py:64-79,205-372 and src/rating_gp/models/kernels.py:242-382
+                   (sigmoid-gated shift kernels, inverted-gate bend kernel, base + periodic, all on log-warped
+                   stage; power-law mean; fixed per-point noise + learned homoskedastic noise)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+from .spec import CovSpec, Factor
+
+LOADEST_FIXED_NOISE = 0.1 ** 2
+RATING_DEFAULT_NOISE = 0.1 ** 2
+RATING_SHARPNESS = 20.0     # SigmoidKernel.a, src/rating_gp/models/kernels.py:271
+RATING_LOG_EPS = 1e-6       # LogWarpKernel eps, src/rating_gp/models/kernels.py:368
+RATING_MIN_NOISE = 1e-4     # GreaterThan(1e-4) default of gpytorch's HomoskedasticNoise
+
+
+def loadest_spec(ndim: int = 2) -> CovSpec:
+    """x = (time, covariates...).  K = s1 Per(t) M52(t) + s2 RBF_ard(q) + s3 M32_ard(t, q)."""
+    if ndim < 2:
+        raise ValueError("loadest-gp needs time + at least one covariate")
+    s = CovSpec(ndim=ndim)
+    cols = [s.col_copy(d) for d in range(ndim)]
+    c = s.param("mean.constant", ("none",), None)
+    s1 = s.param("seasonal.outputscale", prior=("halfnormal", 1.0))
+    lam = s.param("seasonal.periodic.lengthscale")
+    per = s.param("seasonal.periodic.period_length", prior=("normal", 1.0, 0.01))
+    l1 = s.param("seasonal.matern52.lengthscale")
+    s2 = s.param("covariates.outputscale", prior=("halfnormal", 2.0))
+    l2 = [s.param(f"covariates.rbf.lengthscale.{d}", prior=("gamma", 2.0, 3.0)) for d in range(ndim - 1)]
+    s3 = s.param("residual.outputscale", prior=("halfnormal", 0.2))
+    l3 = [s.param(f"residual.matern32.lengthscale.{d}", prior=("gamma", 2.0, 10.0)) for d in range(ndim)]
+    s.term(s1, [Factor(capi.PERIODIC, [cols[0]], [lam], per), Factor(capi.MATERN52, [cols[0]], [l1])])
+    s.term(s2, [Factor(capi.RBF, cols[1:], l2)])
+    s.term(s3, [Factor(capi.MATERN32, cols, l3)])
+    s.mean_kind, s.mean_theta = capi.MEAN_CONST, (c,)
+    return s
+
+
+def rating_spec(b_lo: float, b_hi: float, gate_b_init: Optional[float] = None, pl_a: float = 0.0, pl_b: float = 1.3,
+                pl_c: float = 0.5) -> CovSpec:
+    """x = (time, stage in [1, 2]).  b_lo / b_hi: 10 % / 90 % stage quantiles bounding the switch point
+    (src/rating_gp/models/gpytorch.py:221-235).  The reference draws gate_b, pl_a, pl_b, pl_c at random
+    (gpytorch.py:31-36, kernels.py:276); callers pass the draws, defaults are deterministic."""
+    s = CovSpec(ndim=2)
+    t = s.col_copy(0)
+    hw = s.col_log(1, RATING_LOG_EPS)
+    a = s.param("powerlaw.a", ("none",), init_raw=pl_a)
+    b = s.param("powerlaw.b", ("none",), init_raw=pl_b)
+    c = s.param("powerlaw.c", ("none",), init_raw=pl_c)
+    noise = s.param("likelihood.second_noise", ("greater_than", RATING_MIN_NOISE), ("halfnormal", 0.03), group="likelihood")
+    gb = s.param("sigmoid.b", ("interval", float(b_lo), float(b_hi)), ("normal", 0.0, 1.0))
+    if gate_b_init is None:
+        gate_b_init = 0.5 * (b_lo + b_hi)
+    from .spec import inverse_transform
+    s.params[gb].init_raw = inverse_transform(s.params[gb], gate_b_init)
+    g = s.col_gate(1, RATING_SHARPNESS, gb)
+
+    def shift(name, eta, tp, sp):
+        sc = s.param(f"{name}.outputscale", prior=("halfnormal", eta))
+        lh = s.param(f"{name}.stage_matern52.lengthscale", prior=("gamma",) + sp)
+        lt = s.param(f"{name}.time_matern32.lengthscale", prior=("gamma",) + tp)
+        s.term(sc, [Factor(capi.MATERN52, [hw], [lh]), Factor(capi.MATERN32, [t], [lt])], capi.GATE_SIGMOID, g)
+
+    shift("shiftA", 0.6, (3.0, 1.0), (3.0, 2.0))
+    shift("shiftB", 0.3, (1.0, 7.0), (3.0, 1.0))
+    sc = s.param("bend.outputscale", prior=("halfnormal", 0.6))
+    lh = s.param("bend.stage_matern52.lengthscale", prior=("gamma", 3.0, 2.0))
+    lt = s.param("bend.time_matern52.lengthscale", prior=("gamma", 4.0, 2.0))
+    s.term(sc, [Factor(capi.MATERN52, [hw], [lh]), Factor(capi.MATERN52, [t], [lt])], capi.GATE_INV_SIGMOID, g)
+    sc = s.param("base.outputscale", prior=("halfnormal", 1.0))
+    lb = s.param("base.stage_matern52.lengthscale", prior=("gamma", 4.0, 4.0))
+    s.term(sc, [Factor(capi.MATERN52, [hw], [lb])])
+    sc = s.param("periodic.outputscale", prior=("halfnormal", 0.2))
+    pp = s.param("periodic.period_length", prior=("normal", 1.0, 0.05))
+    pl = s.param("periodic.lengthscale", prior=("gamma", 9.0, 10.0))
+    pm = s.param("periodic.time_matern52.lengthscale")
+    s.term(sc, [Factor(capi.PERIODIC, [t], [pl], pp), Factor(capi.MATERN52, [t], [pm])])
+    s.mean_kind, s.mean_col, s.mean_theta = capi.MEAN_POWERLAW, 1, (a, b, c)
+    s.noise_theta = noise
+    return s
+
+
+def stage_quantile_bounds(stage: np.ndarray):
+    """np.quantile(stage, 0.10 / 0.90) as at src/rating_gp/models/gpytorch.py:221-223."""
+    return float(np.quantile(stage, 0.10)), float(np.quantile(stage, 0.90))

@@ -1,0 +1,193 @@
+"""Host-side covariance specification: the tagged tree the CUDA tile generator consumes.
+
+A model is a sum of terms; a term is  outputscale x optional sigmoid gate x product of stationary
+factors (RBF / Matern-3/2 / Matern-5/2 / periodic) on selected columns of a per-point feature
+table (raw, log-warped or gate columns).  This is exactly the family the reference's models span
+(src/loadest_gp/models/gpytorch.py:61-128, src/rating_gp/models/gpytorch.py:205-372,
+src/rating_gp/models/kernels.py:242-382).  Hyper-parameters carry GPyTorch's constraint /
+prior / initial-value semantics; the O(P) host math (constraint transforms,
+priors, their chain rule) is done with torch on the CPU, the O(n^3) math never is.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import capi
+
+LOG2PI = math.log(2.0 * math.pi)
+
+
+@dataclass
+class Param:
+    name: str
+    constraint: Tuple = ("positive",)      # ("positive",) | ("greater_than", lb) | ("interval", lo, hi) | ("none",)
+    prior: Optional[Tuple] = None          # ("halfnormal", s) | ("normal", mu, s) | ("gamma", conc, rate)
+    init_raw: float = 0.0
+    group: str = "model"                   # "model" or "likelihood" (state-dict split, engines/gpytorch.py:149-150)
+
+
+def transform(p: Param, raw: torch.Tensor) -> torch.Tensor:
+    c = p.constraint
+    if c[0] == "positive":
+        return torch.nn.functional.softplus(raw)
+    if c[0] == "greater_than":
+        return torch.nn.functional.softplus(raw) + c[1]
+    if c[0] == "interval":
+        return c[1] + (c[2] - c[1]) * torch.sigmoid(raw)
+    return raw
+
+
+def inverse_transform(p: Param, value: float) -> float:
+    c = p.constraint
+    v = float(value)
+    if c[0] == "positive":
+        return v + math.log(-math.expm1(-v))
+    if c[0] == "greater_than":
+        v -= c[1]
+        return v + math.log(-math.expm1(-v))
+    if c[0] == "interval":
+        u = (v - c[1]) / (c[2] - c[1])
+        return math.log(u) - math.log1p(-u)
+    return v
+
+
+def log_prior(p: Param, x: torch.Tensor) -> torch.Tensor:
+    pr = p.prior
+    if pr is None:
+        return x.new_zeros(())
+    if pr[0] == "halfnormal":
+        s = pr[1]
+        return math.log(2.0) - 0.5 * LOG2PI - math.log(s) - x * x / (2.0 * s * s)
+    if pr[0] == "normal":
+        mu, s = pr[1], pr[2]
+        return -0.5 * LOG2PI - math.log(s) - (x - mu) ** 2 / (2.0 * s * s)
+    if pr[0] == "gamma":
+        a, b = pr[1], pr[2]
+        return a * math.log(b) + (a - 1.0) * torch.log(x) - b * x - math.lgamma(a)
+    raise ValueError(pr)
+
+
+@dataclass
+class Factor:
+    kind: int
+    cols: Sequence[int]
+    ls: Sequence[int]            # theta indices, one per col
+    period: int = -1
+
+
+@dataclass
+class Term:
+    scale: int
+    factors: List[Factor]
+    gate: int = capi.GATE_NONE
+    gate_col: int = 0
+
+
+@dataclass
+class CovSpec:
+    """Builder of a dgp_spec plus the parameter table that goes with it."""
+
+    ndim: int
+    params: List[Param] = field(default_factory=list)
+    cols: List[Tuple[int, int, int, float]] = field(default_factory=list)  # (kind, src, theta, aux)
+    terms: List[Term] = field(default_factory=list)
+    mean_kind: int = capi.MEAN_ZERO
+    mean_col: int = 0
+    mean_theta: Tuple[int, ...] = ()
+    noise_theta: int = -1
+
+    def param(self, name, constraint=("positive",), prior=None, init_raw=0.0, group="model") -> int:
+        self.params.append(Param(name, tuple(constraint), prior, float(init_raw), group))
+        return len(self.params) - 1
+
+    def col_copy(self, src: int) -> int:
+        self.cols.append((capi.COL_COPY, src, -1, 0.0))
+        return len(self.cols) - 1
+
+    def col_log(self, src: int, eps: float) -> int:
+        self.cols.append((capi.COL_LOG, src, -1, float(eps)))
+        return len(self.cols) - 1
+
+    def col_gate(self, src: int, sharpness: float, theta: int) -> int:
+        self.cols.append((capi.COL_GATE, src, theta, float(sharpness)))
+        return len(self.cols) - 1
+
+    def term(self, scale: int, factors: List[Factor], gate: int = capi.GATE_NONE, gate_col: int = 0):
+        self.terms.append(Term(scale, factors, gate, gate_col))
+
+    @property
+    def ntheta(self) -> int:
+        return len(self.params)
+
+    def index(self, name: str) -> int:
+        for i, p in enumerate(self.params):
+            if p.name == name:
+                return i
+        raise KeyError(name)
+
+    def to_c(self) -> capi.DgpSpec:
+        if len(self.terms) > capi.MAX_TERMS or len(self.cols) > capi.MAX_COLS or self.ntheta > capi.MAX_THETA:
+            raise ValueError("covariance spec exceeds libdgp limits")
+        s = capi.DgpSpec()
+        s.abi = capi.ABI_VERSION
+        s.ndim, s.ncols, s.nterms, s.ntheta = self.ndim, len(self.cols), len(self.terms), self.ntheta
+        s.noise_theta = self.noise_theta
+        s.mean_kind, s.mean_col = self.mean_kind, self.mean_col
+        for k in range(4):
+            s.mean_theta[k] = self.mean_theta[k] if k < len(self.mean_theta) else -1
+        for i, (kind, src, th, aux) in enumerate(self.cols):
+            s.col[i].kind, s.col[i].src, s.col[i].theta, s.col[i].aux = kind, src, th, aux
+        for i, t in enumerate(self.terms):
+            ct = s.term[i]
+            ct.scale, ct.gate, ct.gate_col, ct.nfactors = t.scale, t.gate, t.gate_col, len(t.factors)
+            if len(t.factors) > capi.MAX_FACTORS:
+                raise ValueError("too many factors in a term")
+            for j, f in enumerate(t.factors):
+                cf = ct.factor[j]
+                cf.kind, cf.ndims, cf.period = f.kind, len(f.cols), f.period
+                if len(f.cols) > capi.MAX_FDIMS or len(f.cols) != len(f.ls):
+                    raise ValueError("bad factor dims")
+                for d in range(capi.MAX_FDIMS):
+                    cf.col[d] = f.cols[d] if d < len(f.cols) else 0
+                    cf.ls[d] = f.ls[d] if d < len(f.cols) else -1
+        return s
+
+
+class GPModule(torch.nn.Module):
+    """Raw hyper-parameters of one model as float64 torch Parameters on the CPU (state_dict-able like
+    the gpytorch module the reference checkpoints at discontinuum/engines/gpytorch.py:147-160)."""
+
+    def __init__(self, spec: CovSpec):
+        super().__init__()
+        self.spec = spec
+        self.raw = torch.nn.ParameterDict(
+            {p.name.replace(".", "__"): torch.nn.Parameter(torch.tensor([p.init_raw], dtype=torch.float64)) for p in spec.params})
+        self.training_mode = True
+
+    def raw_list(self) -> List[torch.nn.Parameter]:
+        return [self.raw[p.name.replace(".", "__")] for p in self.spec.params]
+
+    def natural(self) -> torch.Tensor:
+        """Differentiable vector of natural parameter values, in theta order."""
+        return torch.cat([transform(p, r) for p, r in zip(self.spec.params, self.raw_list())])
+
+    def log_prior(self, nat: torch.Tensor) -> torch.Tensor:
+        total = nat.new_zeros(())
+        for i, p in enumerate(self.spec.params):
+            if p.prior is not None:
+                total = total + log_prior(p, nat[i])
+        return total
+
+    def set_natural(self, name: str, value: float):
+        i = self.spec.index(name)
+        with torch.no_grad():
+            self.raw_list()[i].fill_(inverse_transform(self.spec.params[i], value))
+
+    def natural_dict(self) -> Dict[str, float]:
+        with torch.no_grad():
+            nat = self.natural()
+        return {p.name: float(nat[i]) for i, p in enumerate(self.spec.params)}

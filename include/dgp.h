@@ -1,0 +1,158 @@
+/* dgp.h -- C ABI of libdgp.so, the B200 exact-GP engine behind discontinuum's Marginal* engines.
+ *
+ * The reference (thodson-usgs/discontinuum) has NO FFI: its hot path is gpytorch/linear_operator
+ * calls made from Python.  Each entry point below replaces the library calls made at the cited
+ * reference lines (paths relative to the reference's src/):
+ *
+ *   dgp_set_train      <- tensors built in MarginalGPyTorch.fit, discontinuum/engines/gpytorch.py:219-235
+ *                         and the model's build_model (loadest_gp/models/gpytorch.py:48-58,
+ *                         rating_gp/models/gpytorch.py:64-79)
+ *   dgp_covmat         <- ExactGPModel.forward -> covar_module(x)  (loadest_gp/models/gpytorch.py:71-76,
+ *                         rating_gp/models/gpytorch.py:256-265, rating_gp/models/kernels.py:242-382)
+ *   dgp_nlml           <- mll(output, train_y), discontinuum/engines/gpytorch.py:318,353
+ *   dgp_nlml_grad      <- the same + objective.backward(), discontinuum/engines/gpytorch.py:353,384
+ *   dgp_factorize      <- the eval-mode caches GPyTorch builds on the first prediction
+ *                         (discontinuum/engines/gpytorch.py:618-622)
+ *   dgp_predict        <- MarginalGPyTorch.__gpytorch_predict, discontinuum/engines/gpytorch.py:599-626
+ *   dgp_sample         <- f_preds.sample(...), discontinuum/engines/gpytorch.py:578-580
+ *
+ * Conventions: plain pointers and sizes only.  All matrices are float64, row-major.  Every call
+ * returns an int status: 0 = ok; > 0 = LAPACK-style info (1-based index of the first non-positive
+ * pivot met by the Cholesky factorisation); < 0 = bad argument or CUDA error, text available from
+ * dgp_last_error().  A handle owns one CUDA stream-ordered workspace sized at dgp_create; it is
+ * not thread-safe, use one handle per host thread / per concurrent site.  There is no CPU
+ * fallback: without a CUDA device dgp_create fails.
+ */
+#ifndef DGP_H
+#define DGP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGP_ABI_VERSION 1
+
+#define DGP_MAX_TERMS 8    /* additive terms of the covariance                        */
+#define DGP_MAX_FACTORS 3  /* stationary factors multiplied inside one term           */
+#define DGP_MAX_FDIMS 4    /* ARD dimensions of one factor                            */
+#define DGP_MAX_COLS 8     /* columns of the per-point feature table                  */
+#define DGP_MAX_THETA 48   /* natural hyper-parameters (kernel + mean + learned noise) */
+
+/* stationary factor kinds (GPyTorch semantics) */
+enum { DGP_RBF = 0, DGP_MATERN32 = 1, DGP_MATERN52 = 2, DGP_PERIODIC = 3 };
+/* multiplicative gate of a term: g(h)g(h') or (1-g(h))(1-g(h')), g = 1/(1+exp(a(h-b))) */
+enum { DGP_GATE_NONE = 0, DGP_GATE_SIGMOID = 1, DGP_GATE_INV_SIGMOID = 2 };
+/* feature-table column kinds */
+enum { DGP_COL_COPY = 0, DGP_COL_LOG = 1 /* log(x + eps) */, DGP_COL_GATE = 2 /* g(x; a, theta[b]) */ };
+/* mean functions */
+enum { DGP_MEAN_ZERO = 0, DGP_MEAN_CONST = 1, DGP_MEAN_POWERLAW = 2 /* a + b log(x - c) */ };
+
+typedef struct {
+  int32_t kind;                 /* DGP_COL_*                                          */
+  int32_t src;                  /* source column of X                                 */
+  int32_t theta;                /* theta index of the gate switch point (GATE), else -1 */
+  int32_t pad_;
+  double aux;                   /* eps (LOG) or sharpness a (GATE)                    */
+} dgp_col;
+
+typedef struct {
+  int32_t kind;                 /* DGP_RBF ... DGP_PERIODIC                           */
+  int32_t ndims;                /* active dims (PERIODIC: 1)                          */
+  int32_t col[DGP_MAX_FDIMS];   /* feature-table columns                              */
+  int32_t ls[DGP_MAX_FDIMS];    /* theta index of the lengthscale of each dim
+                                   (PERIODIC: ls[0] is GPyTorch's un-squared lengthscale) */
+  int32_t period;               /* theta index of the period (PERIODIC) else -1       */
+  int32_t pad_;
+} dgp_factor;
+
+typedef struct {
+  int32_t scale;                /* theta index of the outputscale, -1 -> 1            */
+  int32_t gate;                 /* DGP_GATE_*                                         */
+  int32_t gate_col;             /* feature-table column holding g (kind DGP_COL_GATE) */
+  int32_t nfactors;
+  dgp_factor factor[DGP_MAX_FACTORS];
+} dgp_term;
+
+typedef struct {
+  int32_t abi;                  /* DGP_ABI_VERSION                                    */
+  int32_t ndim;                 /* columns of X                                       */
+  int32_t ncols;                /* feature-table columns                              */
+  int32_t nterms;
+  int32_t ntheta;               /* length of theta / grad                             */
+  int32_t noise_theta;          /* theta index of the learned homoskedastic noise, -1 = none */
+  int32_t mean_kind;            /* DGP_MEAN_*                                         */
+  int32_t mean_col;             /* X column the mean reads (POWERLAW)                 */
+  int32_t mean_theta[4];        /* theta indices: CONST {c}; POWERLAW {a, b, c}       */
+  dgp_col col[DGP_MAX_COLS];
+  dgp_term term[DGP_MAX_TERMS];
+} dgp_spec;
+
+typedef struct dgp_handle_s* dgp_handle;
+
+/* Create an engine on CUDA device `device` for up to max_n training points and prediction chunks
+ * of up to max_m points (0 -> default).  Allocates every workspace (3 padded n x n float64 panels +
+ * prediction chunk); later calls allocate nothing.  stream: a cudaStream_t to run on, or NULL to
+ * let the handle create its own non-blocking stream. */
+int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream);
+int dgp_destroy(dgp_handle h);
+const char* dgp_last_error(dgp_handle h); /* h may be NULL: error of a failed dgp_create */
+int dgp_abi_version(void);
+size_t dgp_workspace_bytes(int max_n, int max_m);
+
+/* Training set of one site.  X[n, ndim], y[n], noise[n] (fixed per-point noise variances).
+ * on_device != 0: pointers are device memory on the handle's device; else host memory. */
+int dgp_set_train(dgp_handle h, const dgp_spec* spec, const double* X, const double* y,
+                  const double* noise, int n, int on_device);
+
+/* Dense K(X, X; theta) WITHOUT noise, n x n row-major, into K_out (parity/debug entry). */
+int dgp_covmat(dgp_handle h, const double* theta, double* K_out, int out_on_device);
+/* Cross covariance K(Xs, X; theta), m x n row-major (parity/debug entry). */
+int dgp_cross_covmat(dgp_handle h, const double* theta, const double* Xs, int m, int xs_on_device,
+                     double* K_out, int out_on_device);
+
+/* NLML = 1/2 r'Ky^-1 r + sum log L_ii + n/2 log 2pi with Ky = K + diag(noise) + (theta[noise_theta]
+ * + jitter) I and r = y - mean(X).  theta: host array [ntheta] of NATURAL parameter values. */
+int dgp_nlml(dgp_handle h, const double* theta, double jitter, double* nlml_out);
+
+/* NLML and its gradient w.r.t. every natural parameter (kernel, mean, learned noise):
+ * -1/2 tr((alpha alpha' - Ky^-1) dK/dtheta), -J'alpha, -1/2 tr W.  grad_out: host [ntheta]. */
+int dgp_nlml_grad(dgp_handle h, const double* theta, double jitter, double* nlml_out, double* grad_out);
+
+/* Asynchronous pair for multi-site overlap: launch enqueues the whole evaluation and the
+ * device-to-host copy of the results on the handle's stream; wait blocks on that stream. */
+int dgp_nlml_grad_launch(dgp_handle h, const double* theta, double jitter);
+int dgp_nlml_grad_wait(dgp_handle h, double* nlml_out, double* grad_out);
+
+/* Factorise at theta and keep L, L^-1 and alpha resident for dgp_predict / dgp_sample. */
+int dgp_factorize(dgp_handle h, const double* theta, double jitter, double* nlml_out);
+
+/* Posterior mean m(x*) + K*x alpha and LATENT variance k** - |L^-1 Kx*|^2 at Xs[m, ndim]
+ * (host adds the likelihood-noise rule and clamp of SURVEY A.5).  var_out may be NULL. */
+int dgp_predict(dgp_handle h, const double* Xs, int m, int on_device, double* mu_out, double* var_out);
+
+/* Joint latent posterior draws out[S, m] = mu* + Z[S, m] Lpost' with Lpost the exact Cholesky
+ * factor of K** - K*x Ky^-1 Kx* (+ jitter I).  Z: caller-supplied standard normals. */
+int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, double jitter,
+               double* out, int on_device);
+
+/* Parity accessors (valid after dgp_nlml* / dgp_factorize): alpha[n]; L[n, n] lower triangular. */
+int dgp_get_alpha(dgp_handle h, double* alpha_out, int out_on_device);
+int dgp_get_chol(dgp_handle h, double* L_out, int out_on_device);
+/* Ky^-1 [n, n] (lower triangle valid), materialised only when debug_kinv was enabled. */
+int dgp_set_debug_kinv(dgp_handle h, int enable);
+int dgp_get_kinv(dgp_handle h, double* Kinv_out, int out_on_device);
+
+/* Counters for bench.py: kernels launched by this handle since creation. */
+long long dgp_launch_count(dgp_handle h);
+/* Device time (ms, CUDA events on the handle's stream) of the last dgp_nlml / dgp_nlml_grad /
+ * dgp_factorize, split as potrf / trtri / lauum+grad / rest. */
+int dgp_last_timing(dgp_handle h, double* ms4);
+int dgp_set_timing(dgp_handle h, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGP_H */
