@@ -63,6 +63,7 @@ _SIGNATURES = [
     ("dgp_get_chol", C.c_int, [_P, _P, C.c_int]),
     ("dgp_set_debug_kinv", C.c_int, [_P, C.c_int]),
     ("dgp_get_kinv", C.c_int, [_P, _P, C.c_int]),
+    ("dgp_gemm_nt", C.c_int, [_P, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("dgp_launch_count", C.c_longlong, [_P]),
     ("dgp_last_timing", C.c_int, [_P, _P]),
     ("dgp_set_timing", C.c_int, [_P, C.c_int]),
@@ -265,6 +266,13 @@ class Engine:
         Ki = np.empty((self.n, self.n))
         self._check(self.lib.dgp_get_kinv(self._h, Ki.ctypes.data, 0), "dgp_get_kinv")
         return Ki
+
+    def gemm_nt(self, A, B, Cm, mode: int = 0):
+        """Cm (=, +=, -=) A @ B.T on CUDA float64 tensors (row-major, contiguous)."""
+        M, K = A.shape
+        N = B.shape[0]
+        self._check(self.lib.dgp_gemm_nt(self._h, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cm.data_ptr(),
+                                         Cm.stride(0), M, N, K, int(mode)), "dgp_gemm_nt")
 
     def set_timing(self, on: bool):
         self._check(self.lib.dgp_set_timing(self._h, 1 if on else 0), "dgp_set_timing")

@@ -104,11 +104,14 @@ template <int INIT, int EPI>
 static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g) {
   if (g.ntiles <= 0) return 0;
   static bool attr_set = false;
+  static int smem_bytes = SM_TOTAL;
   if (!attr_set) {
-    CK(h, cudaFuncSetAttribute(k_gemm<INIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    const char* pad = getenv("DGP_SMEM_PAD");  // experiment knob: extra bytes force 1 CTA / SM
+    if (pad) smem_bytes = SM_TOTAL + atoi(pad);
+    CK(h, cudaFuncSetAttribute(k_gemm<INIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
-  k_gemm<INIT, EPI><<<g.ntiles, GEMM_THREADS, SM_TOTAL, h->stream>>>(a, b, h->spec, g);
+  k_gemm<INIT, EPI><<<g.ntiles, GEMM_THREADS, smem_bytes, h->stream>>>(a, b, h->spec, g);
   h->launches++;
   CK(h, cudaGetLastError());
   return 0;
@@ -526,6 +529,31 @@ int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, do
   (void)Xs; (void)m; (void)Z; (void)S; (void)jitter; (void)out; (void)on_device;
   if (!h) return -1;
   DGP_FAIL(h, -100, "dgp_sample: not implemented yet");
+}
+
+// ------------------------------------------------------------------ generic NT product on the tile engine
+int dgp_gemm_nt(dgp_handle h, const double* A, long long lda, const double* B, long long ldb, double* Cm, long long ldc,
+                int M, int N, int K, int mode) {
+  if (!h) return -1;
+  if (!A || !B || !Cm || M < 128 || N < 64 || K < 16 || M % 128 || N % 64 || K % 16 || lda % 2 || ldb % 2 || ldc % 2)
+    DGP_FAIL(h, -1, "dgp_gemm_nt: M %% 128, N %% 64, K %% 16 and even leading dimensions required");
+  if (mode < -1 || mode > 1) DGP_FAIL(h, -1, "dgp_gemm_nt: mode must be -1, 0 or 1");
+  CK(h, cudaSetDevice(h->device));
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_map(h, &ta, const_cast<double*>(A), M, K, lda))) return rc;
+  if ((rc = make_map(h, &tb, const_cast<double*>(B), N, K, ldb))) return rc;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.mode = M_GENERIC; g.nb = M / 128; g.n = M;
+  g.aux0 = N / 64; g.aux1 = K / 16; g.aux2 = 0;
+  g.ntiles = (M / 128) * (N / 64);
+  g.C = Cm; g.ldc = ldc; g.sign = (mode == -1) ? -1.0 : 1.0;
+  if (mode == 0) rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, ta, tb, g);
+  else rc = launch_gemm<INIT_LOAD, EPI_STORE>(h, ta, tb, g);
+  if (rc) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 // ------------------------------------------------------------------ accessors

@@ -276,6 +276,14 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   for (int it = 0; it < job.nk; it++) {
     const int s = it % STAGES;
     mbar_wait(&full[s], (it / STAGES) & 1);
+    // Release the PREVIOUS stage only now.  Its fragment loads are known to have returned: every DMMA of
+    // that stage was issued (in order, operands scoreboarded) before the loop back-edge.  Releasing at
+    // the end of the stage itself is not safe: the arrive can overtake shared-memory loads still queued
+    // behind the co-resident CTA's global-load burst, and the TMA refill then lands under them.
+    if (it > 0) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[(it - 1) % STAGES]);
+    }
     const uint32_t st = sbase + s * STAGE_BYTES;
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
@@ -292,8 +300,6 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni], a[mi], b[ni]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
   }
 
   // ---- epilogue

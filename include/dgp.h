@@ -145,6 +145,12 @@ int dgp_get_chol(dgp_handle h, double* L_out, int out_on_device);
 int dgp_set_debug_kinv(dgp_handle h, int enable);
 int dgp_get_kinv(dgp_handle h, double* Kinv_out, int out_on_device);
 
+/* Utility: the FP64 tensor-pipe tile engine as a plain product on device pointers,
+ * C[M, N] = A[M, K] B[N, K]' (mode 0), C += A B' (mode 1), C -= A B' (mode -1).
+ * M % 128 == 0, N % 64 == 0, K % 16 == 0; row-major with leading dimensions lda/ldb/ldc. */
+int dgp_gemm_nt(dgp_handle h, const double* A, long long lda, const double* B, long long ldb, double* C,
+                long long ldc, int M, int N, int K, int mode);
+
 /* Counters for bench.py: kernels launched by this handle since creation. */
 long long dgp_launch_count(dgp_handle h);
 /* Device time (ms, CUDA events on the handle's stream) of the last dgp_nlml / dgp_nlml_grad /
