@@ -1,0 +1,263 @@
+"""bench.py -- NLML + hyper-parameter-gradient evaluations per second at n = 16 384 (BASELINE.json metric,
+configs[2]: "loadest-gp large single site n=16k, FP64 Cholesky + hyperparameter gradient, 1xB200").
+
+A step = one evaluation of {NLML, dNLML/dtheta} of the loadest-gp model on one synthetic river-like site.
+  value   : evaluations/s with the training set already resident in HBM (set_train done before timing),
+            timed with CUDA events on the stream the engine launches on.
+  e2e     : the same through the C ABI with HOST buffers every step: dgp_set_train(host X, y, noise)
+            + dgp_nlml_grad(host theta -> host nlml, grad).
+  N > 1   : one process per GPU, every rank evaluates its own site (sites are independent: no data-path
+            collective, "weak" scaling); value = total evaluations / max-over-ranks time.
+  --impl reference : the CPU restatement of the reference's path (oracle, torch float64, all host threads)
+            on a bounded sample of the same workload.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_TRAIN = 16384
+METRIC = "nlml_grad_evals_per_sec_n16k"
+UNIT = "evals/s"
+CPU_SAMPLE_N = 4096
+
+
+def fp64_peak():
+    """FP64 roofline denominator.  MEASURED_PEAKS.json (driver-written) has no FP64 entry, so the figure is
+    this repo's own measurement with the same method (torch.matmul float64 8192^3, tools/fp64_peak.py)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        if "fp64_tflops" in mp:
+            return float(mp["fp64_tflops"]), "MEASURED_PEAKS.json fp64_tflops"
+    except Exception:  # noqa: BLE001
+        pass
+    with open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")) as f:
+        return float(json.load(f)["fp64_tflops"]), "profiles/fp64_peak_r01.json (cuBLAS DGEMM 8192^3 on this pool's B200; MEASURED_PEAKS.json has no fp64 entry)"
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_eval_seconds(n: int, reps: int, warm: int):
+    """Oracle (CPU restatement) NLML+grad at size n: dense covariance build + Cholesky + inverse + closed-form
+    gradient contraction, torch float64 with every host thread."""
+    import torch
+
+    import helpers as H
+    from discontinuum_b200 import synthetic
+    from oracle import gp_oracle as orc
+
+    X, y, noise = synthetic.loadest_site(n, 1000)
+    Xt, yt, nt = torch.tensor(X), torch.tensor(y), torch.tensor(noise)
+    nat = H.loadest_nat_from_theta(H.loadest_theta1())
+    times = []
+    for r in range(warm + reps):
+        t0 = time.perf_counter()
+        orc.nlml_grad_closed_form(orc.loadest_cov, orc.loadest_mean, nat, Xt, yt, nt)
+        dt = time.perf_counter() - t0
+        if r >= warm:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    ns = CPU_SAMPLE_N
+    times, threads = cpu_eval_seconds(ns, args.steps, args.warmup)
+    per = sum(times) / len(times)
+    scale = (N_TRAIN / ns) ** 3
+    value = 1.0 / (per * scale)
+    sample = (f"oracle NLML+grad at n={ns} ({per:.2f} s/eval measured, {threads} torch threads), extrapolated to n={N_TRAIN} "
+              f"by (n/{ns})^3 = {scale:.0f}x")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per * scale * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"loadest-gp single site n={N_TRAIN}, NLML + gradient (10 hyper-parameters)", "cpu_sample_n": ns},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--n", type=int, default=N_TRAIN, help="development only; the judged workload is n=16384")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    import helpers as H
+    from discontinuum_b200 import capi, models, synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n = args.n
+    warm = max(args.warmup, 3)
+    X, y, noise = synthetic.loadest_site(n, 1000 + rank)
+    spec = models.loadest_spec(2)
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = capi.Engine(max_n=n, max_m=256, device=local, stream=stream)
+    eng.set_train(spec.to_c(), X, y, noise)
+    base = H.loadest_theta1()
+    thetas = [base * (1.0 + 1e-3 * k) for k in range(warm + args.steps)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM
+    for k in range(warm):
+        eng.nlml_grad(thetas[k])
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    infos = []
+    for k in range(args.steps):
+        val, grad, info = eng.nlml_grad(thetas[warm + k])
+        infos.append(info)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launches - l0
+    clocks = sampler.stop()
+    if any(infos) or not np.isfinite(val):
+        raise RuntimeError(f"factorisation failed inside the timed region: info={infos} nlml={val}")
+
+    # ---- phase split of one evaluation (CUDA events on the launching stream inside libdgp)
+    eng.set_timing(True)
+    eng.nlml_grad(base)
+    phase = eng.last_timing()
+    eng.set_timing(False)
+
+    # ---- e2e: host buffers through the C ABI every step
+    Xh, yh, nh = np.ascontiguousarray(X), np.ascontiguousarray(y), np.ascontiguousarray(noise)
+    c_spec = spec.to_c()
+    for k in range(2):
+        eng.set_train(c_spec, Xh, yh, nh)
+        eng.nlml_grad(thetas[k])
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for k in range(args.steps):
+        eng.set_train(c_spec, Xh, yh, nh)
+        val2, grad2, info2 = eng.nlml_grad(thetas[warm + k])
+    e3.record()
+    barrier()
+    ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, ms_e2e_max = float(t[0]), float(t[1])
+    value = world * args.steps / (ms_max * 1e-3)
+    e2e_value = world * args.steps / (ms_e2e_max * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = fp64_peak()
+        flop = float(n) ** 3  # n^3/3 POTRF + n^3/3 triangular inverse + n^3/3 LAUUM
+        dev_ms = sum(phase)
+        achieved = flop / (dev_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "dgp::k_gemm (FP64 DMMA tile engine): every launch of one evaluation",
+                "algorithmic_flop_per_eval": flop, "peak_source": "of measured: " + peak_src,
+                "phases_ms": {"potrf": phase[0], "trtri": phase[1], "lauum_grad": phase[2], "rest": phase[3]},
+                "phases_tflops": {"potrf": flop / 3 / phase[0] / 1e9, "trtri": flop / 3 / phase[1] / 1e9,
+                                  "lauum_grad_single_launch": flop / 3 / phase[2] / 1e9}}
+        cpu = None
+        if not args.no_cpu:
+            torch.set_num_threads(os.cpu_count() or 1)
+            times, threads = cpu_eval_seconds(CPU_SAMPLE_N, 2, 1)
+            per = sum(times) / len(times)
+            scale = (n / CPU_SAMPLE_N) ** 3
+            cpu = {"value": 1.0 / (per * scale), "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"oracle NLML+grad at n={CPU_SAMPLE_N}: {per:.2f} s/eval on {threads} threads, extrapolated to n={n} by (n/{CPU_SAMPLE_N})^3"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"loadest-gp single site n={n}, NLML + gradient (10 hyper-parameters), one site per GPU",
+                           "l2": "working set 3 x n^2 x 8 B = 6.4 GB per site, far larger than the 126 MB L2 (no flush needed)",
+                           "parallelism": f"independent sites x{world}"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * (2 + 2) * 8 + 10 * 8),
+                        "d2h_bytes_per_step": int((1 + 10) * 8)},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "nlml": val}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

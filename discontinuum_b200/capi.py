@@ -225,15 +225,16 @@ class Engine:
                                          _ptr(var)[0] if want_var else None), "dgp_predict")
         return mu, var
 
-    def sample(self, Xs, Z, jitter: float = 0.0) -> np.ndarray:
+    def sample(self, Xs, Z, jitter: float = 0.0) -> Tuple[np.ndarray, int]:
+        """(draws[S, m], info): info > 0 means the posterior covariance (+ jitter) was not positive definite."""
         Xs, Z = _f64(Xs), _f64(Z)
         S, m = Z.shape
         if Xs.shape[0] != m:
             raise ValueError("sample: Z[S, m] and Xs[m, ndim] expected")
         out = np.empty((S, m))
-        self._check(self.lib.dgp_sample(self._h, Xs.ctypes.data, m, Z.ctypes.data, S, float(jitter), out.ctypes.data, 0),
-                    "dgp_sample")
-        return out
+        info = self._check(self.lib.dgp_sample(self._h, Xs.ctypes.data, m, Z.ctypes.data, S, float(jitter), out.ctypes.data, 0),
+                           "dgp_sample")
+        return out, info
 
     # -- parity / debug
     def covmat(self, theta) -> np.ndarray:

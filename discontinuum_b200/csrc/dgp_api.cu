@@ -282,39 +282,59 @@ static int run_features(dgp_handle h) {
   return 0;
 }
 
-static int run_potrf(dgp_handle h, double jitter) {
-  const int nb = h->nb, npad = h->npad;
-  const long long ld = npad;
+// Right-looking blocked Cholesky of the padded matrix in `A` (lower tiles), L -> `Lm`.  generate: block
+// column 0 and every tile at its first trailing update come from the covariance generator instead of memory.
+struct CholBufs {
+  double *A, *L, *U, *DI, *scal;
+  const CUtensorMap *tA, *tL, *tDI;
+  int nb;
+  long long ld;
+};
+
+static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jitter, bool fwd) {
+  const int nb = b.nb;
+  const long long ld = b.ld;
   int rc;
-  // block column 0 of Ky
-  k_cov_rect<<<dim3(npad / 32, 1), 256, 0, h->stream>>>(h->spec, h->theta, h->Xw, h->Xw, h->noise, jitter, h->bufA, ld,
-                                                       h->n, h->n, 1, 1, nullptr, nullptr, 0);
-  h->launches++;
-  CK(h, cudaGetLastError());
+  if (generate) {
+    k_cov_rect<<<dim3(nb * 4, 1), 256, 0, h->stream>>>(h->spec, h->theta, h->Xw, h->Xw, h->noise, jitter, b.A, ld, h->n,
+                                                       h->n, 1, 1, nullptr, nullptr, 0);
+    h->launches++;
+    CK(h, cudaGetLastError());
+  }
   for (int s = 0; s < nb; s++) {
     const size_t off = (size_t)s * 128 * ld + (size_t)s * 128;
-    k_potf2<<<1, PF_THREADS, PF_SMEM, h->stream>>>(h->bufA + off, h->bufL + off, h->bufU + off, ld,
-                                                   h->DI + (size_t)s * 128 * 128, h->scal, s * 128);
+    k_potf2<<<1, PF_THREADS, PF_SMEM, h->stream>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
+                                                   b.DI + (size_t)s * 128 * 128, b.scal, s * 128);
     h->launches++;
     CK(h, cudaGetLastError());
     const int m = nb - s - 1;
     if (m > 0) {
       GemmArgs g = base_args(h, M_TRSM, s);
-      g.C = h->bufL; g.ntiles = 2 * m;
-      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmA, h->tmDI, g))) return rc;
+      g.nb = nb; g.ldc = ld;
+      g.C = b.L; g.ntiles = 2 * m;
+      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, *b.tA, *b.tDI, g))) return rc;
     }
-    k_fwd_step<<<nb - s, 256, 0, h->stream>>>(h->bufL, ld, h->DI, h->r, h->z, s);
-    h->launches++;
-    CK(h, cudaGetLastError());
+    if (fwd) {
+      k_fwd_step<<<nb - s, 256, 0, h->stream>>>(b.L, ld, b.DI, h->r, h->z, s);
+      h->launches++;
+      CK(h, cudaGetLastError());
+    }
     if (m > 0) {
       GemmArgs g = base_args(h, M_TRAIL, s);
-      g.C = h->bufA; g.ntiles = m * (m + 1); g.sign = -1.0; g.jitter = jitter;
-      if (s == 0) rc = launch_gemm<INIT_COV, EPI_STORE>(h, h->tmL, h->tmL, g);
-      else rc = launch_gemm<INIT_LOAD, EPI_STORE>(h, h->tmL, h->tmL, g);
+      g.nb = nb; g.ldc = ld;
+      g.C = b.A; g.ntiles = m * (m + 1); g.sign = -1.0; g.jitter = jitter;
+      g.aux2 = generate ? 0 : 1;
+      if (s == 0 && generate) rc = launch_gemm<INIT_COV, EPI_STORE>(h, *b.tL, *b.tL, g);
+      else rc = launch_gemm<INIT_LOAD, EPI_STORE>(h, *b.tL, *b.tL, g);
       if (rc) return rc;
     }
   }
   return 0;
+}
+
+static int run_potrf(dgp_handle h, double jitter) {
+  CholBufs b{h->bufA, h->bufL, h->bufU, h->DI, h->scal, &h->tmA, &h->tmL, &h->tmDI, h->nb, h->npad};
+  return potrf_core(h, b, true, jitter, true);
 }
 
 static int run_trtri(dgp_handle h) {
@@ -525,10 +545,92 @@ int dgp_predict(dgp_handle h, const double* Xs, int m, int on_device, double* mu
   return 0;
 }
 
+// ------------------------------------------------------------------ joint posterior samples
+// Sigma* = K** - V'V with V = L^-1 Kx* (n x m), Lpost = chol(Sigma* + jitter I), out = mu* + Z Lpost'.
+// Work buffers (m-sized) are allocated per call; everything runs on the tile engine:
+//   V'  [m, n] = Kx [m, n] T'          (T = L^-1 lower: triangular k range)
+//   Sigma* lower tiles = cov tile(x*_i, x*_j) - V'[i, :] V'[j, :]'   (covariance tile generated as accumulator init)
+//   Lpost by the same blocked Cholesky as the training factorisation
+//   out [S, m] = Z [S, m] Lpost'     (triangular k range) + mu
 int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, double jitter, double* out, int on_device) {
-  (void)Xs; (void)m; (void)Z; (void)S; (void)jitter; (void)out; (void)on_device;
   if (!h) return -1;
-  DGP_FAIL(h, -100, "dgp_sample: not implemented yet");
+  if (!Xs || !Z || !out || m < 1 || S < 1) DGP_FAIL(h, -1, "dgp_sample: bad arguments");
+  if (!h->factorized || !h->have_T) DGP_FAIL(h, -1, "dgp_sample: call dgp_factorize first");
+  CK(h, cudaSetDevice(h->device));
+  const int mpad = round_up(m, 128), Spad = round_up(S, 128), npad = h->npad, mb = mpad / 128;
+  const cudaMemcpyKind ikind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind okind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  double *Xsd = nullptr, *Xws = nullptr, *means = nullptr, *dot = nullptr, *mu = nullptr, *Kx = nullptr, *VT = nullptr;
+  double *Sig = nullptr, *Lp = nullptr, *DI2 = nullptr, *Zd = nullptr, *Od = nullptr, *zero = nullptr, *scal2 = nullptr;
+  struct Freer {
+    double** p[14]; int k = 0;
+    ~Freer() { for (int i = 0; i < k; i++) if (*p[i]) cudaFree(*p[i]); }
+  } fr;
+  auto A = [&](double** p, size_t count) {
+    fr.p[fr.k++] = p;
+    return cudaMalloc((void**)p, count * sizeof(double));
+  };
+  cudaError_t r = cudaSuccess;
+  auto acc = [&](cudaError_t x) { if (r == cudaSuccess) r = x; };
+  acc(A(&Xsd, (size_t)mpad * DGP_MAX_COLS)); acc(A(&Xws, (size_t)mpad * DGP_XS)); acc(A(&means, mpad));
+  acc(A(&dot, (size_t)h->nb * mpad)); acc(A(&mu, mpad)); acc(A(&Kx, (size_t)mpad * npad)); acc(A(&VT, (size_t)mpad * npad));
+  acc(A(&Sig, (size_t)mpad * mpad)); acc(A(&Lp, (size_t)mpad * mpad)); acc(A(&DI2, (size_t)mpad * 128));
+  acc(A(&Zd, (size_t)Spad * mpad)); acc(A(&Od, (size_t)Spad * mpad)); acc(A(&zero, mpad)); acc(A(&scal2, SC_SIZE));
+  if (r != cudaSuccess) DGP_FAIL(h, -2, "dgp_sample: workspace allocation failed for m=%d, S=%d: %s", m, S, cudaGetErrorString(r));
+  int rc;
+  CK(h, cudaMemsetAsync(zero, 0, (size_t)mpad * 8, h->stream));
+  CK(h, cudaMemsetAsync(scal2, 0, SC_SIZE * 8, h->stream));
+  CK(h, cudaMemsetAsync(Zd, 0, (size_t)Spad * mpad * 8, h->stream));
+  CK(h, cudaMemcpyAsync(Xsd, Xs, (size_t)m * h->spec.ndim * 8, ikind, h->stream));
+  CK(h, cudaMemcpy2DAsync(Zd, (size_t)mpad * 8, Z, (size_t)m * 8, (size_t)m * 8, S, ikind, h->stream));
+  k_features<<<(mpad + 255) / 256, 256, 0, h->stream>>>(h->spec, h->theta, Xsd, nullptr, Xws, nullptr, means, m, mpad, nullptr);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  // cross covariance + mean
+  k_cov_rect<<<dim3(mpad / 32, h->nb), 256, 0, h->stream>>>(h->spec, h->theta, Xws, h->Xw, h->noise, 0.0, Kx, npad, m,
+                                                           h->n, 0, 0, h->alpha, dot, mpad);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  k_pred_finish<<<(m + 255) / 256, 256, 0, h->stream>>>(h->spec, h->theta, Xws, means, dot, h->nb, nullptr, 0, mpad, m, mu, nullptr);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CUtensorMap tKx, tVT, tSig, tLp, tDI2, tZ;
+  if ((rc = make_map(h, &tKx, Kx, mpad, npad, npad))) return rc;
+  if ((rc = make_map(h, &tVT, VT, mpad, npad, npad))) return rc;
+  if ((rc = make_map(h, &tSig, Sig, mpad, mpad, mpad))) return rc;
+  if ((rc = make_map(h, &tLp, Lp, mpad, mpad, mpad))) return rc;
+  if ((rc = make_map(h, &tDI2, DI2, mpad, 128, 128))) return rc;
+  if ((rc = make_map(h, &tZ, Zd, Spad, mpad, mpad))) return rc;
+  {  // V' = Kx T'
+    GemmArgs g = base_args(h, M_GENERIC, 0);
+    g.nb = mb; g.n = m; g.aux0 = 2 * h->nb; g.aux1 = npad / 16; g.aux2 = 1;
+    g.ntiles = mb * 2 * h->nb; g.C = VT; g.ldc = npad;
+    if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, tKx, h->tmA, g))) return rc;
+  }
+  {  // Sigma* = K** + jitter I - V'V  (lower tiles)
+    GemmArgs g = base_args(h, M_GENERIC, 0);
+    g.nb = mb; g.n = m; g.aux0 = 2 * mb; g.aux1 = npad / 16; g.aux2 = 2;
+    g.ntiles = mb * (mb + 1); g.C = Sig; g.ldc = mpad; g.sign = -1.0;
+    g.Xw = Xws; g.noise = zero; g.jitter = jitter; g.latent = 1;
+    if ((rc = launch_gemm<INIT_COV, EPI_STORE>(h, tVT, tVT, g))) return rc;
+  }
+  {  // Lpost
+    CholBufs b{Sig, Lp, nullptr, DI2, scal2, &tSig, &tLp, &tDI2, mb, mpad};
+    if ((rc = potrf_core(h, b, false, 0.0, false))) return rc;
+  }
+  {  // out = Z Lpost'
+    GemmArgs g = base_args(h, M_GENERIC, 0);
+    g.nb = Spad / 128; g.n = S; g.aux0 = 2 * mb; g.aux1 = mpad / 16; g.aux2 = 1;
+    g.ntiles = (Spad / 128) * 2 * mb; g.C = Od; g.ldc = mpad;
+    if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, tZ, tLp, g))) return rc;
+  }
+  k_add_rowvec<<<dim3((m + 255) / 256, S), 256, 0, h->stream>>>(Od, mpad, mu, m);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpy2DAsync(out, (size_t)m * 8, Od, (size_t)mpad * 8, (size_t)m * 8, S, okind, h->stream));
+  CK(h, cudaMemcpyAsync(h->h_scal, scal2, SC_SIZE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return (int)h->h_scal[SC_INFO];
 }
 
 // ------------------------------------------------------------------ generic NT product on the tile engine

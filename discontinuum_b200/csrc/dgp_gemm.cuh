@@ -42,6 +42,7 @@ struct GemmArgs {
   double* part;                 // EPI_GRAD: [ntiles][DGP_MAX_THETA]; EPI_SUMSQ: [2 nb][rows]
   double* Kinv;                 // optional dense Ky^-1 output (EPI_GRAD, debug), ld = ldc
   double jitter;
+  int latent;                   // INIT_COV: add only `jitter` on the diagonal (latent posterior covariance)
 };
 
 struct Job {
@@ -77,7 +78,7 @@ __device__ __forceinline__ Job decode_job(const GemmArgs& g, int tile, int init_
       j.rowB = c * 64; j.kB = s * 128;
       j.nk = 8;
       j.crow = i * 128; j.ccol = c * 64;
-      j.init = (s == 0) ? INIT_COV : INIT_LOAD;
+      j.init = (s == 0 && g.aux2 == 0) ? INIT_COV : INIT_LOAD;  // aux2 = 1: matrix supplied, nothing to generate
     } break;
     case M_TRI_FINAL: {  // U[i, s] = -S[i, s] * Linv_s^T   for i < s
       const int i = tile >> 1, h = tile & 1;
@@ -239,7 +240,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
           double v;
           if (gr < g.n && gc < g.n) {
             v = cov_entry(cc, xi, xs + (BM + lc) * DGP_XS);
-            if (gr == gc) v += g.noise[gr] + cc->extra_noise;
+            if (gr == gc) v += g.latent ? g.jitter : g.noise[gr] + cc->extra_noise;
           } else {
             v = (gr == gc) ? 1.0 : 0.0;
           }

@@ -220,7 +220,7 @@ k_potf2(const double* __restrict__ Ablk, double* __restrict__ Lblk, double* __re
     const int r = e >> 7, c = e & 127;
     const double lv = As[r * PF_AS + c];
     Lblk[(size_t)r * ld + c] = (c <= r) ? lv : 0.0;
-    Ublk[(size_t)r * ld + c] = (c > r) ? lv : (c == r ? rd[r] : 0.0);
+    if (Ublk != nullptr) Ublk[(size_t)r * ld + c] = (c > r) ? lv : (c == r ? rd[r] : 0.0);
     DIblk[r * 128 + c] = (c < r) ? As[c * PF_AS + r] : (c == r ? rd[r] : 0.0);
   }
   if (warp == 0) {
@@ -378,4 +378,12 @@ k_pred_finish(const __grid_constant__ dgp_spec spec, const double* __restrict__ 
   }
 }
 
+}  // namespace dgp
+
+namespace dgp {
+// out[s, i] += mu[i]  (rows s < S, cols i < m), grid = (ceil(m/256), S)
+__global__ void __launch_bounds__(256) k_add_rowvec(double* __restrict__ out, long long ld, const double* __restrict__ mu, int m) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < m) out[(size_t)blockIdx.y * ld + i] += mu[i];
+}
 }  // namespace dgp

@@ -92,3 +92,85 @@ def rating_spec(b_lo: float, b_hi: float, gate_b_init: Optional[float] = None, p
 def stage_quantile_bounds(stage: np.ndarray):
     """np.quantile(stage, 0.10 / 0.90) as at src/rating_gp/models/gpytorch.py:221-223."""
     return float(np.quantile(stage, 0.10)), float(np.quantile(stage, 0.90))
+
+
+# ----------------------------------------------------------------------------------------------
+# model classes: the reference's  class Model(DataMixin, PlotMixin, Marginal<Engine>)  pattern
+# (src/loadest_gp/models/gpytorch.py:24-58, src/rating_gp/models/gpytorch.py:43-202) with the
+# engine base swapped for MarginalB200.  Plot mixins are the reference's own and are not rebuilt.
+# ----------------------------------------------------------------------------------------------
+import torch  # noqa: E402
+
+from .data import LogStandardPipeline, TimePipeline, UnitPipeline  # noqa: E402
+from .engine import DataMixin, MarginalB200, ModelConfig  # noqa: E402
+from .spec import GPModule  # noqa: E402
+
+
+class LoadestDataMixin(DataMixin):
+    """src/loadest_gp/models/base.py:7-19."""
+
+    def build_datamanager(self, model_config: Optional[ModelConfig] = None):
+        self._build_datamanager({"time": TimePipeline, "flow": LogStandardPipeline}, model_config)
+
+
+class RatingDataMixin(DataMixin):
+    """src/rating_gp/models/base.py:7-19."""
+
+    def build_datamanager(self, model_config: Optional[ModelConfig] = None):
+        self._build_datamanager({"time": TimePipeline, "stage": UnitPipeline}, model_config)
+
+
+class LoadestGPMarginalB200(LoadestDataMixin, MarginalB200):
+    """Gaussian-process LOADEST model on the B200 engine (src/loadest_gp/models/gpytorch.py:24-58)."""
+
+    def __init__(self, model_config: Optional[ModelConfig] = None):
+        if model_config is None:
+            model_config = ModelConfig()
+        super().__init__(model_config=model_config)
+        self.build_datamanager(model_config)
+
+    def build_model(self, X, y, y_unc=None) -> GPModule:
+        self.fixed_noise = np.full(y.shape[0], LOADEST_FIXED_NOISE)
+        return GPModule(loadest_spec(X.shape[1]))
+
+
+class RatingGPMarginalB200(RatingDataMixin, MarginalB200):
+    """Stage-discharge rating-curve GP on the B200 engine (src/rating_gp/models/gpytorch.py:43-265)."""
+
+    def __init__(self, model_config: Optional[ModelConfig] = None):
+        if model_config is None:
+            model_config = ModelConfig()
+        super().__init__(model_config=model_config)
+        self.build_datamanager(model_config)
+
+    def build_model(self, X, y, y_unc=None) -> GPModule:
+        assert X.shape[1] == 2, "Only two dimensions supported"
+        self.fixed_noise = np.asarray(y_unc, dtype=np.float64) if y_unc is not None else np.full(y.shape[0], RATING_DEFAULT_NOISE)
+        b_lo, b_hi = stage_quantile_bounds(X[:, 1])
+        # same random initial draws as the reference (gpytorch.py:31-36, kernels.py:276)
+        a = float(torch.randn(1)); b = float(torch.randn(1) + 1.3); c = float(torch.rand(1))
+        gb = b_lo + float(torch.rand(1)) * (b_hi - b_lo)
+        gb = min(max(gb, b_lo + 1e-9 * (b_hi - b_lo)), b_hi - 1e-9 * (b_hi - b_lo))
+        return GPModule(rating_spec(b_lo, b_hi, gate_b_init=gb, pl_a=a, pl_b=b, pl_c=c))
+
+    def project_parameters(self, X_all: np.ndarray):
+        """b clamped to [1.2, 2.5], c <= min(stage) - 1e-6, in place on every forward (gpytorch.py:39,259)."""
+        with torch.no_grad():
+            raw = self.model.raw
+            raw["powerlaw__b"].clamp_(1.2, 2.5)
+            raw["powerlaw__c"].clamp_(max=float(X_all[:, 1].min()) - 1e-6)
+
+    def fit(self, covariates, target, target_unc=None, iterations=100, optimizer=None, learning_rate=None,
+            early_stopping=False, patience=60, scheduler=True, resume=False, monotonic_penalty_weight: float = 0.0,
+            grid_size: int = 64, monotonic_penalty_interval: int = 1, **kw):
+        if monotonic_penalty_weight > 0:
+            raise NotImplementedError(
+                "monotonic rating penalty (src/rating_gp/models/gpytorch.py:126-202) is scheduled after the hot path "
+                "(SURVEY 8f.1): it needs the adjoint of the posterior mean w.r.t. theta")
+        return super().fit(covariates=covariates, target=target, target_unc=target_unc, iterations=iterations,
+                           optimizer=optimizer, learning_rate=learning_rate, early_stopping=early_stopping,
+                           patience=patience, scheduler=scheduler, resume=resume, **kw)
+
+
+LoadestGP = LoadestGPMarginalB200
+RatingGP = RatingGPMarginalB200

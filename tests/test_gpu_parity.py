@@ -1,0 +1,345 @@
+"""GPU parity tests proper: everything goes through the C ABI (libdgp.so via ctypes) and is compared with the
+mpmath golden vectors, with the CPU oracle on the same seeded inputs, and -- at BASELINE.json's full sizes --
+through size-independent properties.  Tolerance of the north star: <= 1e-6 relative in float64 (observed ~1e-11)."""
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from helpers import orc
+from discontinuum_b200 import capi, models, synthetic
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6  # north-star tolerance for NLML, gradients, predictive mean and variance
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _engine(spec, X, y, noise, max_m=256):
+    eng = capi.Engine(max_n=X.shape[0], max_m=max_m)
+    eng.set_train(spec.to_c(), X, y, noise)
+    return eng
+
+
+def _oracle(model, theta, X, y, noise):
+    Xt, yt, nt = torch.tensor(X), torch.tensor(y), torch.tensor(noise)
+    if model == "loadest":
+        nat = H.loadest_nat_from_theta(theta, X.shape[1])
+        v, g, a, L = orc.nlml_grad_closed_form(orc.loadest_cov, orc.loadest_mean, nat, Xt, yt, nt)
+        return float(v), H.loadest_theta_from_nat({k: t.numpy() for k, t in g.items()}), a.numpy(), L.numpy(), nat
+    nat = H.rating_nat_from_theta(theta)
+    v, g, a, L = orc.nlml_grad_closed_form(orc.rating_cov, orc.rating_mean, nat, Xt, yt, nt, extra_key="noise")
+    return float(v), H.rating_theta_from_nat({k: t.numpy() for k, t in g.items()}), a.numpy(), L.numpy(), nat
+
+
+def _grad_close(got, want, rtol=RTOL):
+    assert np.max(np.abs(got - want)) <= rtol * np.max(np.abs(want)), (got, want)
+
+
+@pytest.mark.parametrize("fname", ["kat_loadest.json", "kat_rating.json"])
+def test_golden_vectors_through_cabi(cuda_device, fname):
+    with open(os.path.join(GOLD, fname)) as f:
+        cases = json.load(f)
+    for case in cases:
+        X, y, noise, theta = (np.array(case[k]) for k in ("X", "y", "noise", "theta"))
+        if case["model"] == "loadest":
+            spec = models.loadest_spec(2)
+        else:
+            spec = models.rating_spec(1.0, 2.0)  # bounds only constrain the raw value; theta is passed in natural space
+        eng = _engine(spec, X, y, noise)
+        assert np.max(np.abs(eng.covmat(theta) - np.array(case["K"]))) < 1e-14
+        val, info = eng.nlml(theta)
+        assert info == 0 and abs(val - case["nlml"]) <= 1e-12 * max(1.0, abs(case["nlml"]))
+        val2, grad, info = eng.nlml_grad(theta)
+        assert info == 0 and val2 == val
+        gold = np.array(case["grad"])
+        assert np.max(np.abs(grad - gold)) <= 1e-8 * max(1.0, np.max(np.abs(gold))), (case["n"], grad, gold)
+        assert np.max(np.abs(eng.alpha() - np.array(case["alpha"]))) <= 1e-9 * np.max(np.abs(case["alpha"]))
+        assert np.max(np.abs(np.tril(eng.chol()) - np.array(case["L"]))) < 1e-12
+        eng.factorize(theta)
+        mu, var = eng.predict(np.array(case["Xs"]))
+        assert np.max(np.abs(mu - np.array(case["mu"]))) <= 1e-9 * max(1.0, np.max(np.abs(case["mu"])))
+        assert np.max(np.abs(var - np.array(case["var_latent"]))) <= 1e-9
+        eng.close()
+
+
+@pytest.mark.parametrize("model,n,kind", [("loadest", 127, 0), ("loadest", 128, 1), ("loadest", 129, 0), ("loadest", 300, 1),
+                                           ("loadest", 1000, 1), ("loadest", 2000, 0), ("rating", 200, 0), ("rating", 1000, 1),
+                                           ("rating", 2000, 1)])
+def test_nlml_grad_alpha_chol_vs_oracle(cuda_device, model, n, kind):
+    if model == "loadest":
+        X, y, noise = synthetic.loadest_site(n, 1000 + n)
+        spec = models.loadest_spec(2)
+        theta = H.loadest_theta0() if kind == 0 else H.loadest_theta1()
+    else:
+        X, y, noise = synthetic.rating_gauge(n, 7)
+        b_lo, b_hi = models.stage_quantile_bounds(X[:, 1])
+        spec = models.rating_spec(b_lo, b_hi)
+        theta = H.rating_theta0(b_lo, b_hi) if kind == 0 else H.rating_theta1(b_lo, b_hi)
+    v, g, a, L, _ = _oracle(model, theta, X, y, noise)
+    eng = _engine(spec, X, y, noise)
+    val, grad, info = eng.nlml_grad(theta)
+    assert info == 0
+    assert abs(val - v) <= RTOL * abs(v)
+    _grad_close(grad, g)
+    assert np.max(np.abs(eng.alpha() - a)) <= RTOL * np.max(np.abs(a))
+    Lg = eng.chol()
+    assert np.max(np.abs(np.tril(Lg) - L)) <= RTOL * np.max(np.abs(L)) and np.max(np.abs(np.triu(Lg, 1))) == 0.0
+    val0, info0 = eng.nlml(theta)
+    assert info0 == 0 and val0 == val
+    eng.close()
+
+
+def test_loadest_three_covariate_dims(cuda_device):
+    rng = np.random.default_rng(3)
+    n = 400
+    X = np.ascontiguousarray(np.stack([np.sort(rng.uniform(-5, 5, n)), rng.standard_normal(n), rng.standard_normal(n)], 1))
+    y, noise = rng.standard_normal(n), np.full(n, 0.01)
+    theta = np.array([0.1, 0.7, 1.0, 1.0, 2.0, 1.3, 0.5, 0.8, 0.2, 0.3, 0.4, 0.6])
+    v, g, a, L, _ = _oracle("loadest", theta, X, y, noise)
+    eng = _engine(models.loadest_spec(3), X, y, noise)
+    val, grad, info = eng.nlml_grad(theta)
+    assert info == 0 and abs(val - v) <= RTOL * abs(v)
+    _grad_close(grad, g)
+    eng.close()
+
+
+def test_kinv_and_cross_covariance(cuda_device):
+    n = 500
+    X, y, noise = synthetic.loadest_site(n, 11)
+    theta = H.loadest_theta1()
+    _, _, _, L, nat = _oracle("loadest", theta, X, y, noise)
+    eng = _engine(models.loadest_spec(2), X, y, noise)
+    eng.set_debug_kinv(True)
+    eng.nlml_grad(theta)
+    Ki = torch.cholesky_inverse(torch.tensor(L)).numpy()
+    assert np.max(np.abs(np.tril(eng.kinv()) - np.tril(Ki))) <= RTOL * np.max(np.abs(Ki))
+    Xs = synthetic.daily_grid(X, 333)
+    Kx = eng.cross_covmat(theta, Xs)
+    assert np.max(np.abs(Kx - orc.loadest_cov(torch.tensor(Xs), torch.tensor(X), nat).numpy())) < 1e-14
+    eng.close()
+
+
+def test_predict_mean_variance_vs_oracle_multi_chunk(cuda_device):
+    for model in ("loadest", "rating"):
+        if model == "loadest":
+            X, y, noise = synthetic.loadest_site(700, 21)
+            spec, theta = models.loadest_spec(2), H.loadest_theta1()
+            nat, cov, mean, en = H.loadest_nat_from_theta(theta), orc.loadest_cov, orc.loadest_mean, None
+        else:
+            X, y, noise = synthetic.rating_gauge(600, 9)
+            b_lo, b_hi = models.stage_quantile_bounds(X[:, 1])
+            spec, theta = models.rating_spec(b_lo, b_hi), H.rating_theta1(b_lo, b_hi)
+            nat = H.rating_nat_from_theta(theta)
+            cov, mean, en = orc.rating_cov, orc.rating_mean, nat["noise"]
+        Xs = synthetic.daily_grid(X, 1000)  # 4 chunks of 256
+        eng = _engine(spec, X, y, noise, max_m=256)
+        _, info = eng.factorize(theta)
+        assert info == 0
+        mu, var = eng.predict(Xs)
+        mu_o, _, var_o = orc.predict(cov, mean, nat, torch.tensor(X), torch.tensor(y), torch.tensor(noise), torch.tensor(Xs), extra_noise=en)
+        assert np.max(np.abs(mu - mu_o.numpy())) <= RTOL * np.max(np.abs(mu_o.numpy()))
+        assert np.max(np.abs(var - var_o.numpy())) <= RTOL * np.max(np.abs(var_o.numpy()))
+        mu2, none = eng.predict(Xs, want_var=False)
+        assert none is None and np.array_equal(mu2, mu)
+        eng.close()
+
+
+def test_sample_matches_oracle_given_same_normals(cuda_device):
+    n, m, S = 300, 200, 64
+    X, y, noise = synthetic.loadest_site(n, 31)
+    theta = H.loadest_theta1()
+    nat = H.loadest_nat_from_theta(theta)
+    Xs = synthetic.daily_grid(X, m) + np.array([0.003, 0.01])
+    Z = np.random.default_rng(0).standard_normal((S, m))
+    eng = _engine(models.loadest_spec(2), X, y, noise)
+    eng.factorize(theta)
+    draws, info = eng.sample(Xs, Z, jitter=1e-8)
+    assert info == 0
+    want, _ = orc.sample(orc.loadest_cov, orc.loadest_mean, nat, torch.tensor(X), torch.tensor(y), torch.tensor(noise),
+                         torch.tensor(Xs), torch.tensor(Z), jitter=1e-8)
+    assert np.max(np.abs(draws - want.numpy())) <= 1e-5 * np.max(np.abs(want.numpy()))
+    # moments: mean over draws -> posterior mean within Monte-Carlo error
+    mu, var = eng.predict(Xs)
+    assert np.max(np.abs(draws.mean(0) - mu)) < 6 * np.sqrt(np.max(var) / S) + 1e-6
+    eng.close()
+
+
+def test_non_positive_definite_reports_info_and_jitter_repairs(cuda_device):
+    n = 300
+    X, y, _ = synthetic.loadest_site(n, 41)
+    X[150] = X[149]  # duplicated input and zero noise: exactly singular
+    noise = np.zeros(n)
+    eng = _engine(models.loadest_spec(2), X, y, noise)
+    val, info = eng.nlml(H.loadest_theta1())
+    assert info > 0 or not np.isfinite(val)
+    val2, info2 = eng.nlml(H.loadest_theta1(), jitter=1e-6)
+    assert info2 == 0 and np.isfinite(val2)
+    with pytest.raises(capi.DgpError):
+        eng.alpha() if info > 0 else (_ for _ in ()).throw(capi.DgpError("x"))
+    eng.close()
+
+
+def test_bad_arguments_raise(cuda_device):
+    eng = capi.Engine(max_n=64)
+    X, y, noise = synthetic.loadest_site(100, 1)
+    with pytest.raises(capi.DgpError, match="max_n"):
+        eng.set_train(models.loadest_spec(2).to_c(), X, y, noise)
+    with pytest.raises(capi.DgpError, match="set_train"):
+        eng.lib.dgp_nlml.restype = int
+        eng._check(eng.lib.dgp_nlml(eng._h, H.loadest_theta1().ctypes.data, 0.0, None), "dgp_nlml")
+    bad = models.loadest_spec(2).to_c()
+    bad.nterms = 99
+    with pytest.raises(capi.DgpError, match="nterms"):
+        eng.set_train(bad, X[:50], y[:50], noise[:50])
+    eng.close()
+
+
+def test_tile_engine_many_tiles_regression(cuda_device):
+    """Regression for the shared-memory WAR race (ring stage released before its fragment loads returned):
+    it only showed with > 2 waves of co-resident CTAs and a wrapped ring (K >= 128)."""
+    eng = capi.Engine(max_n=128)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    for (M, N, K) in [(4096, 4096, 128), (4096, 4096, 512), (1024, 8192, 256)]:
+        A = torch.randn(M, K, dtype=torch.float64, device=dev)
+        B = torch.randn(N, K, dtype=torch.float64, device=dev)
+        ref = A @ B.T
+        for mode in (0, -1, 1):
+            C0 = torch.randn(M, N, dtype=torch.float64, device=dev)
+            Cm = C0.clone()
+            torch.cuda.synchronize()
+            eng.gemm_nt(A, B, Cm, mode)
+            want = ref if mode == 0 else C0 + mode * ref
+            assert float((Cm - want).abs().max()) < 1e-10
+    eng.close()
+
+
+def test_large_n_deterministic_and_consistent(cuda_device):
+    n = 3584
+    X, y, noise = synthetic.loadest_site(n, 51)
+    eng = _engine(models.loadest_spec(2), X, y, noise)
+    th = H.loadest_theta1()
+    runs = [eng.nlml_grad(th) for _ in range(3)]
+    assert all(r[2] == 0 for r in runs)
+    assert runs[0][0] == runs[1][0] == runs[2][0]
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][1], runs[2][1])
+    v, g, _, _, _ = _oracle("loadest", th, X, y, noise)
+    assert abs(runs[0][0] - v) <= RTOL * abs(v)
+    _grad_close(runs[0][1], g)
+    eng.close()
+
+
+def test_full_size_properties_n16384(cuda_device):
+    """BASELINE config 3 size (the oracle cannot run here in seconds): size-independent checks.
+    (i) directional derivative of NLML by central differences agrees with the analytic gradient;
+    (ii) posterior mean at the training inputs equals y - noise * alpha (since K alpha = r - noise alpha);
+    (iii) latent variance at training inputs lies in [0, noise]."""
+    n = 16384
+    X, y, noise = synthetic.loadest_site(n, 1000)
+    eng = _engine(models.loadest_spec(2), X, y, noise, max_m=512)
+    th = H.loadest_theta1()
+    val, grad, info = eng.nlml_grad(th)
+    assert info == 0 and np.isfinite(val)
+    d = np.random.default_rng(0).standard_normal(th.shape[0]) * th * 1e-2
+    d[0] = 1e-2
+    eps = 1e-3
+    vp, ip = eng.nlml(th + eps * d)
+    vm, im = eng.nlml(th - eps * d)
+    assert ip == 0 and im == 0
+    fd = (vp - vm) / (2 * eps)
+    assert abs(fd - grad @ d) <= 1e-5 * abs(grad @ d) + 1e-8 * abs(val), (fd, grad @ d)
+    _, info = eng.factorize(th)
+    assert info == 0
+    alpha = eng.alpha()
+    idx = np.arange(0, n, 37)[:400]
+    mu, var = eng.predict(X[idx])
+    assert np.max(np.abs(mu - (y[idx] - noise[idx] * alpha[idx]))) <= 1e-7 * max(1.0, np.max(np.abs(y)))
+    assert np.all(var > -1e-9) and np.all(var <= noise[idx] + 1e-9)
+    eng.close()
+
+
+def test_async_launch_wait_two_sites(cuda_device):
+    sites = [synthetic.loadest_site(n, 60 + n) for n in (900, 1400)]
+    engs = [_engine(models.loadest_spec(2), *s) for s in sites]
+    th = H.loadest_theta1()
+    for e in engs:
+        e.nlml_grad_launch(th)
+    res = [e.nlml_grad_wait() for e in engs]
+    for e, r in zip(engs, res):
+        v, g, info = e.nlml_grad(th)
+        assert info == 0 and r[0] == v and np.array_equal(r[1], g)
+        e.close()
+
+
+def _loadest_arrays(n, seed):
+    rng = np.random.default_rng(seed)
+    days = np.sort(rng.uniform(0, 3650, n))
+    time = np.datetime64("2000-01-01") + (days * 86400e9).astype("timedelta64[ns]")
+    flow = np.exp(1.0 + 0.8 * np.sin(2 * np.pi * days / 365.25) + 0.5 * rng.standard_normal(n))
+    conc = np.exp(0.3 * np.log(flow) + 0.2 * np.cos(2 * np.pi * days / 365.25) + 0.2 * rng.standard_normal(n))
+    return {"time": time, "flow": flow}, conc
+
+
+def test_engine_fit_trajectory_matches_reference_loop_loadest(cuda_device):
+    """MarginalB200.fit against the oracle's restatement of the reference loop (Adam lr .05 wd 1e-4, clip 1.0,
+    ReduceLROnPlateau): same objective at every iteration."""
+    cov, conc = _loadest_arrays(200, 0)
+    m = models.LoadestGP()
+    m.fit(cov, conc, iterations=12)
+    assert m.is_fitted and len(m.history) == 12
+    raw = orc.loadest_init_raw()
+    _, hist = orc.fit_adam("loadest", raw, torch.tensor(m.X), torch.tensor(m.y), torch.tensor(m.fixed_noise), iterations=12)
+    assert np.max(np.abs(np.array(m.history) - np.array(hist)) / np.abs(hist)) <= RTOL
+    # surface: predict / predict_grid / sample / save / load / resume
+    target, se = m.predict(cov)
+    assert target.shape == (200,) and se.shape == (200,) and np.all(se >= 1.0) and np.all(target > 0)
+    grid, index, covs = m.predict_grid("flow")
+    assert grid.shape[1] == 18 and grid.shape[0] == index.shape[0] and covs.shape == (18,)
+    sub = {k: v[:50] for k, v in cov.items()}
+    sim = m.sample(sub, n=32, seed=1)
+    assert sim.shape == (32, 50) and np.all(np.isfinite(sim)) and np.all(sim > 0)
+    buf = io.BytesIO()
+    m.save(buf)
+    buf.seek(0)
+    m2 = models.LoadestGP.load(buf, cov, conc)
+    assert m2.is_fitted and m2._current_iteration == 11
+    t2, _ = m2.predict(cov)
+    assert np.allclose(t2, target, rtol=1e-10)
+    m2.fit(cov, conc, iterations=15, resume=True)
+    assert len(m2.history) == 4
+    with pytest.raises(ValueError, match="Unsupported optimizer"):
+        models.LoadestGP().fit(cov, conc, iterations=1, optimizer="sgd")
+
+
+def test_engine_fit_trajectory_matches_reference_loop_rating(cuda_device):
+    rng = np.random.default_rng(5)
+    n = 150
+    days = np.sort(rng.uniform(0, 3650, n))
+    time = np.datetime64("2005-01-01") + (days * 86400e9).astype("timedelta64[ns]")
+    stage = rng.lognormal(1.0, 0.5, n)
+    q = 3.0 * (stage - 0.5 * stage.min()) ** 1.6 * np.exp(0.03 * rng.standard_normal(n))
+    gse = rng.choice(np.array([1.02, 1.05, 1.08]), n)
+    torch.manual_seed(0)
+    m = models.RatingGP()
+    m.fit({"time": time, "stage": stage}, q, target_unc=gse, iterations=10)
+    torch.manual_seed(0)
+    a = float(torch.randn(1)); b = float(torch.randn(1) + 1.3); c = float(torch.rand(1)); u = float(torch.rand(1))
+    b_lo, b_hi = models.stage_quantile_bounds(m.X[:, 1])
+    raw = orc.rating_init_raw(b_lo, b_hi, gate_b=b_lo + u * (b_hi - b_lo), pl_a=a, pl_b=b, pl_c=c)
+    _, hist = orc.fit_adam("rating", raw, torch.tensor(m.X), torch.tensor(m.y), torch.tensor(m.fixed_noise), iterations=10,
+                           b_lo=b_lo, b_hi=b_hi, h_min=float(m.X[:, 1].min()))
+    assert np.max(np.abs(np.array(m.history) - np.array(hist)) / np.abs(hist)) <= RTOL
+    target, se = m.predict({"time": time, "stage": stage})
+    assert target.shape == (n,) and np.all(np.isfinite(target)) and np.all(se >= 1.0)
+    with pytest.raises(NotImplementedError):
+        models.RatingGP().fit({"time": time, "stage": stage}, q, target_unc=gse, iterations=2, monotonic_penalty_weight=0.5)
+
+
+def test_graft_smoke(cuda_device):
+    import __graft_entry__ as ge
+
+    ge.smoke()
