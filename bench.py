@@ -162,8 +162,9 @@ def main():
     warm = max(args.warmup, 3)
     X, y, noise = synthetic.loadest_site(n, 1000 + rank)
     spec = models.loadest_spec(2)
-    stream = torch.cuda.current_stream().cuda_stream
-    eng = capi.Engine(max_n=n, max_m=256, device=local, stream=stream)
+    work_stream = torch.cuda.Stream(device=local)  # the engine launches on this stream; the events below are recorded on it
+    torch.cuda.set_stream(work_stream)
+    eng = capi.Engine(max_n=n, max_m=256, device=local, stream=work_stream.cuda_stream)
     eng.set_train(spec.to_c(), X, y, noise)
     base = H.loadest_theta1()
     thetas = [base * (1.0 + 1e-3 * k) for k in range(warm + args.steps)]

@@ -381,7 +381,7 @@ def fit_adam(model, raw, X, y, noise, iterations=100, lr=0.05, b_lo=None, b_hi=N
         obj.backward()
         torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
         opt.step()
-        history.append(float(obj))
+        history.append(float(obj.detach()))
         if sch is not None:
             sch.step(history[-1])
     return raw, history

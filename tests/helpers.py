@@ -30,7 +30,7 @@ RATING_KEYS = ("pl_a", "pl_b", "pl_c", "noise", "gate_b", "shiftA_s", "shiftA_lh
 
 
 def rating_theta_from_nat(nat):
-    return np.array([float(nat[k]) for k in RATING_KEYS])
+    return np.array([float(np.asarray(nat[k]).reshape(-1)[0]) for k in RATING_KEYS])
 
 
 def rating_nat_from_theta(theta):

@@ -169,17 +169,18 @@ def test_sample_matches_oracle_given_same_normals(cuda_device):
 
 
 def test_non_positive_definite_reports_info_and_jitter_repairs(cuda_device):
+    """LAPACK-style info: 1-based index of the first non-positive pivot; jitter on the diagonal repairs it."""
     n = 300
     X, y, _ = synthetic.loadest_site(n, 41)
-    X[150] = X[149]  # duplicated input and zero noise: exactly singular
     noise = np.zeros(n)
+    noise[200:] = -3.0  # k(x, x) = 2.2 < 3: rows >= 200 make the matrix indefinite
     eng = _engine(models.loadest_spec(2), X, y, noise)
     val, info = eng.nlml(H.loadest_theta1())
-    assert info > 0 or not np.isfinite(val)
-    val2, info2 = eng.nlml(H.loadest_theta1(), jitter=1e-6)
+    assert 200 < info <= 300
+    with pytest.raises(capi.DgpError, match="no factorisation"):
+        eng.alpha()
+    val2, info2 = eng.nlml(H.loadest_theta1(), jitter=3.5)
     assert info2 == 0 and np.isfinite(val2)
-    with pytest.raises(capi.DgpError):
-        eng.alpha() if info > 0 else (_ for _ in ()).throw(capi.DgpError("x"))
     eng.close()
 
 
