@@ -1,0 +1,155 @@
+"""Multi-site batch: the B200 counterpart of the reference's `fexec.map(map_retrieval, sites)`
+(examples/nwqn-loadest-example/nwqn-loadest-example.py:38-128,156-159).
+
+Sites are independent GPs: nothing is exchanged while fitting.  One process per GPU (torchrun); sites are
+assigned to ranks by longest-processing-time-first on the cost iterations * n^3; inside a rank several sites are
+in flight at once, each on its own libdgp handle/stream (dgp_nlml_grad_launch / _wait), so that the latency-bound
+panel steps of one site overlap the trailing updates of the others.  The only collective is the final gather.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import capi
+from .engine import JITTERS, MIN_VARIANCE
+from .models import LOADEST_FIXED_NOISE, loadest_spec
+from .spec import GPModule
+
+
+def assign_sites(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Greedy LPT: sites sorted by decreasing cost, each to the least-loaded rank.  Deterministic on every rank."""
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    load = [0.0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += float(costs[i])
+    return out
+
+
+def site_cost(n: int, iterations: int, m_predict: int = 0) -> float:
+    """flop model of one site: iterations * n^3 (NLML+grad) + factorise + n^2 per predicted point."""
+    return float(iterations) * float(n) ** 3 + float(n) ** 3 + float(m_predict) * float(n) ** 2
+
+
+def gather_results(local: Dict[int, dict], dist=None) -> Optional[Dict[int, dict]]:
+    """All ranks -> rank 0.  `dist` is torch.distributed (initialised) or None for a single process."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return dict(local)
+    bucket = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(local, bucket, dst=0)
+    if dist.get_rank() != 0:
+        return None
+    merged: Dict[int, dict] = {}
+    for part in bucket:
+        merged.update(part)
+    return merged
+
+
+@dataclass
+class _SiteState:
+    idx: int
+    X: np.ndarray
+    y: np.ndarray
+    noise: np.ndarray
+    module: GPModule
+    engine: capi.Engine
+    opt: torch.optim.Optimizer
+    sched: Optional[torch.optim.lr_scheduler.ReduceLROnPlateau]
+    nat: Optional[torch.Tensor] = None
+    history: List[float] = field(default_factory=list)
+    failed: Optional[str] = None
+
+
+def _finish_step(s: _SiteState):
+    """Host side of one optimiser step (discontinuum/engines/gpytorch.py:353-420) once the GPU results are back."""
+    val, grad, info = s.engine.nlml_grad_wait()
+    if info != 0 or not np.isfinite(val):
+        th = s.nat.detach().numpy().astype(np.float64)
+        for jit in JITTERS[1:]:
+            val, grad, info = s.engine.nlml_grad(th, jit)
+            if info == 0 and np.isfinite(val):
+                break
+        else:
+            s.failed = f"not positive definite (info={info})"
+            return
+    n = s.X.shape[0]
+    g = torch.from_numpy(grad.copy())
+    nll = val + ((s.nat - s.nat.detach()) * g).sum()  # value = NLML, d/dnat = analytic gradient from the GPU
+    obj = (nll - s.module.log_prior(s.nat)) / n
+    obj.backward()
+    params = s.module.raw_list()
+    torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
+    for p in params:
+        if p.grad is not None and torch.isnan(p.grad).any():
+            p.grad = torch.nan_to_num(p.grad, nan=0.0, posinf=0.0, neginf=0.0)
+    s.opt.step()
+    s.history.append(float(obj.detach()))
+    if s.sched is not None:
+        s.sched.step(s.history[-1])
+
+
+def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int = 0, concurrency: int = 4,
+                    predict: Optional[Dict[int, np.ndarray]] = None, lr: float = 0.05, scheduler: bool = True,
+                    patience: int = 60) -> Dict[int, dict]:
+    """Fit the loadest-gp model on every site of this rank.  sites: {index: (X, y[, noise])} in model space.
+    Returns {index: {"theta", "objective", "history", "mu", "var"}}."""
+    results: Dict[int, dict] = {}
+    order = sorted(sites, key=lambda i: -sites[i][0].shape[0])
+    for start in range(0, len(order), concurrency):
+        group: List[_SiteState] = []
+        for idx in order[start:start + concurrency]:
+            tup = sites[idx]
+            X, y = np.ascontiguousarray(tup[0], dtype=np.float64), np.ascontiguousarray(tup[1], dtype=np.float64)
+            noise = np.ascontiguousarray(tup[2], dtype=np.float64) if len(tup) > 2 else np.full(y.shape[0], LOADEST_FIXED_NOISE)
+            module = GPModule(loadest_spec(X.shape[1]))
+            eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device)
+            eng.set_train(module.spec.to_c(), X, y, noise)
+            opt = torch.optim.Adam(module.raw_list(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+            sch = None
+            if scheduler:
+                sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.7, patience=max(20, patience // 2),
+                                                                 threshold=1e-4, threshold_mode="rel", min_lr=1e-6, cooldown=10)
+            group.append(_SiteState(idx, X, y, noise, module, eng, opt, sch))
+        for _ in range(iterations):
+            live = [s for s in group if s.failed is None]
+            for s in live:  # enqueue every site's evaluation, then collect: the GPU overlaps them
+                s.opt.zero_grad(set_to_none=True)
+                s.nat = s.module.natural()
+                s.engine.nlml_grad_launch(s.nat.detach().numpy().astype(np.float64))
+            for s in live:
+                _finish_step(s)
+        for s in group:
+            with torch.no_grad():
+                theta = s.module.natural().numpy().astype(np.float64)
+            res = {"theta": theta, "history": s.history, "objective": s.history[-1] if s.history else None, "failed": s.failed,
+                   "n": int(s.X.shape[0])}
+            if predict is not None and s.idx in predict and s.failed is None:
+                for jit in JITTERS:
+                    _, info = s.engine.factorize(theta, jit)
+                    if info == 0:
+                        break
+                mu, var = s.engine.predict(predict[s.idx])
+                res["mu"], res["var"] = mu, np.maximum(var, MIN_VARIANCE)
+            results[s.idx] = res
+            s.engine.close()
+    return results
+
+
+def fit_sites(sites: Dict[int, tuple], iterations: int = 100, predict: Optional[Dict[int, np.ndarray]] = None,
+              concurrency: int = 4, dist=None, device: int = 0) -> Optional[Dict[int, dict]]:
+    """Shard `sites` (every rank holds the same dict, or at least the same keys and sizes) over the ranks of
+    `dist`, fit this rank's share, gather everything on rank 0."""
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    keys = sorted(sites)
+    costs = [site_cost(sites[k][0].shape[0], iterations, predict[k].shape[0] if predict and k in predict else 0) for k in keys]
+    mine = [keys[i] for i in assign_sites(costs, world)[rank]]
+    local = fit_sites_local({k: sites[k] for k in mine}, iterations=iterations, device=device, concurrency=concurrency,
+                            predict={k: predict[k] for k in mine} if predict else None)
+    return gather_results(local, dist)

@@ -1,0 +1,74 @@
+"""Site sharding: CPU tests of the assignment and of the final gather with world_size = 2 on gloo, plus a GPU
+test that the concurrent multi-site driver reproduces single-site fits."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from discontinuum_b200 import multisite
+
+
+def test_assign_sites_lpt_balanced_and_complete():
+    rng = np.random.default_rng(42)
+    ns = (2000 + 6000 * rng.uniform(size=128)).astype(int)
+    costs = [multisite.site_cost(int(n), 100, 10958) for n in ns]
+    for world in (1, 2, 4, 8):
+        parts = multisite.assign_sites(costs, world)
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(128))
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) / (sum(loads) / world) < 1.05
+    assert multisite.assign_sites(costs, 4) == multisite.assign_sites(list(costs), 4)  # deterministic
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    costs = [float(c) for c in (9, 7, 5, 4, 3, 1)]
+    mine = multisite.assign_sites(costs, world)[rank]
+    local = {i: {"theta": np.full(3, float(i)), "rank": rank} for i in mine}
+    merged = multisite.gather_results(local, dist)
+    if rank == 0:
+        assert sorted(merged) == list(range(6))
+        assert all(np.array_equal(merged[i]["theta"], np.full(3, float(i))) for i in merged)
+        assert {merged[i]["rank"] for i in merged} == {0, 1}
+        open(os.path.join(out_dir, "ok"), "w").write("ok")
+    else:
+        assert merged is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_results_world2_gloo(tmp_path):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+@pytest.mark.gpu
+def test_concurrent_sites_match_single_site_fits(cuda_device):
+    from discontinuum_b200 import synthetic
+    import helpers as H
+    from helpers import orc
+
+    sites = {i: synthetic.loadest_site(n, 1000 + i)[:2] for i, n in enumerate((300, 450, 700))}
+    grid = {i: synthetic.daily_grid(sites[i][0], 200) for i in sites}
+    res = multisite.fit_sites(sites, iterations=8, predict=grid, concurrency=3)
+    assert sorted(res) == [0, 1, 2]
+    for i, (X, y) in sites.items():
+        raw = orc.loadest_init_raw()
+        _, hist = orc.fit_adam("loadest", raw, torch.tensor(X), torch.tensor(y), orc.loadest_noise(X.shape[0]), iterations=8)
+        assert res[i]["failed"] is None
+        assert np.max(np.abs(np.array(res[i]["history"]) - np.array(hist)) / np.abs(hist)) <= 1e-6
+        assert res[i]["mu"].shape == (200,) and np.all(res[i]["var"] > 0)
