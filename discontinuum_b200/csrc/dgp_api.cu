@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/dgp.h"
 #include "dgp_cov.cuh"
@@ -49,8 +50,12 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct dgp_handle_s {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;     // trailing updates and everything outside the factorisation
+  cudaStream_t stream_hi = nullptr;  // look-ahead: diagonal block + panel solve of the next block column (high priority)
   bool own_stream = false;
+  std::vector<cudaEvent_t> evs;      // look-ahead dependencies (no timing)
+  bool lookahead = true;
+  int panel_blocks = 4;              // block columns per panel of the two-level Cholesky
   int max_n = 0, max_pad = 0, max_m = 0;
   int n = 0, npad = 0, nb = 0;
   bool have_train = false, factorized = false, have_T = false, debug_kinv = false, timing = false;
@@ -58,7 +63,7 @@ struct dgp_handle_s {
   // device buffers
   double *bufA = nullptr, *bufL = nullptr, *bufU = nullptr, *DI = nullptr;
   double *X = nullptr, *y = nullptr, *noise = nullptr, *Xw = nullptr, *r = nullptr, *z = nullptr, *alpha = nullptr;
-  double *theta = nullptr, *scal = nullptr, *gpart = nullptr;
+  double *theta = nullptr, *scal = nullptr, *gpart = nullptr, *zpart = nullptr;
   // prediction chunk
   double *Kx = nullptr, *Xs = nullptr, *Xws = nullptr, *means = nullptr, *dot = nullptr, *vpart = nullptr;
   double *mu = nullptr, *var = nullptr;
@@ -101,8 +106,10 @@ static int make_map(dgp_handle h, CUtensorMap* m, double* base, int rows, int co
 }
 
 template <int INIT, int EPI>
-static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g) {
+static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g,
+                       cudaStream_t st = nullptr) {
   if (g.ntiles <= 0) return 0;
+  if (st == nullptr) st = h->stream;
   static bool attr_set = false;
   static int smem_bytes = SM_TOTAL;
   if (!attr_set) {
@@ -111,7 +118,7 @@ static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b,
     CK(h, cudaFuncSetAttribute(k_gemm<INIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
-  k_gemm<INIT, EPI><<<g.ntiles, GEMM_THREADS, smem_bytes, h->stream>>>(a, b, h->spec, g);
+  k_gemm<INIT, EPI><<<g.ntiles, GEMM_THREADS, smem_bytes, st>>>(a, b, h->spec, g);
   h->launches++;
   CK(h, cudaGetLastError());
   return 0;
@@ -126,7 +133,7 @@ size_t dgp_workspace_bytes(int max_n, int max_m) {
   const size_t mc = round_up(max_m > 0 ? max_m : 2048, 128);
   const size_t nb = np / 128;
   size_t b = 3 * np * np * 8 + np * 128 * 8;
-  b += nb * (nb + 1) * DGP_MAX_THETA * 8;
+  b += nb * (nb + 1) * DGP_MAX_THETA * 8 + nb * np * 8;
   b += mc * np * 8 + (nb + 2 * nb) * mc * 8;
   return b;
 }
@@ -153,6 +160,15 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
   h->max_m = round_up(max_m > 0 ? max_m : 2048, 128);
   if (stream) { h->stream = (cudaStream_t)stream; }
   else { cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking); h->own_stream = true; }
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, hi);
+    const char* la = getenv("DGP_LOOKAHEAD");
+    if (la) h->lookahead = atoi(la) != 0;
+    const char* pb = getenv("DGP_PANEL_BLOCKS");
+    if (pb && atoi(pb) >= 1 && atoi(pb) <= 64) h->panel_blocks = atoi(pb);
+  }
   const size_t np = h->max_pad, mc = h->max_m, nbm = np / 128;
   auto A = [&](double** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(double)); };
   cudaError_t r = cudaSuccess;
@@ -161,6 +177,7 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
   acc(A(&h->X, np * DGP_MAX_COLS)); acc(A(&h->y, np)); acc(A(&h->noise, np)); acc(A(&h->Xw, np * DGP_XS));
   acc(A(&h->r, np)); acc(A(&h->z, np)); acc(A(&h->alpha, np));
   acc(A(&h->theta, DGP_MAX_THETA)); acc(A(&h->scal, SC_SIZE)); acc(A(&h->gpart, nbm * (nbm + 1) * DGP_MAX_THETA));
+  acc(A(&h->zpart, nbm * np));
   acc(A(&h->Kx, mc * np)); acc(A(&h->Xs, mc * DGP_MAX_COLS)); acc(A(&h->Xws, mc * DGP_XS)); acc(A(&h->means, mc));
   acc(A(&h->dot, nbm * mc)); acc(A(&h->vpart, 2 * nbm * mc)); acc(A(&h->mu, mc)); acc(A(&h->var, mc));
   acc(cudaMallocHost((void**)&h->h_theta, DGP_MAX_THETA * sizeof(double)));
@@ -180,8 +197,10 @@ int dgp_destroy(dgp_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream_hi) { cudaStreamSynchronize(h->stream_hi); cudaStreamDestroy(h->stream_hi); }
+  for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   double* bufs[] = {h->bufA, h->bufL, h->bufU, h->DI, h->X, h->y, h->noise, h->Xw, h->r, h->z, h->alpha, h->theta,
-                    h->scal, h->gpart, h->Kx, h->Xs, h->Xws, h->means, h->dot, h->vpart, h->mu, h->var};
+                    h->scal, h->gpart, h->zpart, h->Kx, h->Xs, h->Xws, h->means, h->dot, h->vpart, h->mu, h->var};
   for (double* p : bufs) if (p) cudaFree(p);
   if (h->h_theta) cudaFreeHost(h->h_theta);
   if (h->h_scal) cudaFreeHost(h->h_scal);
@@ -291,69 +310,130 @@ struct CholBufs {
   long long ld;
 };
 
+static int ensure_events(dgp_handle h, size_t count) {
+  while (h->evs.size() < count) {
+    cudaEvent_t e;
+    CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->evs.push_back(e);
+  }
+  return 0;
+}
+
+// Two-level right-looking Cholesky with look-ahead.  Block columns are grouped in panels of `pw` blocks.
+// Stream P (high priority) runs the latency-bound work of one panel, block column by block column:
+//   potf2(s) -> TRSM(s) (all rows below) [-> forward substitution(s)] -> rank-128 update of the panel's own
+//   remaining columns.
+// Stream T runs the throughput-bound rank-(128 pw) update of everything right of the panel, split in two
+// launches: the next panel's columns first (all panel p+1 reads), then the rest, which overlaps panel p+1 on P.
+// The wide update reads/writes each trailing tile once per panel instead of once per block column.
 static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jitter, bool fwd) {
   const int nb = b.nb;
   const long long ld = b.ld;
   int rc;
+  cudaStream_t T = h->stream, P = h->lookahead ? h->stream_hi : h->stream;
+  const int pw = h->panel_blocks;
+  const int npanels = (nb + pw - 1) / pw;
+  if ((rc = ensure_events(h, 2 * (size_t)npanels + 2))) return rc;
+  auto ev_panel = [&](int p) { return h->evs[2 * p]; };
+  auto ev_cols = [&](int p) { return h->evs[2 * p + 1]; };
+  auto trail = [&](int mode, int k0, int kb, int o, int w, int ntiles, bool first_touch, cudaStream_t st) {
+    GemmArgs g = base_args(h, mode, k0);
+    g.nb = nb; g.ldc = ld;
+    g.aux0 = (mode == M_TRAIL_COL) ? (o | (w << 16)) : o;
+    g.aux1 = kb;
+    g.aux2 = first_touch ? 0 : 1;
+    g.C = b.A; g.ntiles = ntiles; g.sign = -1.0; g.jitter = jitter;
+    if (first_touch) return launch_gemm<INIT_COV, EPI_STORE>(h, *b.tL, *b.tL, g, st);
+    return launch_gemm<INIT_LOAD, EPI_STORE>(h, *b.tL, *b.tL, g, st);
+  };
   if (generate) {
-    k_cov_rect<<<dim3(nb * 4, 1), 256, 0, h->stream>>>(h->spec, h->theta, h->Xw, h->Xw, h->noise, jitter, b.A, ld, h->n,
-                                                       h->n, 1, 1, nullptr, nullptr, 0);
+    k_cov_rect<<<dim3(nb * 4, 1), 256, 0, T>>>(h->spec, h->theta, h->Xw, h->Xw, h->noise, jitter, b.A, ld, h->n,
+                                               h->n, 1, 1, nullptr, nullptr, 0);
     h->launches++;
     CK(h, cudaGetLastError());
   }
-  for (int s = 0; s < nb; s++) {
-    const size_t off = (size_t)s * 128 * ld + (size_t)s * 128;
-    k_potf2<<<1, PF_THREADS, PF_SMEM, h->stream>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
-                                                   b.DI + (size_t)s * 128 * 128, b.scal, s * 128);
-    h->launches++;
-    CK(h, cudaGetLastError());
-    const int m = nb - s - 1;
-    if (m > 0) {
-      GemmArgs g = base_args(h, M_TRSM, s);
-      g.nb = nb; g.ldc = ld;
-      g.C = b.L; g.ntiles = 2 * m;
-      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, *b.tA, *b.tDI, g))) return rc;
-    }
-    if (fwd) {
-      k_fwd_step<<<nb - s, 256, 0, h->stream>>>(b.L, ld, b.DI, h->r, h->z, s);
+  if (P != T) {
+    CK(h, cudaEventRecord(ev_cols(0), T));
+    CK(h, cudaStreamWaitEvent(P, ev_cols(0), 0));
+  }
+  for (int p = 0; p < npanels; p++) {
+    const int pb = p * pw, pe = (pb + pw < nb) ? pb + pw : nb;
+    if (P != T && p > 0) CK(h, cudaStreamWaitEvent(P, ev_cols(p), 0));
+    for (int s = pb; s < pe; s++) {
+      const size_t off = (size_t)s * 128 * ld + (size_t)s * 128;
+      k_potf2<<<1, PF_THREADS, PF_SMEM, P>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
+                                             b.DI + (size_t)s * 128 * 128, b.scal, s * 128, b.A + off);
       h->launches++;
       CK(h, cudaGetLastError());
+      const int m = nb - s - 1;
+      if (m > 0) {
+        GemmArgs g = base_args(h, M_TRSM, s);
+        g.nb = nb; g.ldc = ld;
+        g.C = b.L; g.ntiles = 2 * m;
+        if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, *b.tA, *b.tDI, g, P))) return rc;
+      }
+      if (fwd) {
+        k_fwd_step<<<nb - s, 256, 0, P>>>(b.L, ld, b.DI, h->r, h->z, s);
+        h->launches++;
+        CK(h, cudaGetLastError());
+      }
+      if (s + 1 < pe) {  // in-panel rank-128 update: block columns (s, pe), rows >= s + 1
+        const int w = pe - s - 1;
+        if ((rc = trail(M_TRAIL_COL, s, 1, s + 1, w, m * 2 * w, generate && s == 0, P))) return rc;
+      }
     }
-    if (m > 0) {
-      GemmArgs g = base_args(h, M_TRAIL, s);
-      g.nb = nb; g.ldc = ld;
-      g.C = b.A; g.ntiles = m * (m + 1); g.sign = -1.0; g.jitter = jitter;
-      g.aux2 = generate ? 0 : 1;
-      if (s == 0 && generate) rc = launch_gemm<INIT_COV, EPI_STORE>(h, *b.tL, *b.tL, g);
-      else rc = launch_gemm<INIT_LOAD, EPI_STORE>(h, *b.tL, *b.tL, g);
-      if (rc) return rc;
+    if (P != T) {
+      CK(h, cudaEventRecord(ev_panel(p), P));
+      CK(h, cudaStreamWaitEvent(T, ev_panel(p), 0));
+    }
+    if (pe < nb) {  // rank-(128 (pe - pb)) update right of the panel: next panel's columns, then the rest
+      const int ne = (pe + pw < nb) ? pe + pw : nb, w = ne - pe, m = nb - pe;
+      if ((rc = trail(M_TRAIL_COL, pb, pe - pb, pe, w, m * 2 * w, generate && p == 0, T))) return rc;
+      if (P != T) CK(h, cudaEventRecord(ev_cols(p + 1), T));
+      const int m2 = nb - ne;
+      if (m2 > 0 && (rc = trail(M_TRAIL, pb, pe - pb, ne, 0, m2 * (m2 + 1), generate && p == 0, T))) return rc;
     }
   }
   return 0;
 }
 
-static int run_potrf(dgp_handle h, double jitter) {
+static int run_potrf(dgp_handle h, double jitter, bool fwd) {
   CholBufs b{h->bufA, h->bufL, h->bufU, h->DI, h->scal, &h->tmA, &h->tmL, &h->tmDI, h->nb, h->npad};
-  return potrf_core(h, b, true, jitter, true);
+  return potrf_core(h, b, true, jitter, fwd);
 }
 
-static int run_trtri(dgp_handle h) {
+// U = L^-T (upper) by recursive doubling: the diagonal 128-blocks come from k_potf2 (U_ss in bufU, T_ss = L_ss^-1 in
+// the diagonal blocks of bufA); level h merges neighbouring block ranges [o, o+h) | [o+h, o+2h):
+//   M'  = U11 L21'          -> scratch, upper triangle of bufA          (long-K tiles, no read-modify-write)
+//   U12 = -M' T22'          -> bufU
+//   T21 = U12'              -> lower triangle of bufA (operand of the next level / of the prediction kernels)
+// log2(nb) levels x 3 launches instead of 2 nb launches of rank-128 updates.  want_T: also transpose the last level.
+static int run_trtri(dgp_handle h, bool want_T) {
   const int nb = h->nb;
   int rc;
-  for (int s = 0; s < nb; s++) {
-    if (s >= 1) {
-      GemmArgs g = base_args(h, M_TRI_FINAL, s);
-      g.C = h->bufU; g.ntiles = 2 * s; g.sign = -1.0;
-      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmA, h->tmDI, g))) return rc;
+  for (int hb = 1; hb < nb; hb *= 2) {
+    const int npairs = (nb - hb + 2 * hb - 1) / (2 * hb);  // pairs whose second range is non-empty
+    {
+      GemmArgs g = base_args(h, M_INV_M, 0);
+      g.aux0 = hb; g.aux1 = npairs; g.C = h->bufA; g.ntiles = npairs * hb * 2 * hb;
+      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmU, h->tmL, g))) return rc;
     }
-    if (s < nb - 1) {
-      GemmArgs g = base_args(h, M_TRI_UPDATE, s);
-      g.C = h->bufA; g.ntiles = (s + 1) * 2 * (nb - s - 1);
-      if ((rc = launch_gemm<INIT_LOAD, EPI_STORE>(h, h->tmU, h->tmL, g))) return rc;
+    {
+      GemmArgs g = base_args(h, M_INV_U, 0);
+      g.aux0 = hb; g.aux1 = npairs; g.C = h->bufU; g.ntiles = npairs * hb * 2 * hb; g.sign = -1.0;
+      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmA, h->tmA, g))) return rc;
+    }
+    if (want_T || 2 * hb < nb) {
+      k_transpose_pairs<<<npairs * 16 * hb * hb, 256, 0, h->stream>>>(h->bufU, h->bufA, h->npad, hb, h->npad);
+      h->launches++;
+      CK(h, cudaGetLastError());
     }
   }
+  // z = U' r (= L^-1 r), alpha = U z
+  k_upperT_gemv_part<<<dim3(nb, nb), 256, 0, h->stream>>>(h->bufU, h->npad, h->r, h->zpart, h->npad);
+  k_upperT_gemv_sum<<<(h->npad + 255) / 256, 256, 0, h->stream>>>(h->zpart, h->npad, h->z, h->npad);
   k_upper_gemv<<<h->npad / 8, 256, 0, h->stream>>>(h->bufU, h->npad, h->z, h->alpha, h->npad);
-  h->launches++;
+  h->launches += 3;
   CK(h, cudaGetLastError());
   return 0;
 }
@@ -385,18 +465,13 @@ static int evaluate_launch(dgp_handle h, const double* theta, double jitter, int
   if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
   if ((rc = upload_theta(h, theta))) return rc;
   if ((rc = run_features(h))) return rc;
-  if ((rc = run_potrf(h, jitter))) return rc;
+  if ((rc = run_potrf(h, jitter, level == 0))) return rc;  // level >= 1: z = U'r after the inverse instead
   if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
   if (level >= 1) {
-    if ((rc = run_trtri(h))) return rc;
+    if ((rc = run_trtri(h, level == 2))) return rc;
     if (h->timing) CK(h, cudaEventRecord(h->ev[2], h->stream));
     if (level == 1) {
       if ((rc = run_lauum_grad(h))) return rc;
-    } else {
-      dim3 grid(h->npad / 32, h->npad / 32);
-      k_transpose_upper<<<grid, 256, 0, h->stream>>>(h->bufU, h->bufA, h->npad);
-      h->launches++;
-      CK(h, cudaGetLastError());
     }
     if (h->timing) CK(h, cudaEventRecord(h->ev[3], h->stream));
   }

@@ -26,7 +26,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_THREADS = 160;      // 4 consumer warps + 1 producer warp
 constexpr int WS = BN + 1;             // padded row stride of the W tile in the grad epilogue
 
-enum { M_TRSM = 0, M_TRAIL = 1, M_TRI_FINAL = 2, M_TRI_UPDATE = 3, M_LAUUM = 4, M_PREDVAR = 5, M_GENERIC = 6 };
+enum { M_TRSM = 0, M_TRAIL = 1, M_TRAIL_COL = 2, M_INV_M = 3, M_LAUUM = 4, M_PREDVAR = 5, M_GENERIC = 6, M_INV_U = 7 };
 enum { INIT_ZERO = 0, INIT_LOAD = 1, INIT_COV = 2 };
 enum { EPI_STORE = 0, EPI_GRAD = 1, EPI_SUMSQ = 2 };
 
@@ -49,6 +49,7 @@ struct Job {
   int rowA, kA, rowB, kB, nk;   // operand panel origins (elements) and number of 16-wide k steps
   int crow, ccol;               // output tile origin
   int init;                     // INIT_* actually used by this tile
+  int valid;                    // 0: tile index falls outside the (ragged) problem, the CTA exits
 };
 
 __device__ __forceinline__ int isqrt_floor(int x) {
@@ -61,6 +62,7 @@ __device__ __forceinline__ int isqrt_floor(int x) {
 __device__ __forceinline__ Job decode_job(const GemmArgs& g, int tile, int init_default) {
   Job j;
   j.init = init_default;
+  j.valid = 1;
   const int s = g.step;
   switch (g.mode) {
     case M_TRSM: {  // L[i, s] = A[i, s] * Linv_s^T            A: work panel, B: diagonal-inverse table
@@ -70,31 +72,46 @@ __device__ __forceinline__ Job decode_job(const GemmArgs& g, int tile, int init_
       j.nk = h ? 8 : 4;
       j.crow = i * 128; j.ccol = s * 128 + h * 64;
     } break;
-    case M_TRAIL: {  // A[i, c] -= L[i, s] L[c, s]^T  for s < c-block <= i
+    case M_TRAIL: {  // A[i, c] -= L[i, K] L[c, K]^T, K = block columns [step, step + aux1); lower triangle of the
+                     // trailing matrix with origin block o = aux0: rows i = o + ip, 64-col blocks c = 2 o + cp <= row
+      const int o = g.aux0;
       const int ip = (isqrt_floor(4 * tile + 1) - 1) >> 1;
       const int cp = tile - ip * (ip + 1);
-      const int i = s + 1 + ip, c = 2 * (s + 1) + cp;
+      const int i = o + ip, c = 2 * o + cp;
       j.rowA = i * 128; j.kA = s * 128;
       j.rowB = c * 64; j.kB = s * 128;
-      j.nk = 8;
+      j.nk = 8 * g.aux1;
       j.crow = i * 128; j.ccol = c * 64;
-      j.init = (s == 0 && g.aux2 == 0) ? INIT_COV : INIT_LOAD;  // aux2 = 1: matrix supplied, nothing to generate
+      j.init = g.aux2 ? INIT_LOAD : INIT_COV;  // aux2 = 0: first touch of these tiles, generate the covariance
     } break;
-    case M_TRI_FINAL: {  // U[i, s] = -S[i, s] * Linv_s^T   for i < s
-      const int i = tile >> 1, h = tile & 1;
-      j.rowA = i * 128; j.kA = s * 128;
-      j.rowB = s * 128 + h * 64; j.kB = 0;
-      j.nk = h ? 8 : 4;
-      j.crow = i * 128; j.ccol = s * 128 + h * 64;
-    } break;
-    case M_TRI_UPDATE: {  // S[i, c] += U[i, s] L[c, s]^T  for i <= s < c-block
-      const int ncb = 2 * (g.nb - s - 1);
-      const int i = tile / ncb, c = 2 * (s + 1) + tile % ncb;
+    case M_TRAIL_COL: {  // the same update on the block columns [o, o + w) only (w = ntiles-independent, in g.latent's
+                         // place: aux0 = o | (w << 16)): rows i >= o, tiles above the diagonal exit
+      const int o = g.aux0 & 0xffff, w2 = 2 * (g.aux0 >> 16);
+      const int i = o + tile / w2, c = 2 * o + tile % w2;
+      j.valid = c <= 2 * i + 1;
       j.rowA = i * 128; j.kA = s * 128;
       j.rowB = c * 64; j.kB = s * 128;
-      j.nk = 8;
+      j.nk = 8 * g.aux1;
       j.crow = i * 128; j.ccol = c * 64;
-      j.init = (i == s) ? INIT_ZERO : INIT_LOAD;
+      j.init = g.aux2 ? INIT_LOAD : INIT_COV;
+    } break;
+    case M_INV_M:    // recursive triangular inverse, merge of block ranges [o, o+h) and [o+h, o+2h):
+    case M_INV_U: {  //   M' = U11 L21'  (M_INV_M, scratch in the upper triangle of the work matrix)
+                     //   U12 = -M' T22' (M_INV_U), T = L^-1 lower, U = T' upper.  aux0 = h, aux1 = pairs at this level
+      const int hb = g.aux0, np_ = g.aux1;
+      const int pr = tile % np_, w = tile / np_;
+      const int o = pr * 2 * hb;
+      int jb, ic;
+      if (g.mode == M_INV_M) { jb = w / (2 * hb); ic = w % (2 * hb); }
+      else { ic = 2 * hb - 1 - w / hb; jb = w % hb; }
+      const int cb64 = 2 * (o + hb) + ic;
+      j.valid = cb64 < 2 * g.nb;
+      j.rowA = (o + jb) * 128;
+      j.rowB = cb64 * 64;
+      if (g.mode == M_INV_M) { j.kA = (o + jb) * 128; j.nk = (hb - jb) * 8; }
+      else { j.kA = (o + hb) * 128; j.nk = (ic + 1) * 4; }
+      j.kB = j.kA;
+      j.crow = j.rowA; j.ccol = j.rowB;
     } break;
     case M_LAUUM: {  // Kinv[i, c] = sum_{k >= i} U[i, k] U[c, k]^T  (lower tiles, longest K first)
       const int i = (isqrt_floor(4 * tile + 1) - 1) >> 1;
@@ -189,6 +206,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Job job = decode_job(g, blockIdx.x, INIT);
+  if (!job.valid) return;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }

@@ -140,18 +140,30 @@ __device__ __forceinline__ void potf2_trailing(double* As, const double* Pn, int
   }
 }
 
+// Tblk (optional, may alias Ablk: the block is fully staged in shared memory before anything is written) receives
+// L^-1 as a full 128x128 block (zeros above the diagonal): the diagonal block of T for the recursive inverse.
 __global__ void __launch_bounds__(PF_THREADS, 1)
-k_potf2(const double* __restrict__ Ablk, double* __restrict__ Lblk, double* __restrict__ Ublk, long long ld,
-        double* __restrict__ DIblk, double* __restrict__ scal, int base) {
+k_potf2(const double* Ablk, double* __restrict__ Lblk, double* __restrict__ Ublk, long long ld,
+        double* __restrict__ DIblk, double* __restrict__ scal, int base, double* Tblk) {
   extern __shared__ double pf_smem[];
   double* As = pf_smem;
   double* Pn = As + 128 * PF_AS;
   double* rd = Pn + 256 * PF_PN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int e = tid; e < 128 * 128; e += PF_THREADS) {
-    const int r = e >> 7, c = e & 127;
-    As[r * PF_AS + c] = (c <= r) ? Ablk[(size_t)r * ld + c] : 0.0;
+#pragma unroll 1
+  for (int e0 = 0; e0 < 128 * 128; e0 += PF_THREADS * 16) {  // 16 independent loads in flight per thread
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int e = e0 + u * PF_THREADS + tid, r = e >> 7, c = e & 127;
+      v[u] = (c <= r) ? Ablk[(size_t)r * ld + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int e = e0 + u * PF_THREADS + tid, r = e >> 7, c = e & 127;
+      As[r * PF_AS + c] = v[u];
+    }
   }
   __syncthreads();
 
@@ -167,8 +179,8 @@ k_potf2(const double* __restrict__ Ablk, double* __restrict__ Lblk, double* __re
       for (int c = 0; c < 32; c++) {
         const double d = __shfl_sync(0xffffffffu, a[c], c);
         if (!(d > 0.0) && lane == 0 && scal[SC_INFO] == 0.0) scal[SC_INFO] = (double)(base + o + c + 1);
-        const double l = sqrt(d);
-        const double inv = 1.0 / l;
+        const double inv = rsqrt(d);  // one MUFU + Newton chain instead of sqrt followed by a division
+        const double l = d * inv;
         if (lane == c) { a[c] = l; myinv = inv; }
         if (lane > c) a[c] *= inv;
 #pragma unroll
@@ -221,7 +233,9 @@ k_potf2(const double* __restrict__ Ablk, double* __restrict__ Lblk, double* __re
     const double lv = As[r * PF_AS + c];
     Lblk[(size_t)r * ld + c] = (c <= r) ? lv : 0.0;
     if (Ublk != nullptr) Ublk[(size_t)r * ld + c] = (c > r) ? lv : (c == r ? rd[r] : 0.0);
-    DIblk[r * 128 + c] = (c < r) ? As[c * PF_AS + r] : (c == r ? rd[r] : 0.0);
+    const double tv = (c < r) ? As[c * PF_AS + r] : (c == r ? rd[r] : 0.0);
+    DIblk[r * 128 + c] = tv;
+    if (Tblk != nullptr) Tblk[(size_t)r * ld + c] = tv;
   }
   if (warp == 0) {
     double s = 0.0;
@@ -287,23 +301,57 @@ k_upper_gemv(const double* __restrict__ U, long long ld, const double* __restric
   if (lane == 0) out[row] = acc;
 }
 
-// ------------------------------------------------------------------ T = U^T (lower), 32x32 tiles through smem
-// grid = (npad/32, npad/32).  Source tiles on/above the diagonal (bx >= by) are transposed into the lower
-// triangle of T; T tiles above the diagonal but inside a diagonal 128-block are zeroed, because the
-// variance GEMM reads whole 64-column k-blocks of T.
+// ------------------------------------------------------------------ z = U^T r  (U upper triangular), two stages
+// stage 1: grid = (nb, nb); CTA (cb, rb) with rb <= cb sums rows of row block rb for the 128 columns of block cb
+// into part[rb][col]; stage 2 adds the row-block partials in a fixed order.
 __global__ void __launch_bounds__(256)
-k_transpose_upper(const double* __restrict__ U, double* __restrict__ T, long long ld) {
-  __shared__ double tile[32][33];
-  const int bx = blockIdx.x, by = blockIdx.y;  // source tile (row block by, col block bx)
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  if (bx < by) {
-    if ((bx >> 2) == (by >> 2))
-      for (int r = ty; r < 32; r += 8) T[(size_t)(bx * 32 + r) * ld + by * 32 + tx] = 0.0;
-    return;
-  }
-  for (int r = ty; r < 32; r += 8) tile[r][tx] = U[(size_t)(by * 32 + r) * ld + bx * 32 + tx];
+k_upperT_gemv_part(const double* __restrict__ U, long long ld, const double* __restrict__ r, double* __restrict__ part,
+                   long long ldp) {
+  const int cb = blockIdx.x, rb = blockIdx.y;
+  if (rb > cb) return;
+  __shared__ double rs[128];
+  __shared__ double hs[128];
+  const int tid = threadIdx.x, col = tid & 127, half = tid >> 7;
+  if (tid < 128) rs[tid] = r[rb * 128 + tid];
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) T[(size_t)(bx * 32 + r) * ld + by * 32 + tx] = tile[tx][r];
+  const double* up = U + (size_t)(rb * 128 + half * 64) * ld + cb * 128 + col;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < 64; i += 4) {
+    a0 = fma(up[(size_t)(i + 0) * ld], rs[half * 64 + i + 0], a0);
+    a1 = fma(up[(size_t)(i + 1) * ld], rs[half * 64 + i + 1], a1);
+    a2 = fma(up[(size_t)(i + 2) * ld], rs[half * 64 + i + 2], a2);
+    a3 = fma(up[(size_t)(i + 3) * ld], rs[half * 64 + i + 3], a3);
+  }
+  const double acc = (a0 + a1) + (a2 + a3);
+  if (half == 1) hs[col] = acc;
+  __syncthreads();
+  if (half == 0) part[(size_t)rb * ldp + cb * 128 + col] = acc + hs[col];
+}
+
+__global__ void __launch_bounds__(256)
+k_upperT_gemv_sum(const double* __restrict__ part, long long ldp, double* __restrict__ z, int npad) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= npad) return;
+  double s = 0.0;
+  for (int rb = 0; rb <= (j >> 7); rb++) s += part[(size_t)rb * ldp + j];
+  z[j] = s;
+}
+
+// ------------------------------------------------------------------ T21 = U12^T for every pair of one merge level
+// Pair p merges block ranges [o, o+h) and [o+h, o+2h), o = 2 h p.  grid.x = pairs * (4h)^2 tiles of 32x32.
+__global__ void __launch_bounds__(256)
+k_transpose_pairs(const double* __restrict__ U, double* __restrict__ T, long long ld, int hb, int npad) {
+  __shared__ double tile[32][33];
+  const int per = 16 * hb * hb;
+  const int pr = blockIdx.x / per, rem = blockIdx.x % per;
+  const int ty32 = rem / (4 * hb), tx32 = rem % (4 * hb);
+  const int r0 = pr * 2 * hb * 128 + ty32 * 32, c0 = (pr * 2 * hb + hb) * 128 + tx32 * 32;
+  if (c0 >= npad) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = U[(size_t)(r0 + r) * ld + c0 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) T[(size_t)(c0 + r) * ld + r0 + tx] = tile[tx][r];
 }
 
 // ------------------------------------------------------------------ final reductions (deterministic order)
