@@ -232,6 +232,211 @@ __device__ __forceinline__ void term_grad_accum(const TermC& tc, const double* x
   }
 }
 
+// ------------------------------------------------------------------ V-wide evaluators (the fast path)
+// One "own" point A (per-thread, features read from a column-major shared array xaT[col * a_stride + a_idx]) against
+// V "other" points B (the same for every thread of the warp: broadcast reads of row-major rows xb + v * DGP_XS).
+// All the exponentials of a term are merged, term = scale * gate * prod_f poly_f * exp(-sum_f expo_f):
+//   RBF: poly 1, expo d2/2 | Matern32: poly 1 + a, expo a = sqrt(3 d2) | Matern52: poly 1 + a + a^2/3, expo a = sqrt(5 d2)
+//   Periodic: poly 1, expo 2 sin^2(pi dx / p) / lam   (sinpi: exact range reduction, no slow path)
+// and the V entries are evaluated side by side so that the FP64 pipe sees V independent dependency chains.
+__device__ __forceinline__ double fast_sqrt_nonneg(double d2) {
+  return d2 > 0.0 ? d2 * rsqrt(d2) : 0.0;
+}
+
+template <int V>
+__device__ __forceinline__ void cov_vals(const CovC* cc, const double* __restrict__ xaT, int a_stride, int a_idx,
+                                         const double* __restrict__ xb, double (&out)[V]) {
+#pragma unroll
+  for (int v = 0; v < V; v++) out[v] = 0.0;
+  for (int t = 0; t < cc->nterms; t++) {
+    const TermC& tc = cc->t[t];
+    double P[V], EX[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) { P[v] = tc.scale; EX[v] = 0.0; }
+    if (tc.gate != DGP_GATE_NONE) {
+      double ga = xaT[tc.gate_col * a_stride + a_idx];
+      if (tc.gate == DGP_GATE_INV_SIGMOID) ga = 1.0 - ga;
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        double gb = xb[v * DGP_XS + tc.gate_col];
+        if (tc.gate == DGP_GATE_INV_SIGMOID) gb = 1.0 - gb;
+        P[v] *= ga * gb;
+      }
+    }
+    for (int f = 0; f < tc.nf; f++) {
+      const FactorC& fc = tc.f[f];
+      if (fc.kind == DGP_PERIODIC) {
+        const double xa = xaT[fc.col[0] * a_stride + a_idx];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          const double sn = sinpi((xa - xb[v * DGP_XS + fc.col[0]]) * fc.inv_p);
+          EX[v] = fma(2.0 * fc.inv_lam * sn, sn, EX[v]);
+        }
+      } else {
+        double d2[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) d2[v] = 0.0;
+        for (int d = 0; d < fc.ndims; d++) {
+          const double xa = xaT[fc.col[d] * a_stride + a_idx];
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const double z = (xa - xb[v * DGP_XS + fc.col[d]]) * fc.inv_ls[d];
+            d2[v] = fma(z, z, d2[v]);
+          }
+        }
+        if (fc.kind == DGP_RBF) {
+#pragma unroll
+          for (int v = 0; v < V; v++) EX[v] = fma(0.5, d2[v], EX[v]);
+        } else if (fc.kind == DGP_MATERN32) {
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const double a = 1.7320508075688772 * fast_sqrt_nonneg(d2[v]);
+            P[v] *= 1.0 + a;
+            EX[v] += a;
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const double a = 2.23606797749979 * fast_sqrt_nonneg(d2[v]);
+            P[v] *= fma(a, fma(a, 1.0 / 3.0, 1.0), 1.0);
+            EX[v] += a;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < V; v++) out[v] = fma(P[v], exp(-EX[v]), out[v]);
+  }
+}
+
+// Accumulate w[v] * d(term)/d(param) over V entries into acc[NSLOT] (same slot layout as term_grad_accum).
+template <int V>
+__device__ __forceinline__ void term_grad_accum_v(const TermC& tc, const double* __restrict__ xaT, int a_stride, int a_idx,
+                                                  const double* __restrict__ xb, const double (&w)[V], double (&acc)[NSLOT]) {
+  double G[V], dG[V], EX[V];
+  double poly[DGP_MAX_FACTORS][V], aux[DGP_MAX_FACTORS][V];  // aux: Matern a | periodic sin*cos*u
+#pragma unroll
+  for (int v = 0; v < V; v++) { G[v] = 1.0; dG[v] = 0.0; EX[v] = 0.0; }
+  if (tc.gate != DGP_GATE_NONE) {
+    double ga = xaT[tc.gate_col * a_stride + a_idx];
+    double sgn = tc.gate_a;
+    if (tc.gate == DGP_GATE_INV_SIGMOID) { ga = 1.0 - ga; sgn = -sgn; }
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      double gb = xb[v * DGP_XS + tc.gate_col];
+      if (tc.gate == DGP_GATE_INV_SIGMOID) gb = 1.0 - gb;
+      G[v] = ga * gb;
+      dG[v] = sgn * G[v] * (2.0 - ga - gb);
+    }
+  }
+  // pass 1: polynomial parts and the merged exponent
+#pragma unroll
+  for (int f = 0; f < DGP_MAX_FACTORS; f++) {
+#pragma unroll
+    for (int v = 0; v < V; v++) { poly[f][v] = 1.0; aux[f][v] = 0.0; }
+    if (f < tc.nf) {
+      const FactorC& fc = tc.f[f];
+      if (fc.kind == DGP_PERIODIC) {
+        const double xa = xaT[fc.col[0] * a_stride + a_idx];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          const double x = (xa - xb[v * DGP_XS + fc.col[0]]) * fc.inv_p;
+          double sn, cs;
+          sincospi(x, &sn, &cs);
+          EX[v] = fma(2.0 * fc.inv_lam * sn, sn, EX[v]);
+          aux[f][v] = sn * cs * x;  // u / pi, folded into the period slot below
+          poly[f][v] = sn * sn;     // reused for the lam slot (the factor's polynomial part is 1)
+        }
+      } else {
+        double d2[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) d2[v] = 0.0;
+        for (int d = 0; d < fc.ndims; d++) {
+          const double xa = xaT[fc.col[d] * a_stride + a_idx];
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const double z = (xa - xb[v * DGP_XS + fc.col[d]]) * fc.inv_ls[d];
+            d2[v] = fma(z, z, d2[v]);
+          }
+        }
+        if (fc.kind == DGP_RBF) {
+#pragma unroll
+          for (int v = 0; v < V; v++) EX[v] = fma(0.5, d2[v], EX[v]);
+        } else if (fc.kind == DGP_MATERN32) {
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const double a = 1.7320508075688772 * fast_sqrt_nonneg(d2[v]);
+            poly[f][v] = 1.0 + a; aux[f][v] = a; EX[v] += a;
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const double a = 2.23606797749979 * fast_sqrt_nonneg(d2[v]);
+            poly[f][v] = fma(a, fma(a, 1.0 / 3.0, 1.0), 1.0); aux[f][v] = a; EX[v] += a;
+          }
+        }
+      }
+    }
+  }
+  double E[V], F[V];
+#pragma unroll
+  for (int v = 0; v < V; v++) {
+    E[v] = exp(-EX[v]);
+    F[v] = E[v];
+#pragma unroll
+    for (int f = 0; f < DGP_MAX_FACTORS; f++)
+      if (f < tc.nf && tc.f[f].kind != DGP_PERIODIC) F[v] *= poly[f][v];
+  }
+#pragma unroll
+  for (int v = 0; v < V; v++) {
+    acc[SLOT_SCALE] = fma(w[v], G[v] * F[v], acc[SLOT_SCALE]);
+    acc[SLOT_GATE] = fma(w[v] * tc.scale, dG[v] * F[v], acc[SLOT_GATE]);
+  }
+  // pass 2: per-parameter derivative factors (the factor's own exponential is already inside E)
+#pragma unroll
+  for (int f = 0; f < DGP_MAX_FACTORS; f++) {
+    if (f < tc.nf) {
+      const FactorC& fc = tc.f[f];
+      double wo[V];  // w * scale * gate * E * prod_{g != f} poly_g
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        double o = w[v] * tc.scale * G[v] * E[v];
+#pragma unroll
+        for (int g = 0; g < DGP_MAX_FACTORS; g++)
+          if (g != f && g < tc.nf && tc.f[g].kind != DGP_PERIODIC) o *= poly[g][v];
+        wo[v] = o;
+      }
+      if (fc.kind == DGP_PERIODIC) {
+        const double cl = 2.0 * fc.inv_lam * fc.inv_lam;                        // d/d lam   : val * 2 s^2 / lam^2
+        const double cp = 4.0 * 3.14159265358979323846 * fc.inv_lam * fc.inv_p;  // d/d period: val * (4/lam) s c u / p
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          acc[SLOT_F0 + f * SLOT_PER_F + 0] = fma(wo[v] * cl, poly[f][v], acc[SLOT_F0 + f * SLOT_PER_F + 0]);
+          acc[SLOT_F0 + f * SLOT_PER_F + DGP_MAX_FDIMS] = fma(wo[v] * cp, aux[f][v], acc[SLOT_F0 + f * SLOT_PER_F + DGP_MAX_FDIMS]);
+        }
+      } else {
+        double cm[V];  // d factor / d ls_d = cm * z_d^2 / ls_d  (exponential excluded)
+#pragma unroll
+        for (int v = 0; v < V; v++)
+          cm[v] = wo[v] * (fc.kind == DGP_RBF ? 1.0 : (fc.kind == DGP_MATERN32 ? 3.0 : (5.0 / 3.0) * (1.0 + aux[f][v])));
+#pragma unroll
+        for (int d = 0; d < DGP_MAX_FDIMS; d++) {
+          if (d < fc.ndims) {
+            const double xa = xaT[fc.col[d] * a_stride + a_idx];
+            double sd = 0.0;
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+              const double z = (xa - xb[v * DGP_XS + fc.col[d]]) * fc.inv_ls[d];
+              sd = fma(cm[v] * z, z, sd);
+            }
+            acc[SLOT_F0 + f * SLOT_PER_F + d] = fma(sd, fc.inv_ls[d], acc[SLOT_F0 + f * SLOT_PER_F + d]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // theta index of a slot of term tc (-1: unused)
 __device__ __forceinline__ int term_slot_theta(const TermC& tc, int slot) {
   if (slot == SLOT_SCALE) return tc.scale_idx;

@@ -216,6 +216,8 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
 
   if (warp == 4) {
     // ------------------------------------------------------------ TMA producer
+    // INIT_COV tiles stage the generated covariance tile in the (still idle) ring: wait until it has been consumed
+    if (INIT == INIT_COV && job.init == INIT_COV) asm volatile("bar.sync 2, 160;" ::: "memory");
     if (lane == 0) {
       for (int it = 0; it < job.nk; it++) {
         const int s = it % STAGES;
@@ -237,35 +239,43 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
 
   // ---- accumulator initialisation
   if (INIT == INIT_COV && job.init == INIT_COV) {
-    double* xs = (double*)(smem + SM_XS);
+    // Thread t generates row t of the tile, 8 columns at a time (cov_vals<8>), into a padded tile in the ring;
+    // the fragments are then read back in the DMMA accumulator layout.
+    double* xaT = (double*)(smem + SM_XS);          // [DGP_XS][128] row-point features, column-major
+    double* xb = xaT + DGP_XS * BM;                 // [64][DGP_XS]  column-point features
+    double* W = (double*)(smem + SM_STAGES);
     const int t = threadIdx.x;  // 0..127
     cov_compile(cc, spec, g.theta, g.jitter, t, 128);
-    for (int e = t; e < (BM + BN) * DGP_XS; e += 128) {
-      const int r = e / DGP_XS, c = e % DGP_XS;
-      const int gr = (r < BM) ? job.crow + r : job.ccol + (r - BM);
-      xs[e] = g.Xw[(size_t)gr * DGP_XS + c];
-    }
+    for (int e = t; e < BM * DGP_XS; e += 128) xaT[(e % DGP_XS) * BM + e / DGP_XS] = g.Xw[(size_t)job.crow * DGP_XS + e];
+    for (int e = t; e < BN * DGP_XS; e += 128) xb[e] = g.Xw[(size_t)job.ccol * DGP_XS + e];
     consumer_bar();
+    {
+      const int gr = job.crow + t;
+      const double dn = (gr < g.n) ? (g.latent ? g.jitter : g.noise[gr] + cc->extra_noise) : 0.0;
 #pragma unroll 1
-    for (int mi = 0; mi < 8; mi++) {
-      const int lr = 64 * wm + 8 * mi + g8, gr = job.crow + lr;
-      const double* xi = xs + lr * DGP_XS;
+      for (int c0 = 0; c0 < BN; c0 += 8) {
+        double val[8];
+        cov_vals<8>(cc, xaT, BM, t, xb + c0 * DGP_XS, val);
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int lc = 32 * wn + 8 * ni + 2 * q + e, gc = job.ccol + lc;
-          double v;
-          if (gr < g.n && gc < g.n) {
-            v = cov_entry(cc, xi, xs + (BM + lc) * DGP_XS);
-            if (gr == gc) v += g.latent ? g.jitter : g.noise[gr] + cc->extra_noise;
-          } else {
-            v = (gr == gc) ? 1.0 : 0.0;
-          }
-          acc[mi][ni][e] = g.sign * v;
+        for (int v = 0; v < 8; v++) {
+          const int gc = job.ccol + c0 + v;
+          double x = val[v];
+          if (gr < g.n && gc < g.n) { if (gr == gc) x += dn; }
+          else x = (gr == gc) ? 1.0 : 0.0;
+          W[t * WS + c0 + v] = g.sign * x;
         }
       }
     }
+    consumer_bar();
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+        const double* wp = W + (64 * wm + 8 * mi + g8) * WS + 32 * wn + 8 * ni + 2 * q;
+        acc[mi][ni][0] = wp[0];
+        acc[mi][ni][1] = wp[1];
+      }
+    asm volatile("bar.sync 2, 160;" ::: "memory");  // release the ring to the producer
   } else if ((INIT == INIT_LOAD || INIT == INIT_COV) && job.init == INIT_LOAD) {
 #pragma unroll
     for (int mi = 0; mi < 8; mi++) {
@@ -384,19 +394,15 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
       }
     }
     cov_compile(cc, spec, g.theta, 0.0, t, 128);
-    for (int e = t; e < (BM + BN) * DGP_XS; e += 128) {
-      const int r = e / DGP_XS, c = e % DGP_XS;
-      const int gr = (r < BM) ? job.crow + r : job.ccol + (r - BM);
-      xs[e] = g.Xw[(size_t)gr * DGP_XS + c];
-    }
+    double* xaT = xs;                 // [DGP_XS][128] row-point features, column-major
+    double* xb = xs + DGP_XS * BM;    // [64][DGP_XS]  column-point features
+    for (int e = t; e < BM * DGP_XS; e += 128) xaT[(e % DGP_XS) * BM + e / DGP_XS] = g.Xw[(size_t)job.crow * DGP_XS + e];
+    for (int e = t; e < BN * DGP_XS; e += 128) xb[e] = g.Xw[(size_t)job.ccol * DGP_XS + e];
     for (int e = t; e < BM + BN; e += 128) al[e] = g.alpha[(e < BM) ? job.crow + e : job.ccol + (e - BM)];
     consumer_bar();
 
-    // thread t owns row t of the tile
+    // thread t owns row t of the tile; 4 columns side by side (term_grad_accum_v<4>)
     const int grow = job.crow + t;
-    double xi[DGP_XS];
-#pragma unroll
-    for (int c = 0; c < DGP_XS; c++) xi[c] = xs[t * DGP_XS + c];
     const double ai = al[t];
     double trw = 0.0;
     for (int term = 0; term < cc->nterms; term++) {
@@ -405,14 +411,17 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
       for (int k = 0; k < NSLOT; k++) sl[k] = 0.0;
       const TermC& tc = cc->t[term];
 #pragma unroll 1
-      for (int c = 0; c < BN; c++) {
-        const int gcol = job.ccol + c;
-        if (grow < g.n && gcol <= grow) {
-          const double wgt = (gcol == grow) ? 1.0 : 2.0;
-          const double w = wgt * (ai * al[BM + c] - W[t * WS + c]);
-          term_grad_accum(tc, xi, xs + (BM + c) * DGP_XS, w, sl);
-          if (term == 0 && gcol == grow) trw += w;
+      for (int c0 = 0; c0 < BN; c0 += 4) {
+        if (grow >= g.n || job.ccol + c0 > grow) continue;  // padding rows / strictly above the diagonal
+        double w[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          const int c = c0 + v, gcol = job.ccol + c;
+          const double wgt = (gcol < grow) ? 2.0 : (gcol == grow ? 1.0 : 0.0);
+          w[v] = wgt * (ai * al[BM + c] - W[t * WS + c]);
+          if (term == 0 && gcol == grow) trw += w[v];
         }
+        term_grad_accum_v<4>(tc, xaT, BM, t, xb + c0 * DGP_XS, w, sl);
       }
 #pragma unroll
       for (int k = 0; k < NSLOT; k++) {

@@ -56,33 +56,38 @@ k_cov_rect(const __grid_constant__ dgp_spec spec, const double* __restrict__ the
            double jitter, double* __restrict__ out, long long ld, int na, int nb_, int diag_noise, int ident_pad,
            const double* __restrict__ vec, double* __restrict__ dot, int dot_ld) {
   __shared__ CovC cc;
-  __shared__ double xa[32 * DGP_XS];
-  __shared__ double xb[128 * DGP_XS];
+  __shared__ double xa[32 * DGP_XS];    // row points, row-major (broadcast side)
+  __shared__ double xbT[DGP_XS * 128];  // column points, column-major (per-thread side)
   __shared__ double red[32][9];
   const int t = threadIdx.x;
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
   cov_compile(&cc, spec, theta, jitter, t, 256);
   for (int e = t; e < 32 * DGP_XS; e += 256) xa[e] = XwA[(size_t)r0 * DGP_XS + e];
-  for (int e = t; e < 128 * DGP_XS; e += 256) xb[e] = XwB[(size_t)c0 * DGP_XS + e];
+  for (int e = t; e < 128 * DGP_XS; e += 256) xbT[(e % DGP_XS) * 128 + e / DGP_XS] = XwB[(size_t)c0 * DGP_XS + e];
   __syncthreads();
-  const int lc = t & 127, half = t >> 7;  // thread: column lc, rows half*16 .. +16
+  const int lc = t & 127, half = t >> 7;  // thread: column lc, rows half*16 .. +16 (the same rows for the whole warp)
   const int gc = c0 + lc;
   const double vj = (vec != nullptr) ? vec[gc] : 0.0;
-  for (int rr = 0; rr < 16; rr++) {
-    const int lr = half * 16 + rr, gr = r0 + lr;
-    double v;
-    if (gr < na && gc < nb_) {
-      v = cov_entry(&cc, xa + lr * DGP_XS, xb + lc * DGP_XS);
-      if (diag_noise && gr == gc) v += noise[gr] + cc.extra_noise;
-    } else {
-      v = (ident_pad && gr == gc) ? 1.0 : 0.0;
-    }
-    if (out != nullptr) out[(size_t)gr * ld + gc] = v;
-    if (dot != nullptr) {
-      double s = v * vj;
+#pragma unroll 1
+  for (int rr0 = 0; rr0 < 16; rr0 += 8) {
+    double val[8];
+    cov_vals<8>(&cc, xbT, 128, lc, xa + (half * 16 + rr0) * DGP_XS, val);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if ((t & 31) == 0) red[lr][(t >> 5) & 3] = s;
+    for (int u = 0; u < 8; u++) {
+      const int lr = half * 16 + rr0 + u, gr = r0 + lr;
+      double v = val[u];
+      if (gr < na && gc < nb_) {
+        if (diag_noise && gr == gc) v += noise[gr] + cc.extra_noise;
+      } else {
+        v = (ident_pad && gr == gc) ? 1.0 : 0.0;
+      }
+      if (out != nullptr) out[(size_t)gr * ld + gc] = v;
+      if (dot != nullptr) {
+        double s = v * vj;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((t & 31) == 0) red[lr][(t >> 5) & 3] = s;
+      }
     }
   }
   if (dot != nullptr) {
