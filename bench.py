@@ -135,6 +135,10 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=N_TRAIN, help="development only; the judged workload is n=16384")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the predictive-points/s and sites/s legs (development)")
+    ap.add_argument("--sites-per-gpu", type=int, default=8, help="sites of the NWQN-style batch fitted per GPU in the sites/s leg")
+    ap.add_argument("--site-iterations", type=int, default=100)
+    ap.add_argument("--predict-m", type=int, default=32768, help="grid points of the predictive-points/s leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -164,7 +168,7 @@ def main():
     spec = models.loadest_spec(2)
     work_stream = torch.cuda.Stream(device=local)  # the engine launches on this stream; the events below are recorded on it
     torch.cuda.set_stream(work_stream)
-    eng = capi.Engine(max_n=n, max_m=256, device=local, stream=work_stream.cuda_stream)
+    eng = capi.Engine(max_n=n, max_m=2048, device=local, stream=work_stream.cuda_stream)
     eng.set_train(spec.to_c(), X, y, noise)
     base = H.loadest_theta1()
     thetas = [base * (1.0 + 1e-3 * k) for k in range(warm + args.steps)]
@@ -218,12 +222,77 @@ def main():
     barrier()
     ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    # ---- extra legs of the BASELINE metric: predictive points/s on this site, sites/s on an NWQN-style batch
+    extra_local = [0.0, 0.0, 0.0, 0.0]
+    site_info = None
+    if not args.no_extra:
+        m_pred = args.predict_m
+        grid = synthetic.daily_grid(X, m_pred)
+        _, info_f = eng.factorize(base)
+        if info_f != 0:
+            raise RuntimeError(f"factorize failed: info={info_f}")
+        grid_d = torch.from_numpy(grid).to(f"cuda:{local}")
+        eng.predict(grid_d[:4096])
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        mu_d, var_d = eng.predict(grid_d)            # inputs and outputs resident in HBM
+        p1.record()
+        barrier()
+        extra_local[0] = p0.elapsed_time(p1)
+        t0 = time.perf_counter()
+        mu_h, var_h = eng.predict(grid)              # host grid in, host mean/variance out
+        torch.cuda.synchronize()
+        extra_local[1] = (time.perf_counter() - t0) * 1e3
+        if not (np.all(np.isfinite(mu_h)) and np.all(var_h > -1e-8) and np.allclose(mu_h, mu_d.cpu().numpy())):
+            raise RuntimeError("prediction leg produced invalid output")
+        eng.close()
+        eng = None
+        # sites/s: SURVEY 8d config 4 sizes (n_s = 2000 + 6000 u_s, seed 42), `sites_per_gpu` sites on every rank,
+        # 100 Adam iterations each + mean/variance on a 10 958-point daily grid; host arrays in, host results out.
+        from discontinuum_b200 import multisite
+
+        rng = np.random.default_rng(42)
+        ns_all = (2000 + 6000 * rng.uniform(size=128)).astype(int)
+        S = args.sites_per_gpu
+        mine = [(rank * S + k) % 128 for k in range(S)]
+        sites = {k: synthetic.loadest_site(int(ns_all[k]), 1000 + k) for k in mine}
+        grids = {k: synthetic.daily_grid(sites[k][0], 10958) for k in mine}
+        warm_site = {999: synthetic.loadest_site(512, 7)}
+        multisite.fit_sites_local(warm_site, iterations=3, device=local, concurrency=1)
+        barrier()
+        t0 = time.perf_counter()
+        res = multisite.fit_sites_local(sites, iterations=args.site_iterations, device=local, concurrency=4, predict=grids)
+        torch.cuda.synchronize()
+        extra_local[2] = (time.perf_counter() - t0) * 1e3
+        extra_local[3] = float(sum(float(ns_all[k]) ** 3 * args.site_iterations for k in mine))
+        bad = [k for k, r in res.items() if r["failed"] is not None or not np.all(np.isfinite(r["mu"]))]
+        if bad:
+            raise RuntimeError(f"site fits failed: {bad}")
+        site_info = {"n_min": int(min(ns_all[k] for k in mine)), "n_max": int(max(ns_all[k] for k in mine))}
+
+    t = torch.tensor([ms, ms_e2e] + extra_local[:3], dtype=torch.float64, device="cuda")
+    fl = torch.tensor([extra_local[3]], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
     ms_max, ms_e2e_max = float(t[0]), float(t[1])
     value = world * args.steps / (ms_max * 1e-3)
     e2e_value = world * args.steps / (ms_e2e_max * 1e-3)
+    extra = None
+    if not args.no_extra:
+        m_pred = args.predict_m
+        pred_flop = float(m_pred) * float(n) ** 2  # variance via the triangular product, n^2 flop per point
+        extra = {
+            "predict": {"metric": "predictive_points_per_sec", "value": world * m_pred / (float(t[2]) * 1e-3), "unit": "points/s",
+                        "e2e": world * m_pred / (float(t[3]) * 1e-3), "n_train": n, "m_grid_per_gpu": m_pred,
+                        "what": "posterior mean + latent variance, grid sharded one slice per GPU",
+                        "tflops": pred_flop / (float(t[2]) * 1e-3) / 1e12},
+            "sites": {"metric": "sites_per_sec", "value": world * args.sites_per_gpu / (float(t[4]) * 1e-3), "unit": "sites/s",
+                      "sites": world * args.sites_per_gpu, "iterations": args.site_iterations, "predict_grid": 10958,
+                      "fit_tflops": float(fl[0]) / (float(t[4]) * 1e-3) / 1e12, "n_range": site_info,
+                      "what": "NWQN-style batch (SURVEY 8d config 4 sizes): fit + daily-grid prediction per site, host arrays in/out, "
+                              "4 sites in flight per GPU, no collective"}}
 
     if rank == 0:
         peak, peak_src = fp64_peak()
@@ -253,9 +322,10 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * (2 + 2) * 8 + 10 * 8),
                         "d2h_bytes_per_step": int((1 + 10) * 8)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "nlml": val}
+                "nlml": val, "extra": extra}
         print(json.dumps(line), flush=True)
-    eng.close()
+    if eng is not None:
+        eng.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -56,6 +56,9 @@ struct dgp_handle_s {
   std::vector<cudaEvent_t> evs;      // look-ahead dependencies (no timing)
   bool lookahead = true;
   int panel_blocks = 4;              // block columns per panel of the two-level Cholesky
+  struct GraphSlot { cudaGraphExec_t exec = nullptr; double jitter = 0.0; bool seen = false; long long launches = 0; };
+  GraphSlot graphs[3];               // per evaluation level (nlml / nlml+grad / factorize)
+  bool use_graphs = false;  // opt-in (DGP_GRAPHS=1): replay loses the stream priorities of the look-ahead, measured slower
   int max_n = 0, max_pad = 0, max_m = 0;
   int n = 0, npad = 0, nb = 0;
   bool have_train = false, factorized = false, have_T = false, debug_kinv = false, timing = false;
@@ -166,6 +169,8 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
     cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, hi);
     const char* la = getenv("DGP_LOOKAHEAD");
     if (la) h->lookahead = atoi(la) != 0;
+    const char* ug = getenv("DGP_GRAPHS");
+    if (ug) h->use_graphs = atoi(ug) != 0;
     const char* pb = getenv("DGP_PANEL_BLOCKS");
     if (pb && atoi(pb) >= 1 && atoi(pb) <= 64) h->panel_blocks = atoi(pb);
   }
@@ -199,6 +204,7 @@ int dgp_destroy(dgp_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stream_hi) { cudaStreamSynchronize(h->stream_hi); cudaStreamDestroy(h->stream_hi); }
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
+  for (auto& gs : h->graphs) if (gs.exec) cudaGraphExecDestroy(gs.exec);
   double* bufs[] = {h->bufA, h->bufL, h->bufU, h->DI, h->X, h->y, h->noise, h->Xw, h->r, h->z, h->alpha, h->theta,
                     h->scal, h->gpart, h->zpart, h->Kx, h->Xs, h->Xws, h->means, h->dot, h->vpart, h->mu, h->var};
   for (double* p : bufs) if (p) cudaFree(p);
@@ -255,6 +261,12 @@ int dgp_set_train(dgp_handle h, const dgp_spec* spec, const double* X, const dou
   int rc = check_spec(h, spec);
   if (rc) return rc;
   CK(h, cudaSetDevice(h->device));
+  if (!h->have_train || n != h->n || memcmp(&h->spec, spec, sizeof(dgp_spec)) != 0) {
+    for (auto& gs : h->graphs) {  // captured launch sequences bake in n and the spec
+      if (gs.exec) cudaGraphExecDestroy(gs.exec);
+      gs = dgp_handle_s::GraphSlot();
+    }
+  }
   h->spec = *spec;
   h->n = n;
   h->npad = round_up(n, 128);
@@ -454,16 +466,9 @@ static int run_finish(dgp_handle h, int want_grad) {
   return 0;
 }
 
-static int evaluate_launch(dgp_handle h, const double* theta, double jitter, int level) {
-  // level 0: nlml ; 1: nlml + grad ; 2: factorize for prediction (L, U, alpha, T)
-  if (!h) return -1;
-  if (!h->have_train) DGP_FAIL(h, -1, "no training data: call dgp_set_train first");
-  if (!theta) DGP_FAIL(h, -1, "theta is NULL");
-  CK(h, cudaSetDevice(h->device));
+static int evaluate_enqueue(dgp_handle h, double jitter, int level) {
   int rc;
-  h->factorized = false; h->have_T = false;
-  if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
-  if ((rc = upload_theta(h, theta))) return rc;
+  CK(h, cudaMemcpyAsync(h->theta, h->h_theta, sizeof(double) * h->spec.ntheta, cudaMemcpyHostToDevice, h->stream));
   if ((rc = run_features(h))) return rc;
   if ((rc = run_potrf(h, jitter, level == 0))) return rc;  // level >= 1: z = U'r after the inverse instead
   if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
@@ -476,7 +481,47 @@ static int evaluate_launch(dgp_handle h, const double* theta, double jitter, int
     if (h->timing) CK(h, cudaEventRecord(h->ev[3], h->stream));
   }
   if ((rc = run_finish(h, level == 1))) return rc;
-  if (h->timing) CK(h, cudaEventRecord(h->ev[4], h->stream));
+  return 0;
+}
+
+// The launch sequence of an evaluation depends only on (n, level, jitter): the first call of a kind runs eagerly,
+// the second is captured into a CUDA graph (both streams; the look-ahead events become graph edges) and every
+// later call replays it, so that the ~10^3 launches cost one cudaGraphLaunch on the host.
+static int evaluate_launch(dgp_handle h, const double* theta, double jitter, int level) {
+  // level 0: nlml ; 1: nlml + grad ; 2: factorize for prediction (L, U, alpha, T)
+  if (!h) return -1;
+  if (!h->have_train) DGP_FAIL(h, -1, "no training data: call dgp_set_train first");
+  if (!theta) DGP_FAIL(h, -1, "theta is NULL");
+  CK(h, cudaSetDevice(h->device));
+  int rc;
+  h->factorized = false; h->have_T = false;
+  memcpy(h->h_theta, theta, sizeof(double) * h->spec.ntheta);
+  dgp_handle_s::GraphSlot& gs = h->graphs[level];
+  const bool use_graph = h->use_graphs && !h->timing && !h->debug_kinv;
+  if (use_graph && gs.exec != nullptr && gs.jitter == jitter) {
+    CK(h, cudaGraphLaunch(gs.exec, h->stream));
+    h->launches += gs.launches;
+  } else if (use_graph && gs.seen && gs.jitter == jitter) {
+    if (gs.exec != nullptr) { cudaGraphExecDestroy(gs.exec); gs.exec = nullptr; }
+    const long long l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    rc = evaluate_enqueue(h, jitter, level);
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) DGP_FAIL(h, -2, "graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&gs.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { gs.exec = nullptr; DGP_FAIL(h, -2, "graph instantiate failed: %s", cudaGetErrorString(ce)); }
+    gs.launches = h->launches - l0;
+    CK(h, cudaGraphLaunch(gs.exec, h->stream));
+  } else {
+    if (gs.exec != nullptr && gs.jitter != jitter) { cudaGraphExecDestroy(gs.exec); gs.exec = nullptr; }
+    gs.seen = true; gs.jitter = jitter;
+    if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = evaluate_enqueue(h, jitter, level))) return rc;
+    if (h->timing) CK(h, cudaEventRecord(h->ev[4], h->stream));
+  }
   h->pending = true;
   h->pending_grad = level;
   return 0;

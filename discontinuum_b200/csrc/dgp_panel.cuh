@@ -105,7 +105,7 @@ k_cov_rect(const __grid_constant__ dgp_spec spec, const double* __restrict__ the
 constexpr int PF_THREADS = 256;
 constexpr int PF_AS = 129;  // row stride of As
 constexpr int PF_PN = 33;   // row stride of the 32-column panel scratch
-constexpr int PF_SMEM = (128 * PF_AS + 256 * PF_PN + 128) * 8;
+constexpr int PF_SMEM = (128 * PF_AS + 256 * PF_PN + 128 + 64) * 8;
 
 template <int REM>
 __device__ __forceinline__ void potf2_trailing(double* As, const double* Pn, int o, int tid) {
@@ -154,6 +154,7 @@ k_potf2(const double* Ablk, double* __restrict__ Lblk, double* __restrict__ Ublk
   double* As = pf_smem;
   double* Pn = As + 128 * PF_AS;
   double* rd = Pn + 256 * PF_PN;
+  double* cb = rd + 128;  // [2][32] column exchange buffer of the diagonal sub-block
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
 #pragma unroll 1
@@ -174,7 +175,9 @@ k_potf2(const double* Ablk, double* __restrict__ Lblk, double* __restrict__ Ublk
 
   for (int kb = 0; kb < 4; kb++) {
     const int o = 32 * kb;
-    // (1) 32x32 diagonal sub-block, one warp, rows in registers
+    // (1) 32x32 diagonal sub-block, one warp, lane = row, the row in registers.  Column c is exchanged through a
+    // double-buffered shared vector (one STS + broadcast LDS.128 per lane instead of 31 - c register shuffles):
+    //   a[c2] -= a[c] * A[c2][c] / d,  L[r][c] = a[c] / sqrt(d)
     if (warp == 0) {
       double a[32];
 #pragma unroll
@@ -182,17 +185,17 @@ k_potf2(const double* Ablk, double* __restrict__ Lblk, double* __restrict__ Ublk
       double myinv = 0.0;
 #pragma unroll
       for (int c = 0; c < 32; c++) {
-        const double d = __shfl_sync(0xffffffffu, a[c], c);
+        double* cbuf = cb + (c & 1) * 32;
+        cbuf[lane] = a[c];
+        __syncwarp();
+        const double d = cbuf[c];
         if (!(d > 0.0) && lane == 0 && scal[SC_INFO] == 0.0) scal[SC_INFO] = (double)(base + o + c + 1);
         const double inv = rsqrt(d);  // one MUFU + Newton chain instead of sqrt followed by a division
-        const double l = d * inv;
-        if (lane == c) { a[c] = l; myinv = inv; }
-        if (lane > c) a[c] *= inv;
+        const double tfac = a[c] * inv * inv;
 #pragma unroll
-        for (int c2 = c + 1; c2 < 32; c2++) {
-          const double v = __shfl_sync(0xffffffffu, a[c], c2);
-          a[c2] = fma(-a[c], v, a[c2]);
-        }
+        for (int c2 = c + 1; c2 < 32; c2++) a[c2] = fma(-tfac, cbuf[c2], a[c2]);
+        a[c] = (lane == c) ? d * inv : a[c] * inv;
+        if (lane == c) myinv = inv;
       }
 #pragma unroll
       for (int c = 0; c < 32; c++)

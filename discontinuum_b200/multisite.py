@@ -94,50 +94,73 @@ def _finish_step(s: _SiteState):
         s.sched.step(s.history[-1])
 
 
+def _open_site(idx, tup, device, lr, scheduler, patience) -> _SiteState:
+    X, y = np.ascontiguousarray(tup[0], dtype=np.float64), np.ascontiguousarray(tup[1], dtype=np.float64)
+    noise = np.ascontiguousarray(tup[2], dtype=np.float64) if len(tup) > 2 else np.full(y.shape[0], LOADEST_FIXED_NOISE)
+    module = GPModule(loadest_spec(X.shape[1]))
+    eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device)
+    eng.set_train(module.spec.to_c(), X, y, noise)
+    opt = torch.optim.Adam(module.raw_list(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    sch = None
+    if scheduler:
+        sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.7, patience=max(20, patience // 2),
+                                                         threshold=1e-4, threshold_mode="rel", min_lr=1e-6, cooldown=10)
+    return _SiteState(idx, X, y, noise, module, eng, opt, sch)
+
+
+def _launch_step(s: _SiteState):
+    s.opt.zero_grad(set_to_none=True)
+    s.nat = s.module.natural()
+    s.engine.nlml_grad_launch(s.nat.detach().numpy().astype(np.float64))
+
+
+def _close_site(s: _SiteState, predict) -> dict:
+    with torch.no_grad():
+        theta = s.module.natural().numpy().astype(np.float64)
+    res = {"theta": theta, "history": s.history, "objective": s.history[-1] if s.history else None, "failed": s.failed,
+           "n": int(s.X.shape[0])}
+    if predict is not None and s.idx in predict and s.failed is None:
+        for jit in JITTERS:
+            _, info = s.engine.factorize(theta, jit)
+            if info == 0:
+                break
+        mu, var = s.engine.predict(predict[s.idx])
+        res["mu"], res["var"] = mu, np.maximum(var, MIN_VARIANCE)
+    s.engine.close()
+    return res
+
+
 def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int = 0, concurrency: int = 4,
                     predict: Optional[Dict[int, np.ndarray]] = None, lr: float = 0.05, scheduler: bool = True,
                     patience: int = 60) -> Dict[int, dict]:
     """Fit the loadest-gp model on every site of this rank.  sites: {index: (X, y[, noise])} in model space.
-    Returns {index: {"theta", "objective", "history", "mu", "var"}}."""
+    Returns {index: {"theta", "objective", "history", "mu", "var"}}.
+
+    `concurrency` sites are in flight at any time, each a pipeline of its own: as soon as a site's evaluation is
+    back the host does its optimiser step and enqueues its next evaluation, while the GPU works on the others; a
+    finished site is predicted, closed and replaced by the next largest one (no group barrier)."""
     results: Dict[int, dict] = {}
-    order = sorted(sites, key=lambda i: -sites[i][0].shape[0])
-    for start in range(0, len(order), concurrency):
-        group: List[_SiteState] = []
-        for idx in order[start:start + concurrency]:
-            tup = sites[idx]
-            X, y = np.ascontiguousarray(tup[0], dtype=np.float64), np.ascontiguousarray(tup[1], dtype=np.float64)
-            noise = np.ascontiguousarray(tup[2], dtype=np.float64) if len(tup) > 2 else np.full(y.shape[0], LOADEST_FIXED_NOISE)
-            module = GPModule(loadest_spec(X.shape[1]))
-            eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device)
-            eng.set_train(module.spec.to_c(), X, y, noise)
-            opt = torch.optim.Adam(module.raw_list(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
-            sch = None
-            if scheduler:
-                sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.7, patience=max(20, patience // 2),
-                                                                 threshold=1e-4, threshold_mode="rel", min_lr=1e-6, cooldown=10)
-            group.append(_SiteState(idx, X, y, noise, module, eng, opt, sch))
-        for _ in range(iterations):
-            live = [s for s in group if s.failed is None]
-            for s in live:  # enqueue every site's evaluation, then collect: the GPU overlaps them
-                s.opt.zero_grad(set_to_none=True)
-                s.nat = s.module.natural()
-                s.engine.nlml_grad_launch(s.nat.detach().numpy().astype(np.float64))
-            for s in live:
+    queue = sorted(sites, key=lambda i: -sites[i][0].shape[0])
+    active: List[_SiteState] = []
+
+    def refill():
+        while queue and len(active) < max(1, concurrency):
+            s = _open_site(queue[0], sites[queue.pop(0)], device, lr, scheduler, patience)
+            if iterations > 0:
+                _launch_step(s)
+            active.append(s)
+
+    refill()
+    while active:
+        for s in list(active):
+            if iterations > 0:
                 _finish_step(s)
-        for s in group:
-            with torch.no_grad():
-                theta = s.module.natural().numpy().astype(np.float64)
-            res = {"theta": theta, "history": s.history, "objective": s.history[-1] if s.history else None, "failed": s.failed,
-                   "n": int(s.X.shape[0])}
-            if predict is not None and s.idx in predict and s.failed is None:
-                for jit in JITTERS:
-                    _, info = s.engine.factorize(theta, jit)
-                    if info == 0:
-                        break
-                mu, var = s.engine.predict(predict[s.idx])
-                res["mu"], res["var"] = mu, np.maximum(var, MIN_VARIANCE)
-            results[s.idx] = res
-            s.engine.close()
+            if s.failed is None and len(s.history) < iterations:
+                _launch_step(s)
+                continue
+            active.remove(s)
+            results[s.idx] = _close_site(s, predict)
+            refill()
     return results
 
 
