@@ -320,6 +320,7 @@ struct CholBufs {
   const CUtensorMap *tA, *tL, *tDI;
   int nb;
   long long ld;
+  double* P = nullptr;  // in-place factorisation (L == A): [rows][128] staging buffer of the panel solve
 };
 
 static int ensure_events(dgp_handle h, size_t count) {
@@ -373,8 +374,9 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
     if (P != T && p > 0) CK(h, cudaStreamWaitEvent(P, ev_cols(p), 0));
     for (int s = pb; s < pe; s++) {
       const size_t off = (size_t)s * 128 * ld + (size_t)s * 128;
+      const bool inplace = (b.L == b.A);
       k_potf2<<<1, PF_THREADS, PF_SMEM, P>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
-                                             b.DI + (size_t)s * 128 * 128, b.scal, s * 128, b.A + off);
+                                             b.DI + (size_t)s * 128 * 128, b.scal, s * 128, inplace ? nullptr : b.A + off);
       h->launches++;
       CK(h, cudaGetLastError());
       const int m = nb - s - 1;
@@ -382,7 +384,13 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
         GemmArgs g = base_args(h, M_TRSM, s);
         g.nb = nb; g.ldc = ld;
         g.C = b.L; g.ntiles = 2 * m;
+        if (inplace) { g.C = b.P; g.ldc = 128; g.aux0 = 1; }  // both half-tiles read the whole block: stage, then copy
         if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, *b.tA, *b.tDI, g, P))) return rc;
+        if (inplace) {
+          k_copy_panel<<<m, 256, 0, P>>>(b.P, b.A, ld, s);
+          h->launches++;
+          CK(h, cudaGetLastError());
+        }
       }
       if (fwd) {
         k_fwd_step<<<nb - s, 256, 0, P>>>(b.L, ld, b.DI, h->r, h->z, s);
@@ -680,8 +688,11 @@ int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, do
   const int mpad = round_up(m, 128), Spad = round_up(S, 128), npad = h->npad, mb = mpad / 128;
   const cudaMemcpyKind ikind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const cudaMemcpyKind okind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  double *Xsd = nullptr, *Xws = nullptr, *means = nullptr, *dot = nullptr, *mu = nullptr, *Kx = nullptr, *VT = nullptr;
-  double *Sig = nullptr, *Lp = nullptr, *DI2 = nullptr, *Zd = nullptr, *Od = nullptr, *zero = nullptr, *scal2 = nullptr;
+  // m-sized work buffers, allocated per call: V' (m x n), Sigma* (m x m, factorised in place), the panel staging
+  // buffer and block inverses of that factorisation, Z and the draws.  The cross covariance goes through the
+  // handle's prediction chunk, so the footprint is 8 (m n + m^2) B + O(m): 106 GB at m = 100k, n = 32k.
+  double *Xsd = nullptr, *Xws = nullptr, *means = nullptr, *dot = nullptr, *mu = nullptr, *VT = nullptr;
+  double *Sig = nullptr, *Pb = nullptr, *DI2 = nullptr, *Zd = nullptr, *Od = nullptr, *zero = nullptr, *scal2 = nullptr;
   struct Freer {
     double** p[14]; int k = 0;
     ~Freer() { for (int i = 0; i < k; i++) if (*p[i]) cudaFree(*p[i]); }
@@ -693,40 +704,44 @@ int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, do
   cudaError_t r = cudaSuccess;
   auto acc = [&](cudaError_t x) { if (r == cudaSuccess) r = x; };
   acc(A(&Xsd, (size_t)mpad * DGP_MAX_COLS)); acc(A(&Xws, (size_t)mpad * DGP_XS)); acc(A(&means, mpad));
-  acc(A(&dot, (size_t)h->nb * mpad)); acc(A(&mu, mpad)); acc(A(&Kx, (size_t)mpad * npad)); acc(A(&VT, (size_t)mpad * npad));
-  acc(A(&Sig, (size_t)mpad * mpad)); acc(A(&Lp, (size_t)mpad * mpad)); acc(A(&DI2, (size_t)mpad * 128));
+  acc(A(&dot, (size_t)h->nb * mpad)); acc(A(&mu, mpad)); acc(A(&VT, (size_t)mpad * npad));
+  acc(A(&Sig, (size_t)mpad * mpad)); acc(A(&Pb, (size_t)mpad * 128)); acc(A(&DI2, (size_t)mpad * 128));
   acc(A(&Zd, (size_t)Spad * mpad)); acc(A(&Od, (size_t)Spad * mpad)); acc(A(&zero, mpad)); acc(A(&scal2, SC_SIZE));
-  if (r != cudaSuccess) DGP_FAIL(h, -2, "dgp_sample: workspace allocation failed for m=%d, S=%d: %s", m, S, cudaGetErrorString(r));
+  if (r != cudaSuccess) {
+    cudaGetLastError();
+    DGP_FAIL(h, -2, "dgp_sample: workspace allocation failed for m=%d, S=%d: %s", m, S, cudaGetErrorString(r));
+  }
   int rc;
   CK(h, cudaMemsetAsync(zero, 0, (size_t)mpad * 8, h->stream));
   CK(h, cudaMemsetAsync(scal2, 0, SC_SIZE * 8, h->stream));
   CK(h, cudaMemsetAsync(Zd, 0, (size_t)Spad * mpad * 8, h->stream));
+  CK(h, cudaMemsetAsync(Xsd, 0, (size_t)mpad * DGP_MAX_COLS * 8, h->stream));
   CK(h, cudaMemcpyAsync(Xsd, Xs, (size_t)m * h->spec.ndim * 8, ikind, h->stream));
   CK(h, cudaMemcpy2DAsync(Zd, (size_t)mpad * 8, Z, (size_t)m * 8, (size_t)m * 8, S, ikind, h->stream));
   k_features<<<(mpad + 255) / 256, 256, 0, h->stream>>>(h->spec, h->theta, Xsd, nullptr, Xws, nullptr, means, m, mpad, nullptr);
   h->launches++;
   CK(h, cudaGetLastError());
-  // cross covariance + mean
-  k_cov_rect<<<dim3(mpad / 32, h->nb), 256, 0, h->stream>>>(h->spec, h->theta, Xws, h->Xw, h->noise, 0.0, Kx, npad, m,
-                                                           h->n, 0, 0, h->alpha, dot, mpad);
-  h->launches++;
-  CK(h, cudaGetLastError());
+  CUtensorMap tVT, tSig, tDI2, tZ;
+  if ((rc = make_map(h, &tVT, VT, mpad, npad, npad))) return rc;
+  if ((rc = make_map(h, &tSig, Sig, mpad, mpad, mpad))) return rc;
+  if ((rc = make_map(h, &tDI2, DI2, mpad, 128, 128))) return rc;
+  if ((rc = make_map(h, &tZ, Zd, Spad, mpad, mpad))) return rc;
+  // cross covariance (+ posterior-mean partials) and V' = Kx T', one prediction chunk of rows at a time
+  for (int m0 = 0; m0 < mpad; m0 += h->max_m) {
+    const int mc = (mpad - m0 < h->max_m) ? mpad - m0 : h->max_m;  // multiple of 128
+    const int mv = (m - m0 < mc) ? m - m0 : mc;                     // valid rows of the chunk
+    k_cov_rect<<<dim3(mc / 32, h->nb), 256, 0, h->stream>>>(h->spec, h->theta, Xws + (size_t)m0 * DGP_XS, h->Xw, h->noise,
+                                                           0.0, h->Kx, npad, mv, h->n, 0, 0, h->alpha, dot + m0, mpad);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    GemmArgs g = base_args(h, M_GENERIC, 0);
+    g.nb = mc / 128; g.n = mv; g.aux0 = 2 * h->nb; g.aux1 = npad / 16; g.aux2 = 1;
+    g.ntiles = (mc / 128) * 2 * h->nb; g.C = VT + (size_t)m0 * npad; g.ldc = npad;
+    if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmKx, h->tmA, g))) return rc;
+  }
   k_pred_finish<<<(m + 255) / 256, 256, 0, h->stream>>>(h->spec, h->theta, Xws, means, dot, h->nb, nullptr, 0, mpad, m, mu, nullptr);
   h->launches++;
   CK(h, cudaGetLastError());
-  CUtensorMap tKx, tVT, tSig, tLp, tDI2, tZ;
-  if ((rc = make_map(h, &tKx, Kx, mpad, npad, npad))) return rc;
-  if ((rc = make_map(h, &tVT, VT, mpad, npad, npad))) return rc;
-  if ((rc = make_map(h, &tSig, Sig, mpad, mpad, mpad))) return rc;
-  if ((rc = make_map(h, &tLp, Lp, mpad, mpad, mpad))) return rc;
-  if ((rc = make_map(h, &tDI2, DI2, mpad, 128, 128))) return rc;
-  if ((rc = make_map(h, &tZ, Zd, Spad, mpad, mpad))) return rc;
-  {  // V' = Kx T'
-    GemmArgs g = base_args(h, M_GENERIC, 0);
-    g.nb = mb; g.n = m; g.aux0 = 2 * h->nb; g.aux1 = npad / 16; g.aux2 = 1;
-    g.ntiles = mb * 2 * h->nb; g.C = VT; g.ldc = npad;
-    if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, tKx, h->tmA, g))) return rc;
-  }
   {  // Sigma* = K** + jitter I - V'V  (lower tiles)
     GemmArgs g = base_args(h, M_GENERIC, 0);
     g.nb = mb; g.n = m; g.aux0 = 2 * mb; g.aux1 = npad / 16; g.aux2 = 2;
@@ -734,15 +749,15 @@ int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, do
     g.Xw = Xws; g.noise = zero; g.jitter = jitter; g.latent = 1;
     if ((rc = launch_gemm<INIT_COV, EPI_STORE>(h, tVT, tVT, g))) return rc;
   }
-  {  // Lpost
-    CholBufs b{Sig, Lp, nullptr, DI2, scal2, &tSig, &tLp, &tDI2, mb, mpad};
+  {  // Lpost, in place
+    CholBufs b{Sig, Sig, nullptr, DI2, scal2, &tSig, &tSig, &tDI2, mb, mpad, Pb};
     if ((rc = potrf_core(h, b, false, 0.0, false))) return rc;
   }
   {  // out = Z Lpost'
     GemmArgs g = base_args(h, M_GENERIC, 0);
     g.nb = Spad / 128; g.n = S; g.aux0 = 2 * mb; g.aux1 = mpad / 16; g.aux2 = 1;
     g.ntiles = (Spad / 128) * 2 * mb; g.C = Od; g.ldc = mpad;
-    if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, tZ, tLp, g))) return rc;
+    if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, tZ, tSig, g))) return rc;
   }
   k_add_rowvec<<<dim3((m + 255) / 256, S), 256, 0, h->stream>>>(Od, mpad, mu, m);
   h->launches++;

@@ -70,7 +70,7 @@ __device__ __forceinline__ Job decode_job(const GemmArgs& g, int tile, int init_
       j.rowA = i * 128; j.kA = s * 128;
       j.rowB = s * 128 + h * 64; j.kB = 0;
       j.nk = h ? 8 : 4;
-      j.crow = i * 128; j.ccol = s * 128 + h * 64;
+      j.crow = i * 128; j.ccol = (g.aux0 ? 0 : s * 128) + h * 64;  // aux0 = 1: into a [rows][128] panel buffer
     } break;
     case M_TRAIL: {  // A[i, c] -= L[i, K] L[c, K]^T, K = block columns [step, step + aux1); lower triangle of the
                      // trailing matrix with origin block o = aux0: rows i = o + ip, 64-col blocks c = 2 o + cp <= row

@@ -437,6 +437,18 @@ k_pred_finish(const __grid_constant__ dgp_spec spec, const double* __restrict__ 
 }  // namespace dgp
 
 namespace dgp {
+// In-place factorisation: block column s of L, staged by the panel solve in P[rows][128], goes back into the matrix.
+// grid = (row blocks below the diagonal block), block = 256.
+__global__ void __launch_bounds__(256)
+k_copy_panel(const double* __restrict__ P, double* __restrict__ A, long long ld, int s) {
+  const size_t row0 = (size_t)(s + 1 + blockIdx.x) * 128;
+  for (int e = threadIdx.x; e < 128 * 64; e += 256) {
+    const int r = e >> 6, c2 = (e & 63) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(P + (row0 + r) * 128 + c2);
+    *reinterpret_cast<double2*>(A + (row0 + r) * ld + (size_t)s * 128 + c2) = v;
+  }
+}
+
 // out[s, i] += mu[i]  (rows s < S, cols i < m), grid = (ceil(m/256), S)
 __global__ void __launch_bounds__(256) k_add_rowvec(double* __restrict__ out, long long ld, const double* __restrict__ mu, int m) {
   const int i = blockIdx.x * 256 + threadIdx.x;

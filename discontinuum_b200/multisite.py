@@ -176,3 +176,38 @@ def fit_sites(sites: Dict[int, tuple], iterations: int = 100, predict: Optional[
     local = fit_sites_local({k: sites[k] for k in mine}, iterations=iterations, device=device, concurrency=concurrency,
                             predict={k: predict[k] for k in mine} if predict else None)
     return gather_results(local, dist)
+
+
+# ---------------------------------------------------------------- sharded prediction grid
+def shard_rows(m: int, world: int) -> List[tuple]:
+    """Contiguous row ranges [start, stop) of an m-point grid, one per rank, sizes differing by at most one."""
+    base, rem = divmod(int(m), int(world))
+    out, start = [], 0
+    for r in range(world):
+        stop = start + base + (1 if r < rem else 0)
+        out.append((start, stop))
+        start = stop
+    return out
+
+
+def predict_sharded(engine, Xs: np.ndarray, dist=None, want_var: bool = True):
+    """Posterior mean / latent variance over a grid sharded across ranks.  Every rank holds the same factorisation
+    (fitted redundantly or loaded from the same checkpoint: `engine.factorize` was called with the same theta) and
+    predicts its contiguous slice; the only collective is the final all_gather of 16 m bytes.  `engine` is a
+    capi.Engine (anything with .predict(Xs, want_var) -> (mu, var)).  Returns (mu[m], var[m]) on every rank."""
+    Xs = np.ascontiguousarray(Xs, dtype=np.float64)
+    m = Xs.shape[0]
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lo, hi = shard_rows(m, world)[rank]
+    if hi > lo:
+        mu, var = engine.predict(Xs[lo:hi], want_var)
+    else:
+        mu, var = np.empty(0), (np.empty(0) if want_var else None)
+    if world == 1:
+        return mu, var
+    parts = [None] * world
+    dist.all_gather_object(parts, (np.asarray(mu), None if var is None else np.asarray(var)))
+    mu_all = np.concatenate([p[0] for p in parts])
+    var_all = np.concatenate([p[1] for p in parts]) if want_var else None
+    return mu_all, var_all

@@ -168,6 +168,24 @@ def test_sample_matches_oracle_given_same_normals(cuda_device):
     eng.close()
 
 
+def test_sample_multi_chunk_in_place_factorisation(cuda_device):
+    """m spans several prediction chunks and several panels of the in-place posterior Cholesky (ragged m, n)."""
+    n, m, S = 450, 1100, 8
+    X, y, noise = synthetic.loadest_site(n, 32)
+    theta = H.loadest_theta1()
+    nat = H.loadest_nat_from_theta(theta)
+    Xs = synthetic.daily_grid(X, m) + np.array([0.0007, 0.01])
+    Z = np.random.default_rng(1).standard_normal((S, m))
+    eng = _engine(models.loadest_spec(2), X, y, noise, max_m=256)
+    eng.factorize(theta)
+    draws, info = eng.sample(Xs, Z, jitter=1e-6)
+    assert info == 0
+    want, _ = orc.sample(orc.loadest_cov, orc.loadest_mean, nat, torch.tensor(X), torch.tensor(y), torch.tensor(noise),
+                         torch.tensor(Xs), torch.tensor(Z), jitter=1e-6)
+    assert np.max(np.abs(draws - want.numpy())) <= 1e-5 * np.max(np.abs(want.numpy()))
+    eng.close()
+
+
 def test_non_positive_definite_reports_info_and_jitter_repairs(cuda_device):
     """LAPACK-style info: 1-based index of the first non-positive pivot; jitter on the diagonal repairs it."""
     n = 300

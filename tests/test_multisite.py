@@ -56,6 +56,36 @@ def test_gather_results_world2_gloo(tmp_path):
     assert (tmp_path / "ok").exists()
 
 
+class _FakeEngine:
+    """Stands in for capi.Engine on the CPU: 'predicts' a known function of the inputs."""
+
+    def predict(self, Xs, want_var=True):
+        return Xs[:, 0] * 2.0 + Xs[:, 1], (Xs[:, 0] ** 2 if want_var else None)
+
+
+def _pred_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Xs = np.stack([np.arange(11.0), np.arange(11.0)[::-1]], axis=1)
+    mu, var = multisite.predict_sharded(_FakeEngine(), Xs, dist)
+    assert np.array_equal(mu, Xs[:, 0] * 2.0 + Xs[:, 1]) and np.array_equal(var, Xs[:, 0] ** 2)
+    mu2, var2 = multisite.predict_sharded(_FakeEngine(), Xs[:1], dist, want_var=False)  # fewer points than ranks
+    assert mu2.shape == (1,) and var2 is None
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_rows_and_sharded_prediction_world2_gloo(tmp_path):
+    assert multisite.shard_rows(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert multisite.shard_rows(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    for m, w in ((100000, 8), (10958, 3), (7, 7)):
+        rows = multisite.shard_rows(m, w)
+        assert rows[0][0] == 0 and rows[-1][1] == m and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+    mp.spawn(_pred_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
 @pytest.mark.gpu
 def test_concurrent_sites_match_single_site_fits(cuda_device):
     from discontinuum_b200 import synthetic
