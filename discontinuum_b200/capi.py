@@ -58,6 +58,7 @@ _SIGNATURES = [
     ("dgp_nlml_grad_wait", C.c_int, [_P, _P, _P]),
     ("dgp_factorize", C.c_int, [_P, _P, C.c_double, _P]),
     ("dgp_predict", C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    ("dgp_mean_functional_grad", C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     ("dgp_sample", C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_double, _P, C.c_int]),
     ("dgp_get_alpha", C.c_int, [_P, _P, C.c_int]),
     ("dgp_get_chol", C.c_int, [_P, _P, C.c_int]),
@@ -224,6 +225,17 @@ class Engine:
         self._check(self.lib.dgp_predict(self._h, _ptr(Xs)[0], m, 1 if on_dev else 0, _ptr(mu)[0],
                                          _ptr(var)[0] if want_var else None), "dgp_predict")
         return mu, var
+
+    def mean_functional_grad(self, Xs, c) -> Tuple[float, np.ndarray]:
+        """F = sum_p c[p] mu(Xs[p]) and dF/dtheta at the theta of the last nlml_grad / factorize."""
+        Xs, c = _f64(Xs), _f64(c).reshape(-1)
+        if Xs.ndim != 2 or Xs.shape[1] != self.ndim or c.shape[0] != Xs.shape[0]:
+            raise ValueError("mean_functional_grad: Xs[m, ndim], c[m] expected")
+        val = C.c_double(0.0)
+        grad = np.zeros(self.ntheta)
+        self._check(self.lib.dgp_mean_functional_grad(self._h, Xs.ctypes.data, int(Xs.shape[0]), c.ctypes.data,
+                                                      C.addressof(val), grad.ctypes.data), "dgp_mean_functional_grad")
+        return val.value, grad
 
     def sample(self, Xs, Z, jitter: float = 0.0) -> Tuple[np.ndarray, int]:
         """(draws[S, m], info): info > 0 means the posterior covariance (+ jitter) was not positive definite."""

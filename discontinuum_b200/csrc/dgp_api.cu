@@ -67,6 +67,10 @@ struct dgp_handle_s {
   double *bufA = nullptr, *bufL = nullptr, *bufU = nullptr, *DI = nullptr;
   double *X = nullptr, *y = nullptr, *noise = nullptr, *Xw = nullptr, *r = nullptr, *z = nullptr, *alpha = nullptr;
   double *theta = nullptr, *scal = nullptr, *gpart = nullptr, *zpart = nullptr;
+  // adjoint of the posterior mean (dgp_mean_functional_grad)
+  double *cvec = nullptr, *vvec = nullptr, *gam = nullptr, *tmpz = nullptr, *mfg_out = nullptr, *wpart = nullptr;
+  double* h_mfg = nullptr;
+  size_t wpart_count = 0;
   // prediction chunk
   double *Kx = nullptr, *Xs = nullptr, *Xws = nullptr, *means = nullptr, *dot = nullptr, *vpart = nullptr;
   double *mu = nullptr, *var = nullptr;
@@ -183,6 +187,8 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
   acc(A(&h->r, np)); acc(A(&h->z, np)); acc(A(&h->alpha, np));
   acc(A(&h->theta, DGP_MAX_THETA)); acc(A(&h->scal, SC_SIZE)); acc(A(&h->gpart, nbm * (nbm + 1) * DGP_MAX_THETA));
   acc(A(&h->zpart, nbm * np));
+  acc(A(&h->cvec, mc)); acc(A(&h->vvec, np)); acc(A(&h->gam, np)); acc(A(&h->tmpz, np)); acc(A(&h->mfg_out, 1 + DGP_MAX_THETA));
+  acc(cudaMallocHost((void**)&h->h_mfg, (1 + DGP_MAX_THETA) * sizeof(double)));
   acc(A(&h->Kx, mc * np)); acc(A(&h->Xs, mc * DGP_MAX_COLS)); acc(A(&h->Xws, mc * DGP_XS)); acc(A(&h->means, mc));
   acc(A(&h->dot, nbm * mc)); acc(A(&h->vpart, 2 * nbm * mc)); acc(A(&h->mu, mc)); acc(A(&h->var, mc));
   acc(cudaMallocHost((void**)&h->h_theta, DGP_MAX_THETA * sizeof(double)));
@@ -206,10 +212,11 @@ int dgp_destroy(dgp_handle h) {
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   for (auto& gs : h->graphs) if (gs.exec) cudaGraphExecDestroy(gs.exec);
   double* bufs[] = {h->bufA, h->bufL, h->bufU, h->DI, h->X, h->y, h->noise, h->Xw, h->r, h->z, h->alpha, h->theta,
-                    h->scal, h->gpart, h->zpart, h->Kx, h->Xs, h->Xws, h->means, h->dot, h->vpart, h->mu, h->var};
+                    h->scal, h->gpart, h->zpart, h->cvec, h->vvec, h->gam, h->tmpz, h->mfg_out, h->wpart, h->Kx, h->Xs, h->Xws, h->means, h->dot, h->vpart, h->mu, h->var};
   for (double* p : bufs) if (p) cudaFree(p);
   if (h->h_theta) cudaFreeHost(h->h_theta);
   if (h->h_scal) cudaFreeHost(h->h_scal);
+  if (h->h_mfg) cudaFreeHost(h->h_mfg);
   for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -643,7 +650,8 @@ int dgp_cross_covmat(dgp_handle h, const double* theta, const double* Xs, int m,
 int dgp_predict(dgp_handle h, const double* Xs, int m, int on_device, double* mu_out, double* var_out) {
   if (!h) return -1;
   if (!Xs || !mu_out || m < 1) DGP_FAIL(h, -1, "dgp_predict: bad arguments");
-  if (!h->factorized || !h->have_T) DGP_FAIL(h, -1, "dgp_predict: call dgp_factorize first");
+  if (!h->factorized || (var_out && !h->have_T))
+    DGP_FAIL(h, -1, "dgp_predict: call dgp_factorize first (the mean alone is also available after dgp_nlml_grad)");
   CK(h, cudaSetDevice(h->device));
   int rc;
   const cudaMemcpyKind okind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -670,6 +678,53 @@ int dgp_predict(dgp_handle h, const double* Xs, int m, int on_device, double* mu
     if (var_out) CK(h, cudaMemcpyAsync(var_out + m0, h->var, (size_t)mc * 8, okind, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------ adjoint of the posterior mean
+// F = sum_p c_p mu(x*_p) and dF/dtheta at the theta of the last dgp_nlml_grad / dgp_factorize (U = L^-T and alpha
+// resident).  Used by the rating-curve monotonicity penalty (src/rating_gp/models/gpytorch.py:126-187), whose value
+// is such a functional once the active set is fixed.  m <= the handle's prediction chunk.
+int dgp_mean_functional_grad(dgp_handle h, const double* Xs, int m, const double* c, double* val_out, double* grad_out) {
+  if (!h) return -1;
+  if (!Xs || !c || !grad_out || m < 1) DGP_FAIL(h, -1, "dgp_mean_functional_grad: bad arguments");
+  if (m > h->max_m) DGP_FAIL(h, -1, "dgp_mean_functional_grad: m=%d exceeds the prediction chunk %d", m, h->max_m);
+  if (!h->factorized || h->pending_grad < 1) DGP_FAIL(h, -1, "dgp_mean_functional_grad: call dgp_nlml_grad or dgp_factorize first");
+  CK(h, cudaSetDevice(h->device));
+  int rc;
+  const int mpad = round_up(m, 128), npad = h->npad, nb = h->nb;
+  const size_t nparts = (size_t)(mpad / 128 + nb) * (npad / 64);
+  if (h->wpart_count < nparts * DGP_MAX_THETA) {
+    if (h->wpart) cudaFree(h->wpart);
+    h->wpart = nullptr; h->wpart_count = 0;
+    CK(h, cudaMalloc((void**)&h->wpart, nparts * DGP_MAX_THETA * sizeof(double)));
+    h->wpart_count = nparts * DGP_MAX_THETA;
+  }
+  cudaStream_t st = h->stream;
+  if ((rc = stage_xs(h, Xs, 0, m, 0))) return rc;
+  CK(h, cudaMemsetAsync(h->cvec, 0, (size_t)mpad * 8, st));
+  CK(h, cudaMemcpyAsync(h->cvec, c, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+  k_cov_rect<<<dim3(mpad / 32, nb), 256, 0, st>>>(h->spec, h->theta, h->Xws, h->Xw, h->noise, 0.0, h->Kx, npad, m, h->n,
+                                                  0, 0, h->alpha, h->dot, h->max_m);
+  k_pred_finish<<<(m + 255) / 256, 256, 0, st>>>(h->spec, h->theta, h->Xws, h->means, h->dot, nb, nullptr, 0, h->max_m, m,
+                                                 h->mu, nullptr);
+  // gamma = Ky^-1 (Kx*' c) = U (U' v)
+  k_colsum_weighted<<<npad / 256 + (npad % 256 ? 1 : 0), 256, 0, st>>>(h->Kx, npad, h->cvec, mpad, h->vvec);
+  k_upperT_gemv_part<<<dim3(nb, nb), 256, 0, st>>>(h->bufU, npad, h->vvec, h->zpart, npad);
+  k_upperT_gemv_sum<<<(npad + 255) / 256, 256, 0, st>>>(h->zpart, npad, h->tmpz, npad);
+  k_upper_gemv<<<npad / 8, 256, 0, st>>>(h->bufU, npad, h->tmpz, h->gam, npad);
+  // the two weighted contractions of dK/dtheta
+  k_wgrad<<<dim3(npad / 64, mpad / 128), 128, 0, st>>>(h->spec, h->theta, h->Xws, h->Xw, h->cvec, h->alpha, 1.0, h->wpart);
+  k_wgrad<<<dim3(npad / 64, nb), 128, 0, st>>>(h->spec, h->theta, h->Xw, h->Xw, h->gam, h->alpha, -1.0,
+                                               h->wpart + (size_t)(mpad / 128) * (npad / 64) * DGP_MAX_THETA);
+  k_mfg_finish<<<h->spec.ntheta + 1, 256, 0, st>>>(h->spec, h->theta, h->wpart, (int)nparts, h->cvec, h->mu, h->Xs, m, h->gam,
+                                                   h->alpha, h->X, h->n, h->mfg_out);
+  h->launches += 9;
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(h->h_mfg, h->mfg_out, (1 + DGP_MAX_THETA) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  if (val_out) *val_out = h->h_mfg[0];
+  memcpy(grad_out, h->h_mfg + 1, sizeof(double) * h->spec.ntheta);
   return 0;
 }
 

@@ -455,3 +455,114 @@ __global__ void __launch_bounds__(256) k_add_rowvec(double* __restrict__ out, lo
   if (i < m) out[(size_t)blockIdx.y * ld + i] += mu[i];
 }
 }  // namespace dgp
+
+namespace dgp {
+// ------------------------------------------------------------------ gradient of a linear functional of the posterior mean
+// F(theta) = sum_p c_p mu(x*_p),  mu = m(x*) + K*x alpha:
+//   dF/dtheta_k = sum_{p,j} c_p alpha_j dk(x*_p, x_j)/dtheta_k - sum_{i,j} gamma_i alpha_j dK(x_i, x_j)/dtheta_k,
+//   gamma = Ky^-1 Kx* c  (adjoint of the solve).  Both sums are rank-1-weighted contractions of dK/dtheta:
+// k_wgrad: part[cta][t] = sgn * sum_{i in rows, j in cols of this 128x64 tile} wa_i wb_j dk(xa_i, xb_j)/dtheta_t.
+// grid = (col blocks of 64, row blocks of 128), block = 128 (thread = row); wa / wb are zero on padding.
+__global__ void __launch_bounds__(128)
+k_wgrad(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta, const double* __restrict__ XwA,
+        const double* __restrict__ XwB, const double* __restrict__ wa, const double* __restrict__ wb, double sgn,
+        double* __restrict__ part) {
+  __shared__ CovC cc;
+  __shared__ double xaT[DGP_XS * 128];
+  __shared__ double xb[64 * DGP_XS];
+  __shared__ double wbs[64];
+  __shared__ double red[4 * DGP_MAX_TERMS * NSLOT];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const size_t r0 = (size_t)blockIdx.y * 128, c0b = (size_t)blockIdx.x * 64;
+  cov_compile(&cc, spec, theta, 0.0, t, 128);
+  for (int e = t; e < 128 * DGP_XS; e += 128) xaT[(e % DGP_XS) * 128 + e / DGP_XS] = XwA[r0 * DGP_XS + e];
+  for (int e = t; e < 64 * DGP_XS; e += 128) xb[e] = XwB[c0b * DGP_XS + e];
+  if (t < 64) wbs[t] = wb[c0b + t];
+  __syncthreads();
+  const double wi = wa[r0 + t];
+  for (int term = 0; term < cc.nterms; term++) {
+    double sl[NSLOT];
+#pragma unroll
+    for (int k = 0; k < NSLOT; k++) sl[k] = 0.0;
+    const TermC& tc = cc.t[term];
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 4) {
+      double w[4];
+#pragma unroll
+      for (int v = 0; v < 4; v++) w[v] = wi * wbs[c0 + v];
+      term_grad_accum_v<4>(tc, xaT, 128, t, xb + c0 * DGP_XS, w, sl);
+    }
+#pragma unroll
+    for (int k = 0; k < NSLOT; k++) {
+      double v = sl[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[(warp * DGP_MAX_TERMS + term) * NSLOT + k] = v;
+    }
+  }
+  __syncthreads();
+  if (t < DGP_MAX_THETA) {
+    double s = 0.0;
+    if (t < cc.ntheta)
+      for (int term = 0; term < cc.nterms; term++)
+        for (int k = 0; k < NSLOT; k++)
+          if (term_slot_theta(cc.t[term], k) == t)
+            for (int w4 = 0; w4 < 4; w4++) s += red[(w4 * DGP_MAX_TERMS + term) * NSLOT + k];
+    part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * DGP_MAX_THETA + t] = sgn * s;
+  }
+}
+
+// v[j] = sum_p c[p] Kx[p, j]   (p < mpad), grid = npad / 256
+__global__ void __launch_bounds__(256)
+k_colsum_weighted(const double* __restrict__ Kx, long long ld, const double* __restrict__ c, int mpad, double* __restrict__ v) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= ld) return;
+  double s = 0.0;
+  for (int p = 0; p < mpad; p++) s = fma(c[p], Kx[(size_t)p * ld + j], s);
+  v[j] = s;
+}
+
+// block b < ntheta: grad[b] = sum_parts part[.][b] + mean-parameter terms + learned-noise term; block ntheta: F = c'mu.
+// out[0] = F, out[1 + b] = dF/dtheta_b.
+__global__ void __launch_bounds__(256)
+k_mfg_finish(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta, const double* __restrict__ part,
+             int nparts, const double* __restrict__ c, const double* __restrict__ mu, const double* __restrict__ Xs, int m,
+             const double* __restrict__ gamma, const double* __restrict__ alpha, const double* __restrict__ X, int n,
+             double* __restrict__ out) {
+  __shared__ double red[256];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  double s = 0.0;
+  if (b == spec.ntheta) {
+    for (int p = tid; p < m; p += 256) s = fma(c[p], mu[p], s);
+  } else {
+    for (int i = tid; i < nparts; i += 256) s += part[(size_t)i * DGP_MAX_THETA + b];
+    if (b == spec.noise_theta)
+      for (int i = tid; i < n; i += 256) s = fma(-gamma[i], alpha[i], s);
+    int mk = -1;
+    for (int k = 0; k < 3; k++)
+      if ((spec.mean_kind == DGP_MEAN_CONST && k == 0 && spec.mean_theta[0] == b) ||
+          (spec.mean_kind == DGP_MEAN_POWERLAW && spec.mean_theta[k] == b)) mk = k;
+    if (mk >= 0) {
+      double pb = 0.0, pc = 0.0;
+      if (spec.mean_kind == DGP_MEAN_POWERLAW) { pb = theta[spec.mean_theta[1]]; pc = theta[spec.mean_theta[2]]; }
+      for (int i = tid; i < m + n; i += 256) {
+        const bool test = i < m;
+        const double* x = test ? Xs + (size_t)i * spec.ndim : X + (size_t)(i - m) * spec.ndim;
+        double j = 1.0;  // d mean / d param
+        if (spec.mean_kind == DGP_MEAN_POWERLAW && mk > 0) {
+          const double u = x[spec.mean_col] - pc;
+          j = (mk == 1) ? log(u) : -pb / u;
+        }
+        s = fma(test ? c[i] : -gamma[i - m], j, s);
+      }
+    }
+  }
+  red[tid] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) out[(b == spec.ntheta) ? 0 : 1 + b] = red[0];
+}
+}  // namespace dgp

@@ -59,6 +59,7 @@ class _NLML(torch.autograd.Function):
         else:
             raise NotPSDError(f"Matrix not positive definite after adding jitter up to {JITTERS[-1]:g} (info={info})")
         owner._last_jitter = jit
+        owner._last_theta = th.copy()  # the factorisation of this theta stays resident (U, alpha): penalty adjoints reuse it
         ctx.grad = torch.from_numpy(grad.copy())
         return torch.tensor(val, dtype=torch.float64)
 
@@ -99,6 +100,7 @@ class MarginalB200:
         self._engine: Optional[capi.Engine] = None
         self._factorized_at = None
         self._last_jitter = 0.0
+        self._last_theta = None
         self.fixed_noise = None
         self.history = []
 

@@ -102,7 +102,7 @@ def stage_quantile_bounds(stage: np.ndarray):
 import torch  # noqa: E402
 
 from .data import LogStandardPipeline, TimePipeline, UnitPipeline  # noqa: E402
-from .engine import DataMixin, MarginalB200, ModelConfig  # noqa: E402
+from .engine import JITTERS, DataMixin, MarginalB200, ModelConfig  # noqa: E402
 from .spec import GPModule  # noqa: E402
 
 
@@ -163,13 +163,77 @@ class RatingGPMarginalB200(RatingDataMixin, MarginalB200):
     def fit(self, covariates, target, target_unc=None, iterations=100, optimizer=None, learning_rate=None,
             early_stopping=False, patience=60, scheduler=True, resume=False, monotonic_penalty_weight: float = 0.0,
             grid_size: int = 64, monotonic_penalty_interval: int = 1, **kw):
-        if monotonic_penalty_weight > 0:
-            raise NotImplementedError(
-                "monotonic rating penalty (src/rating_gp/models/gpytorch.py:126-202) is scheduled after the hot path "
-                "(SURVEY 8f.1): it needs the adjoint of the posterior mean w.r.t. theta")
+        """src/rating_gp/models/gpytorch.py:81-202: optional penalty on negative dQ/dStage of the posterior mean over a
+        random (time uniform, stage log-uniform) grid, every `monotonic_penalty_interval` iterations."""
+        if monotonic_penalty_weight <= 0:
+            return super().fit(covariates=covariates, target=target, target_unc=target_unc, iterations=iterations,
+                               optimizer=optimizer, learning_rate=learning_rate, early_stopping=early_stopping,
+                               patience=patience, scheduler=scheduler, resume=resume, **kw)
+        step = {"i": 0}
+
+        def penalty_callback():
+            step["i"] += 1
+            if monotonic_penalty_interval > 1 and (step["i"] % monotonic_penalty_interval) != 0:
+                return torch.zeros((), dtype=torch.float64)
+            grid = monotonic_penalty_grid(self.dm.X, grid_size)
+            pen = _MonotonicPenalty.apply(self.model.natural(), self, grid, 1e-3)
+            if monotonic_penalty_interval > 1:
+                pen = pen * float(monotonic_penalty_interval)
+            return pen
+
         return super().fit(covariates=covariates, target=target, target_unc=target_unc, iterations=iterations,
                            optimizer=optimizer, learning_rate=learning_rate, early_stopping=early_stopping,
-                           patience=patience, scheduler=scheduler, resume=resume, **kw)
+                           patience=patience, scheduler=scheduler, resume=resume, penalty_callback=penalty_callback,
+                           penalty_weight=float(monotonic_penalty_weight), **kw)
+
+
+def monotonic_penalty_grid(X: np.ndarray, grid_size: int = 64, time_dim: int = 0, stage_dim: int = 1) -> np.ndarray:
+    """The reference's random grid (rating_gp/models/gpytorch.py:139-158): float32 draws from torch's global generator,
+    time uniform over the training range (drawn first), stage log-uniform."""
+    x_min, x_max = X.min(axis=0), X.max(axis=0)
+    u_time = torch.rand((grid_size,), dtype=torch.float32)
+    time_grid = u_time * (x_max[time_dim] - x_min[time_dim]) + x_min[time_dim]
+    eps = 1e-6
+    log_xmin, log_xmax = float(np.log(x_min[stage_dim] + eps)), float(np.log(x_max[stage_dim] + eps))
+    u_stage = torch.rand((grid_size,), dtype=torch.float32)
+    stage_grid = torch.exp(u_stage * (log_xmax - log_xmin) + log_xmin)
+    cols = [None, None]
+    cols[time_dim], cols[stage_dim] = time_grid, stage_grid
+    return torch.stack(cols, dim=1).to(torch.float64).numpy()
+
+
+class _MonotonicPenalty(torch.autograd.Function):
+    """mean_p clamp(-(mu(x_p + eps e_stage) - mu(x_p)) / eps, 0) on the GPU engine.  With the active set fixed the
+    penalty is a linear functional c'mu of the posterior mean; its gradient w.r.t. natural theta comes from
+    dgp_mean_functional_grad (adjoint of the solve), replacing the reference's autograd through two predictions."""
+
+    @staticmethod
+    def forward(ctx, nat: torch.Tensor, owner: "RatingGPMarginalB200", grid: np.ndarray, fd_eps: float, stage_dim: int = 1):
+        th = nat.detach().cpu().numpy().astype(np.float64)
+        eng = owner._engine
+        if getattr(owner, "_last_theta", None) is None or not np.array_equal(owner._last_theta, th):
+            for jit in JITTERS:  # the factorisation of this theta must be resident (normally left by _NLML.forward)
+                val, _, info = eng.nlml_grad(th, jit)
+                if info == 0 and np.isfinite(val):
+                    break
+            owner._last_theta = th.copy()
+        G = grid.shape[0]
+        plus = grid.copy()
+        plus[:, stage_dim] += fd_eps
+        pts = np.ascontiguousarray(np.concatenate([grid, plus], axis=0))
+        mu, _ = eng.predict(pts, want_var=False)
+        d = (mu[G:] - mu[:G]) / fd_eps
+        active = d < 0.0
+        c = np.zeros(2 * G)
+        c[:G][active] = 1.0 / (G * fd_eps)
+        c[G:][active] = -1.0 / (G * fd_eps)
+        val, grad = eng.mean_functional_grad(pts, c)
+        ctx.grad = torch.from_numpy(grad.copy())
+        return torch.tensor(float(np.maximum(-d, 0.0).mean()), dtype=torch.float64)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.grad, None, None, None, None
 
 
 LoadestGP = LoadestGPMarginalB200

@@ -133,6 +133,13 @@ int dgp_factorize(dgp_handle h, const double* theta, double jitter, double* nlml
  * (host adds the likelihood-noise rule and clamp of SURVEY A.5).  var_out may be NULL. */
 int dgp_predict(dgp_handle h, const double* Xs, int m, int on_device, double* mu_out, double* var_out);
 
+/* Adjoint of the posterior mean: F = sum_p c[p] mu(Xs[p]) and dF/dtheta[ntheta] (natural parameters, including mean
+ * and learned-noise parameters) at the theta of the last dgp_nlml_grad / dgp_factorize.  Replaces the autograd pass
+ * through two eval-mode predictions in the rating-curve monotonicity penalty (rating_gp/models/gpytorch.py:126-187):
+ * once the active set is fixed the penalty is such a functional.  Host pointers; m <= prediction chunk. */
+int dgp_mean_functional_grad(dgp_handle h, const double* Xs, int m, const double* c, double* val_out,
+                             double* grad_out);
+
 /* Joint latent posterior draws out[S, m] = mu* + Z[S, m] Lpost' with Lpost the exact Cholesky
  * factor of K** - K*x Ky^-1 Kx* (+ jitter I).  Z: caller-supplied standard normals. */
 int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, double jitter,

@@ -332,6 +332,34 @@ def predict(cov, mean, nat, X, y, noise, Xs, extra_noise=None, min_variance=1e-1
     return mu, torch.clamp_min(var_obs, min_variance), var_lat
 
 
+def monotonic_penalty(cov, mean, nat, X, y, noise, x_grid, stage_dim=1, fd_eps=1e-3, extra_noise=None):
+    """rating_gp/models/gpytorch.py:126-187: mean over the grid of clamp(-(mu(x + eps e_stage) - mu(x)) / eps, min=0),
+    mu = eval-mode posterior mean; differentiable w.r.t. nat through the solve (what the reference's autograd does)."""
+    mu = predict(cov, mean, nat, X, y, noise, x_grid, extra_noise)[0]
+    xp = x_grid.clone()
+    xp[:, stage_dim] = x_grid[:, stage_dim] + fd_eps
+    mu_plus = predict(cov, mean, nat, X, y, noise, xp, extra_noise)[0]
+    d = (mu_plus - mu) / fd_eps
+    return torch.clamp(-d, min=0.0).mean()
+
+
+def monotonic_grid(X, grid_size=64, time_dim=0, stage_dim=1):
+    """The reference's random penalty grid (rating_gp/models/gpytorch.py:139-158): time uniform, stage log-uniform,
+    both drawn in float32 from torch's global generator (time first)."""
+    import numpy as np
+
+    x_min, x_max = np.asarray(X).min(axis=0), np.asarray(X).max(axis=0)
+    u_time = torch.rand((grid_size,), dtype=torch.float32)
+    time_grid = u_time * (x_max[time_dim] - x_min[time_dim]) + x_min[time_dim]
+    eps = 1e-6
+    log_xmin, log_xmax = float(np.log(x_min[stage_dim] + eps)), float(np.log(x_max[stage_dim] + eps))
+    u_stage = torch.rand((grid_size,), dtype=torch.float32)
+    stage_grid = torch.exp(u_stage * (log_xmax - log_xmin) + log_xmin)
+    cols = [None, None]
+    cols[time_dim], cols[stage_dim] = time_grid, stage_grid
+    return torch.stack(cols, dim=1).to(DT)
+
+
 def _diag_cov(cov, Xs, nat, chunk=2048):
     out = []
     for i in range(0, Xs.shape[0], chunk):
@@ -361,7 +389,7 @@ def sample(cov, mean, nat, X, y, noise, Xs, Z, extra_noise=None, jitter=0.0):
 # fit-trajectory parity tests and the CPU baseline
 # ----------------------------------------------------------------------------------------
 def fit_adam(model, raw, X, y, noise, iterations=100, lr=0.05, b_lo=None, b_hi=None,
-             optimizer="adam", scheduler=True, patience=60, h_min=None):
+             optimizer="adam", scheduler=True, patience=60, h_min=None, penalty_weight=0.0, grid_size=64):
     params = [v.requires_grad_(True) for v in raw.values()]
     if optimizer == "adam":
         opt = torch.optim.Adam(params, lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
@@ -378,6 +406,11 @@ def fit_adam(model, raw, X, y, noise, iterations=100, lr=0.05, b_lo=None, b_hi=N
         if model == "rating":
             rating_project_(raw, h_min)
         obj = objective(model, raw, X, y, noise, b_lo, b_hi)
+        if penalty_weight > 0.0 and model == "rating":  # engines/gpytorch.py:371-373 with the rating-gp callback
+            nat = rating_natural(raw, b_lo, b_hi)
+            grid = monotonic_grid(X.numpy(), grid_size)
+            obj = obj + penalty_weight * monotonic_penalty(rating_cov, rating_mean, nat, X, y, noise, grid,
+                                                           extra_noise=nat["noise"])
         obj.backward()
         torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
         opt.step()

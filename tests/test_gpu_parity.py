@@ -186,6 +186,43 @@ def test_sample_multi_chunk_in_place_factorisation(cuda_device):
     eng.close()
 
 
+@pytest.mark.parametrize("model", ["loadest", "rating"])
+def test_mean_functional_gradient_vs_autograd(cuda_device, model):
+    """dgp_mean_functional_grad: F = c'mu(X*) and dF/dtheta against torch autograd through the solve (oracle)."""
+    n, m = 300, 100
+    rng = np.random.default_rng(5)
+    if model == "loadest":
+        X, y, noise = synthetic.loadest_site(n, 41)
+        spec, theta = models.loadest_spec(2), H.loadest_theta1()
+        nat0 = H.loadest_nat_from_theta(theta)
+        cov, mean, extra, to_theta = orc.loadest_cov, orc.loadest_mean, None, H.loadest_theta_from_nat
+    else:
+        X, y, noise = synthetic.rating_gauge(n, 7)
+        b_lo, b_hi = models.stage_quantile_bounds(X[:, 1])
+        spec, theta = models.rating_spec(b_lo, b_hi), H.rating_theta1(b_lo, b_hi)
+        nat0 = H.rating_nat_from_theta(theta)
+        cov, mean, extra, to_theta = orc.rating_cov, orc.rating_mean, "noise", H.rating_theta_from_nat
+    Xs = synthetic.daily_grid(X, m) + np.array([0.004, 0.0])
+    c = rng.standard_normal(m)
+    eng = _engine(spec, X, y, noise)
+    _, _, info = eng.nlml_grad(theta)
+    assert info == 0
+    val, grad = eng.mean_functional_grad(Xs, c)
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in nat0.items()}
+    mu = orc.predict(cov, mean, leaves, torch.tensor(X), torch.tensor(y), torch.tensor(noise), torch.tensor(Xs),
+                     leaves[extra] if extra else None)[0]
+    F = (torch.tensor(c) * mu).sum()
+    gs = torch.autograd.grad(F, list(leaves.values()), allow_unused=True)
+    want = to_theta({k: (g if g is not None else torch.zeros_like(leaves[k])).numpy() for k, g in zip(leaves, gs)})
+    assert abs(val - float(F)) <= RTOL * abs(float(F))
+    _grad_close(grad, want)
+    # the same call after dgp_factorize (prediction state) gives the same numbers
+    eng.factorize(theta)
+    val2, grad2 = eng.mean_functional_grad(Xs, c)
+    assert abs(val2 - val) <= 1e-12 * abs(val) and np.max(np.abs(grad2 - grad)) <= 1e-10 * np.max(np.abs(grad))
+    eng.close()
+
+
 def test_non_positive_definite_reports_info_and_jitter_repairs(cuda_device):
     """LAPACK-style info: 1-based index of the first non-positive pivot; jitter on the diagonal repairs it."""
     n = 300
@@ -354,8 +391,18 @@ def test_engine_fit_trajectory_matches_reference_loop_rating(cuda_device):
     assert np.max(np.abs(np.array(m.history) - np.array(hist)) / np.abs(hist)) <= RTOL
     target, se = m.predict({"time": time, "stage": stage})
     assert target.shape == (n,) and np.all(np.isfinite(target)) and np.all(se >= 1.0)
-    with pytest.raises(NotImplementedError):
-        models.RatingGP().fit({"time": time, "stage": stage}, q, target_unc=gse, iterations=2, monotonic_penalty_weight=0.5)
+    # monotonic rating penalty (src/rating_gp/models/gpytorch.py:126-202; reference test tests/test_rating_gp.py:52-65):
+    # same random grids (torch global generator), same objective trajectory as autograd through two predictions
+    torch.manual_seed(3)
+    mp_ = models.RatingGP()
+    mp_.fit({"time": time, "stage": stage}, q, target_unc=gse, iterations=8, monotonic_penalty_weight=0.5, grid_size=64)
+    torch.manual_seed(3)
+    a = float(torch.randn(1)); b = float(torch.randn(1) + 1.3); c = float(torch.rand(1)); u = float(torch.rand(1))
+    raw = orc.rating_init_raw(b_lo, b_hi, gate_b=b_lo + u * (b_hi - b_lo), pl_a=a, pl_b=b, pl_c=c)
+    _, histp = orc.fit_adam("rating", raw, torch.tensor(mp_.X), torch.tensor(mp_.y), torch.tensor(mp_.fixed_noise), iterations=8,
+                            b_lo=b_lo, b_hi=b_hi, h_min=float(mp_.X[:, 1].min()), penalty_weight=0.5, grid_size=64)
+    assert mp_.is_fitted and np.max(np.abs(np.array(mp_.history) - np.array(histp)) / np.abs(histp)) <= RTOL
+    assert np.max(np.abs(np.array(histp) - np.array(hist[:8]))) > 0  # the penalty was active on this data
 
 
 def test_graft_smoke(cuda_device):
