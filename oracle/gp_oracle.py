@@ -385,6 +385,37 @@ def sample(cov, mean, nat, X, y, noise, Xs, Z, extra_noise=None, jitter=0.0):
 
 
 # ----------------------------------------------------------------------------------------
+# PyMC variant (loadest_gp/models/pymc.py:37-88): PyMC's own kernel formulas
+# ----------------------------------------------------------------------------------------
+def pymc_loadest_cov(X1, X2, v):
+    """eta_per^2 Periodic(period, ls_psmooth) Matern52(ls_pdecay) + eta_trend^2 ExpQuad(t) + eta_cov^2 ExpQuad(q)
+    + eta_res^2 Matern32(t, q), with pm.gp.cov semantics: Periodic = exp(-sin^2(pi |d| / T) / (2 ls^2)),
+    ExpQuad = exp(-|d|^2 / (2 ls^2)), Matern as GPyTorch's."""
+    d = X1.shape[1]
+    t1, t2 = X1[:, 0:1], X2[:, 0:1]
+    dt = (t1 - t2.T).abs()
+    per = torch.exp(-torch.sin(math.pi * dt / v["period"]) ** 2 / (2.0 * v["ls_psmooth"] ** 2))
+    seasonal = v["eta_per"] ** 2 * per * k_matern(X1, X2, [0], v["ls_pdecay"], 2.5)
+    trend = v["eta_trend"] ** 2 * k_rbf(X1, X2, [0], v["ls_trend"])
+    covs = v["eta_covariates"] ** 2 * k_rbf(X1, X2, list(range(1, d)), v["ls_covariates"])
+    res = v["eta_res"] ** 2 * k_matern(X1, X2, list(range(d)), v["ls_res"], 1.5)
+    return seasonal + trend + covs + res
+
+
+def pymc_loadest_neg_logp(v, X, y, sigma=0.1, jitter=1e-6):
+    """-(log N(y | 0, K + (sigma^2 + jitter) I) + sum log prior), the quantity pm.find_MAP minimises (no Jacobian)."""
+    n = X.shape[0]
+    Ky = pymc_loadest_cov(X, X, v) + (sigma ** 2 + jitter) * torch.eye(n, dtype=DT)
+    val = nlml_from_K(Ky, y)[0]
+    lp = lp_halfnormal(v["eta_per"], 1.0).sum() + lp_gamma(v["ls_pdecay"], 10.0, 1.0).sum() + lp_normal(v["period"], 1.0, 0.05).sum()
+    lp = lp + lp_gamma(v["ls_psmooth"], 4.0, 3.0).sum() + (-math.log(1.5) - v["eta_trend"] / 1.5).sum()
+    lp = lp + lp_gamma(v["ls_trend"], 4.0, 1.0).sum() + lp_halfnormal(v["eta_covariates"], 2.0).sum()
+    lp = lp + lp_gamma(v["ls_covariates"], 2.0, 3.0).sum() + (-math.log(0.2) - v["eta_res"] / 0.2).sum()
+    lp = lp + lp_gamma(v["ls_res"], 2.0, 10.0).sum()
+    return val - lp
+
+
+# ----------------------------------------------------------------------------------------
 # reference optimiser loop restated (discontinuum/engines/gpytorch.py:266-444), used by the
 # fit-trajectory parity tests and the CPU baseline
 # ----------------------------------------------------------------------------------------
