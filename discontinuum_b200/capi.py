@@ -41,6 +41,11 @@ class DgpSpec(C.Structure):
                 ("mean_theta", C.c_int32 * 4), ("col", DgpCol * MAX_COLS), ("term", DgpTerm * MAX_TERMS)]
 
 
+class DgpFluxReduce(C.Structure):
+    _fields_ = [("y_mean", C.c_double), ("y_scale", C.c_double), ("log_transform", C.c_int32), ("ngroups", C.c_int32),
+                ("weight", C.c_void_p), ("group_start", C.c_void_p)]
+
+
 # every symbol include/dgp.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 _SIGNATURES = [
@@ -60,6 +65,7 @@ _SIGNATURES = [
     ("dgp_predict", C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     ("dgp_mean_functional_grad", C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     ("dgp_sample", C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_double, _P, C.c_int]),
+    ("dgp_sample_ex", C.c_int, [_P, _P, C.c_int, _P, C.c_ulonglong, C.c_int, C.c_double, C.POINTER(DgpFluxReduce), _P, C.c_int]),
     ("dgp_get_alpha", C.c_int, [_P, _P, C.c_int]),
     ("dgp_get_chol", C.c_int, [_P, _P, C.c_int]),
     ("dgp_set_debug_kinv", C.c_int, [_P, C.c_int]),
@@ -246,6 +252,32 @@ class Engine:
         out = np.empty((S, m))
         info = self._check(self.lib.dgp_sample(self._h, Xs.ctypes.data, m, Z.ctypes.data, S, float(jitter), out.ctypes.data, 0),
                            "dgp_sample")
+        return out, info
+
+    def sample_ex(self, Xs, S: int, Z=None, seed: int = 0, jitter: float = 0.0, flux: Optional[dict] = None):
+        """Draws with device-generated normals (Z=None -> Philox stream `seed`) and / or the grouped flux reduction.
+        flux = {"y_mean", "y_scale", "log_transform", "weight"[m], "group_start"[G+1]} -> returns [S, G] instead of [S, m]."""
+        Xs = _f64(Xs)
+        m = int(Xs.shape[0])
+        zp = None
+        if Z is not None:
+            Z = _f64(Z)
+            if Z.shape != (S, m):
+                raise ValueError("sample_ex: Z[S, m] expected")
+            zp = Z.ctypes.data
+        red = None
+        if flux is not None:
+            w = _f64(flux["weight"]).reshape(-1)
+            gs = np.ascontiguousarray(np.asarray(flux["group_start"], dtype=np.int32))
+            if w.shape[0] != m:
+                raise ValueError("sample_ex: weight[m] expected")
+            red = DgpFluxReduce(float(flux["y_mean"]), float(flux["y_scale"]), int(flux.get("log_transform", 1)),
+                                int(gs.shape[0] - 1), w.ctypes.data, gs.ctypes.data)
+            out = np.empty((S, gs.shape[0] - 1))
+        else:
+            out = np.empty((S, m))
+        info = self._check(self.lib.dgp_sample_ex(self._h, Xs.ctypes.data, m, zp, int(seed), int(S), float(jitter),
+                                                  C.byref(red) if red is not None else None, out.ctypes.data, 0), "dgp_sample_ex")
         return out, info
 
     # -- parity / debug

@@ -737,7 +737,20 @@ int dgp_mean_functional_grad(dgp_handle h, const double* Xs, int m, const double
 //   out [S, m] = Z [S, m] Lpost'     (triangular k range) + mu
 int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, double jitter, double* out, int on_device) {
   if (!h) return -1;
-  if (!Xs || !Z || !out || m < 1 || S < 1) DGP_FAIL(h, -1, "dgp_sample: bad arguments");
+  if (!Z) DGP_FAIL(h, -1, "dgp_sample: Z is NULL (use dgp_sample_ex for device-generated normals)");
+  return dgp_sample_ex(h, Xs, m, Z, 0ull, S, jitter, nullptr, out, on_device);
+}
+
+int dgp_sample_ex(dgp_handle h, const double* Xs, int m, const double* Z, unsigned long long seed, int S, double jitter,
+                  const dgp_flux_reduce* red, double* out, int on_device) {
+  if (!h) return -1;
+  if (!Xs || !out || m < 1 || S < 1) DGP_FAIL(h, -1, "dgp_sample: bad arguments");
+  if (red && (red->ngroups < 1 || !red->weight || !red->group_start)) DGP_FAIL(h, -1, "dgp_sample_ex: bad reduction spec");
+  if (red) {
+    if (red->group_start[0] < 0 || red->group_start[red->ngroups] > m) DGP_FAIL(h, -1, "dgp_sample_ex: group range outside the grid");
+    for (int g = 0; g < red->ngroups; g++)
+      if (red->group_start[g] > red->group_start[g + 1]) DGP_FAIL(h, -1, "dgp_sample_ex: group_start must be non-decreasing");
+  }
   if (!h->factorized || !h->have_T) DGP_FAIL(h, -1, "dgp_sample: call dgp_factorize first");
   CK(h, cudaSetDevice(h->device));
   const int mpad = round_up(m, 128), Spad = round_up(S, 128), npad = h->npad, mb = mpad / 128;
@@ -748,8 +761,9 @@ int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, do
   // handle's prediction chunk, so the footprint is 8 (m n + m^2) B + O(m): 106 GB at m = 100k, n = 32k.
   double *Xsd = nullptr, *Xws = nullptr, *means = nullptr, *dot = nullptr, *mu = nullptr, *VT = nullptr;
   double *Sig = nullptr, *Pb = nullptr, *DI2 = nullptr, *Zd = nullptr, *Od = nullptr, *zero = nullptr, *scal2 = nullptr;
+  double *wd = nullptr, *gout = nullptr, *gstart = nullptr;
   struct Freer {
-    double** p[14]; int k = 0;
+    double** p[18]; int k = 0;
     ~Freer() { for (int i = 0; i < k; i++) if (*p[i]) cudaFree(*p[i]); }
   } fr;
   auto A = [&](double** p, size_t count) {
@@ -762,6 +776,9 @@ int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, do
   acc(A(&dot, (size_t)h->nb * mpad)); acc(A(&mu, mpad)); acc(A(&VT, (size_t)mpad * npad));
   acc(A(&Sig, (size_t)mpad * mpad)); acc(A(&Pb, (size_t)mpad * 128)); acc(A(&DI2, (size_t)mpad * 128));
   acc(A(&Zd, (size_t)Spad * mpad)); acc(A(&Od, (size_t)Spad * mpad)); acc(A(&zero, mpad)); acc(A(&scal2, SC_SIZE));
+  if (red) {
+    acc(A(&wd, mpad)); acc(A(&gout, (size_t)S * red->ngroups)); acc(A(&gstart, (size_t)(red->ngroups + 2) / 2 + 1));
+  }
   if (r != cudaSuccess) {
     cudaGetLastError();
     DGP_FAIL(h, -2, "dgp_sample: workspace allocation failed for m=%d, S=%d: %s", m, S, cudaGetErrorString(r));
@@ -772,7 +789,12 @@ int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, do
   CK(h, cudaMemsetAsync(Zd, 0, (size_t)Spad * mpad * 8, h->stream));
   CK(h, cudaMemsetAsync(Xsd, 0, (size_t)mpad * DGP_MAX_COLS * 8, h->stream));
   CK(h, cudaMemcpyAsync(Xsd, Xs, (size_t)m * h->spec.ndim * 8, ikind, h->stream));
-  CK(h, cudaMemcpy2DAsync(Zd, (size_t)mpad * 8, Z, (size_t)m * 8, (size_t)m * 8, S, ikind, h->stream));
+  if (Z != nullptr) {
+    CK(h, cudaMemcpy2DAsync(Zd, (size_t)mpad * 8, Z, (size_t)m * 8, (size_t)m * 8, S, ikind, h->stream));
+  } else {
+    k_fill_normals<<<dim3((m + 255) / 256, S), 256, 0, h->stream>>>(Zd, mpad, m, seed);
+    h->launches++;
+  }
   k_features<<<(mpad + 255) / 256, 256, 0, h->stream>>>(h->spec, h->theta, Xsd, nullptr, Xws, nullptr, means, m, mpad, nullptr);
   h->launches++;
   CK(h, cudaGetLastError());
@@ -817,7 +839,17 @@ int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, do
   k_add_rowvec<<<dim3((m + 255) / 256, S), 256, 0, h->stream>>>(Od, mpad, mu, m);
   h->launches++;
   CK(h, cudaGetLastError());
-  CK(h, cudaMemcpy2DAsync(out, (size_t)m * 8, Od, (size_t)mpad * 8, (size_t)m * 8, S, okind, h->stream));
+  if (red == nullptr) {
+    CK(h, cudaMemcpy2DAsync(out, (size_t)m * 8, Od, (size_t)mpad * 8, (size_t)m * 8, S, okind, h->stream));
+  } else {  // annual (grouped) flux of every draw, reduced where the draws are
+    CK(h, cudaMemcpyAsync(wd, red->weight, (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(gstart, red->group_start, (size_t)(red->ngroups + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    k_flux_reduce<<<dim3(red->ngroups, (S + 7) / 8), 256, 0, h->stream>>>(Od, mpad, wd, (const int*)gstart, red->ngroups, S,
+                                                                      red->y_mean, red->y_scale, red->log_transform, gout);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(out, gout, (size_t)S * red->ngroups * 8, okind, h->stream));
+  }
   CK(h, cudaMemcpyAsync(h->h_scal, scal2, SC_SIZE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   return (int)h->h_scal[SC_INFO];

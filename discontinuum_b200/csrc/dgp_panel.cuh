@@ -457,6 +457,59 @@ __global__ void __launch_bounds__(256) k_add_rowvec(double* __restrict__ out, lo
 }  // namespace dgp
 
 namespace dgp {
+// ------------------------------------------------------------------ base normals on the device
+// Standard normal number e of the stream keyed by `seed`: Philox4x32-10 on counter (e >> 1, 0), key = seed, gives
+// two 53-bit uniforms u1, u2 in (0, 1); z = sqrt(-2 ln u1) * (e odd ? sin : cos)(2 pi u2)   (Box-Muller).
+// tests/test_gpu_parity.py restates the generator in numpy.
+__device__ __forceinline__ double philox_normal(unsigned long long seed, unsigned long long e) {
+  unsigned int c0 = (unsigned int)(e >> 1), c1 = (unsigned int)(e >> 33), c2 = 0u, c3 = 0u;
+  unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const unsigned long long a = ((unsigned long long)c1 << 32) | c0, b = ((unsigned long long)c3 << 32) | c2;
+  const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  const double rad = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  return rad * ((e & 1ull) ? sn : cs);
+}
+
+// Z[s, i] = normal number s * m + i, rows s < S, cols i < m of a [*, ld] matrix.  grid = (ceil(m / 256), S)
+__global__ void __launch_bounds__(256)
+k_fill_normals(double* __restrict__ Z, long long ld, int m, unsigned long long seed) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < m) Z[(size_t)blockIdx.y * ld + i] = philox_normal(seed, (unsigned long long)blockIdx.y * (unsigned long long)m + i);
+}
+
+// ------------------------------------------------------------------ flux post-processing of the draws
+// out[s, g] = sum_{i in [start[g], start[g+1])} w[i] * T(draw[s, i]),  T(z) = exp(z * scale + mean) (log pipelines,
+// clipped below at 1e-6 like the reference's inverse transform), z * scale + mean clipped at 0 (standard pipeline), or affine:
+// concentration_to_flux + resample("YE").sum() of src/loadest_gp/utils.py:14-56,89 without moving the draws.
+// grid = (groups, ceil(S / 8)), block = 256: one warp per (draw, group).
+__global__ void __launch_bounds__(256)
+k_flux_reduce(const double* __restrict__ D, long long ld, const double* __restrict__ w, const int* __restrict__ start,
+              int ngroups, int S, double mean, double scale, int log_transform, double* __restrict__ out) {
+  const int g = blockIdx.x, s = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s >= S) return;
+  const double* row = D + (size_t)s * ld;
+  double acc = 0.0;
+  for (int i = start[g] + lane; i < start[g + 1]; i += 32) {
+    double v = fma(row[i], scale, mean);
+    if (log_transform == 1) v = fmax(exp(v), 1e-6);
+    else if (log_transform == 2) v = fmax(v, 0.0);
+    acc = fma(w[i], v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[(size_t)s * ngroups + g] = acc;
+}
+
 // ------------------------------------------------------------------ gradient of a linear functional of the posterior mean
 // F(theta) = sum_p c_p mu(x*_p),  mu = m(x*) + K*x alpha:
 //   dF/dtheta_k = sum_{p,j} c_p alpha_j dk(x*_p, x_j)/dtheta_k - sum_{i,j} gamma_i alpha_j dK(x_i, x_j)/dtheta_k,

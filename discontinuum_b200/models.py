@@ -133,6 +133,42 @@ class LoadestGPMarginalB200(LoadestDataMixin, MarginalB200):
         self.fixed_noise = np.full(y.shape[0], LOADEST_FIXED_NOISE)
         return GPModule(loadest_spec(X.shape[1]))
 
+    def sample_annual_flux(self, covariates, n: int = 1000, seed: int = 0, flow_key: str = "flow", time_key: str = "time"):
+        """Annual flux (kg / year) of `n` joint posterior draws over a regular (e.g. daily) grid, reduced on the GPU:
+        draws -> concentration (inverse target pipeline) -> concentration * flow * dt * 1e-3 (src/loadest_gp/utils.py:
+        14-56) -> sum per calendar year (`flux.resample(time="YE").sum()`, utils.py:89).  The n x m draw matrix and its
+        base normals never leave the device.  Returns (years[G], flux[n, G])."""
+        from .data import _cov_dict
+        from .engine import JITTERS, NotPSDError
+
+        if not self.is_fitted:
+            raise RuntimeError("The model hasn't been fitted yet, call .fit().")
+        cov = _cov_dict(covariates)
+        time = np.asarray(cov[time_key]).astype("datetime64[ns]")
+        if np.any(np.diff(time) <= np.timedelta64(0, "ns")):
+            raise ValueError("sample_annual_flux needs a strictly increasing time grid")
+        dts = np.unique(np.diff(time).astype("timedelta64[ns]").astype(np.int64))
+        if dts.shape[0] != 1:
+            import warnings
+
+            warnings.warn("Time delta is not constant", UserWarning, stacklevel=2)
+        dt_s = float(dts[0]) * 1e-9
+        weight = np.asarray(cov[flow_key], dtype=np.float64) * dt_s * 1e-3
+        years = time.astype("datetime64[Y]").astype(np.int64) + 1970
+        uniq, first = np.unique(years, return_index=True)
+        group_start = np.concatenate([first, [time.shape[0]]]).astype(np.int32)
+        tp = self.dm.target_pipeline
+        log_t = 1 if isinstance(tp, LogStandardPipeline) else 2  # exp clipped at 1e-6 | affine clipped at 0 (data.py pipelines)
+        Xnew = np.ascontiguousarray(self.dm.Xnew(covariates), dtype=np.float64)
+        self._ensure_factorized(Xnew)
+        for jit in JITTERS:
+            flux, info = self._engine.sample_ex(Xnew, n, Z=None, seed=seed, jitter=jit,
+                                                flux=dict(y_mean=float(tp.mean_), y_scale=float(tp.scale_), log_transform=log_t,
+                                                          weight=weight, group_start=group_start))
+            if info == 0 and np.all(np.isfinite(flux)):
+                return uniq, flux
+        raise NotPSDError("posterior covariance not positive definite")
+
 
 class RatingGPMarginalB200(RatingDataMixin, MarginalB200):
     """Stage-discharge rating-curve GP on the B200 engine (src/rating_gp/models/gpytorch.py:43-265)."""

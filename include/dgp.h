@@ -145,6 +145,25 @@ int dgp_mean_functional_grad(dgp_handle h, const double* Xs, int m, const double
 int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, double jitter,
                double* out, int on_device);
 
+/* Extended sampling entry.
+ *  - Z == NULL: the base normals are generated on the device, Z[s, i] = standard normal number s*m + i of the
+ *    Philox4x32-10 stream keyed by `seed` (Box-Muller; generator documented in csrc/dgp_panel.cuh), so the S x m
+ *    matrix never crosses PCIe.
+ *  - red != NULL: instead of the draws, out[S, ngroups] receives, for every draw, the grouped sums
+ *      sum_{i in [group_start[g], group_start[g+1])} weight[i] * T(draw[s, i]),  T(z) = exp(z*y_scale + y_mean) or affine,
+ *    i.e. concentration_to_flux + annual resample-sum of src/loadest_gp/utils.py:14-56,89 applied on the device
+ *    (weight[i] = flow_i * dt * 1e-3, groups = calendar years of a time-sorted grid).  weight / group_start: host. */
+typedef struct {
+  double y_mean, y_scale;       /* target pipeline: model space -> original units                 */
+  int32_t log_transform;        /* 1: exp, clipped below at 1e-6 (LogStandardPipeline); 2: affine clipped at 0
+                                   (StandardPipeline); 0: affine                                     */
+  int32_t ngroups;
+  const double* weight;         /* [m]                                                              */
+  const int32_t* group_start;   /* [ngroups + 1], non-decreasing indices into the grid              */
+} dgp_flux_reduce;
+int dgp_sample_ex(dgp_handle h, const double* Xs, int m, const double* Z, unsigned long long seed, int S,
+                  double jitter, const dgp_flux_reduce* red, double* out, int on_device);
+
 /* Parity accessors (valid after dgp_nlml* / dgp_factorize): alpha[n]; L[n, n] lower triangular. */
 int dgp_get_alpha(dgp_handle h, double* alpha_out, int out_on_device);
 int dgp_get_chol(dgp_handle h, double* L_out, int out_on_device);

@@ -62,3 +62,25 @@ def rating_theta1(b_lo, b_hi):
 def relerr(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def philox_normals(seed: int, count: int) -> np.ndarray:
+    """numpy restatement of csrc/dgp_panel.cuh::philox_normal: Philox4x32-10 on counter (e >> 1, 0), key = seed,
+    two 53-bit uniforms, Box-Muller (cos for even e, sin for odd e)."""
+    e = np.arange(count, dtype=np.uint64)
+    ctr = e >> np.uint64(1)
+    c0, c1 = (ctr & np.uint64(0xFFFFFFFF)), (ctr >> np.uint64(32))
+    c2, c3 = np.zeros_like(c0), np.zeros_like(c0)
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & MASK, (k1 + np.uint64(0xBB67AE85)) & MASK
+    a, b = (c1 << np.uint64(32)) | c0, (c3 << np.uint64(32)) | c2
+    u1 = ((a >> np.uint64(11)).astype(np.float64) + 0.5) / 9007199254740992.0
+    u2 = ((b >> np.uint64(11)).astype(np.float64) + 0.5) / 9007199254740992.0
+    rad = np.sqrt(-2.0 * np.log(u1))
+    ang = 2.0 * np.pi * u2
+    return rad * np.where((e & np.uint64(1)) == 1, np.sin(ang), np.cos(ang))

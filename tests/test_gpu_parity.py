@@ -186,6 +186,41 @@ def test_sample_multi_chunk_in_place_factorisation(cuda_device):
     eng.close()
 
 
+def test_sample_device_normals_and_fused_flux_reduction(cuda_device):
+    """dgp_sample_ex: (i) Z = NULL draws equal the draws from the numpy restatement of the Philox stream;
+    (ii) the grouped flux reduction equals concentration_to_flux + annual sums computed on the host from the draws."""
+    n, m, S = 300, 730, 24
+    X, y, noise = synthetic.loadest_site(n, 33)
+    theta = H.loadest_theta1()
+    Xs = synthetic.daily_grid(X, m) + np.array([0.0011, 0.0])
+    eng = _engine(models.loadest_spec(2), X, y, noise)
+    eng.factorize(theta)
+    Z = H.philox_normals(1234567891011, S * m).reshape(S, m)
+    assert abs(Z.mean()) < 0.03 and abs(Z.std() - 1.0) < 0.03
+    want, info = eng.sample(Xs, Z, jitter=1e-8)
+    got, info2 = eng.sample_ex(Xs, S, Z=None, seed=1234567891011, jitter=1e-8)
+    assert info == 0 and info2 == 0
+    assert np.max(np.abs(got - want)) <= 1e-9 * np.max(np.abs(want))
+    # flux: weight = flow * dt * 1e-3, groups = "years" of 365 grid points, log-standard target pipeline
+    rng = np.random.default_rng(2)
+    w = np.exp(rng.standard_normal(m)) * 86400.0 * 1e-3
+    gs = np.array([0, 365, 730], dtype=np.int32)
+    y_mean, y_scale = 0.7, 1.3
+    flux, info3 = eng.sample_ex(Xs, S, Z=Z, jitter=1e-8, flux=dict(y_mean=y_mean, y_scale=y_scale, log_transform=1,
+                                                                 weight=w, group_start=gs))
+    conc = np.clip(np.exp(want * y_scale + y_mean), 1e-6, None)
+    ref = np.stack([(conc[:, a:b] * w[a:b]).sum(axis=1) for a, b in zip(gs[:-1], gs[1:])], axis=1)
+    assert info3 == 0 and flux.shape == (S, 2)
+    assert np.max(np.abs(flux - ref) / np.abs(ref)) <= 1e-10
+    aff, _ = eng.sample_ex(Xs, S, Z=Z, jitter=1e-8, flux=dict(y_mean=y_mean, y_scale=y_scale, log_transform=0,
+                                                            weight=w, group_start=gs))
+    ref2 = np.stack([((want[:, a:b] * y_scale + y_mean) * w[a:b]).sum(axis=1) for a, b in zip(gs[:-1], gs[1:])], axis=1)
+    assert np.max(np.abs(aff - ref2)) <= 1e-10 * np.max(np.abs(ref2))
+    with pytest.raises(capi.DgpError):
+        eng.sample_ex(Xs, S, Z=Z, flux=dict(y_mean=0.0, y_scale=1.0, weight=w, group_start=np.array([0, 800], dtype=np.int32)))
+    eng.close()
+
+
 @pytest.mark.parametrize("model", ["loadest", "rating"])
 def test_mean_functional_gradient_vs_autograd(cuda_device, model):
     """dgp_mean_functional_grad: F = c'mu(X*) and dF/dtheta against torch autograd through the solve (oracle)."""
@@ -214,7 +249,7 @@ def test_mean_functional_gradient_vs_autograd(cuda_device, model):
     F = (torch.tensor(c) * mu).sum()
     gs = torch.autograd.grad(F, list(leaves.values()), allow_unused=True)
     want = to_theta({k: (g if g is not None else torch.zeros_like(leaves[k])).numpy() for k, g in zip(leaves, gs)})
-    assert abs(val - float(F)) <= RTOL * abs(float(F))
+    assert abs(val - float(F.detach())) <= RTOL * abs(float(F.detach()))
     _grad_close(grad, want)
     # the same call after dgp_factorize (prediction state) gives the same numbers
     eng.factorize(theta)
@@ -369,6 +404,20 @@ def test_engine_fit_trajectory_matches_reference_loop_loadest(cuda_device):
     assert len(m2.history) == 4
     with pytest.raises(ValueError, match="Unsupported optimizer"):
         models.LoadestGP().fit(cov, conc, iterations=1, optimizer="sgd")
+    # annual flux of joint draws, reduced on the device (src/loadest_gp/utils.py:14-56,89)
+    days = np.arange(0, 800)
+    daily = {"time": np.datetime64("2001-06-01") + days.astype("timedelta64[D]"),
+             "flow": np.exp(1.0 + 0.8 * np.sin(2 * np.pi * days / 365.25))}
+    years, flux = m.sample_annual_flux(daily, n=16, seed=77)
+    assert list(years) == [2001, 2002, 2003] and flux.shape == (16, 3) and np.all(flux > 0)
+    Xd = m.dm.Xnew(daily)
+    Zs = H.philox_normals(77, 16 * 800).reshape(16, 800)
+    draws, info = m._engine.sample(Xd, Zs, jitter=0.0)
+    concd = np.asarray(m.dm.y_t(draws.reshape(-1))).reshape(16, 800)
+    fl = concd * daily["flow"] * 86400.0 * 1e-3
+    yr = daily["time"].astype("datetime64[Y]").astype(int) + 1970
+    ref = np.stack([fl[:, yr == yv].sum(axis=1) for yv in years], axis=1)
+    assert info == 0 and np.max(np.abs(flux - ref) / ref) <= 1e-9
 
 
 def test_engine_fit_trajectory_matches_reference_loop_rating(cuda_device):
