@@ -60,7 +60,8 @@ struct dgp_handle_s {
   GraphSlot graphs[3];               // per evaluation level (nlml / nlml+grad / factorize)
   bool use_graphs = false;  // opt-in (DGP_GRAPHS=1): replay loses the stream priorities of the look-ahead, measured slower
   int max_n = 0, max_pad = 0, max_m = 0;
-  int n = 0, npad = 0, nb = 0;
+  int n = 0, npad = 0, nb = 0, sms = 148;
+  bool stagger = true;
   bool have_train = false, factorized = false, have_T = false, debug_kinv = false, timing = false;
   dgp_spec spec;
   // device buffers
@@ -162,6 +163,8 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
     g_create_error = "dgp_create: libdgp is built for sm_100a (B200) only";
     delete h; return -2;
   }
+  h->sms = prop.multiProcessorCount;
+  { const char* sg = getenv("DGP_STAGGER"); if (sg) h->stagger = atoi(sg) != 0; }
   h->max_n = max_n;
   h->max_pad = round_up(max_n, 128);
   h->max_m = round_up(max_m > 0 ? max_m : 2048, 128);
@@ -468,8 +471,20 @@ static int run_trtri(dgp_handle h, bool want_T) {
 static int run_lauum_grad(dgp_handle h) {
   GemmArgs g = base_args(h, M_LAUUM, 0);
   g.C = h->bufA; g.ntiles = h->nb * (h->nb + 1);
+  g.aux0 = h->stagger ? 2 * h->sms : 0;  // 2 CTAs per SM in the first wave: stagger them (see decode_job)
   g.Kinv = h->debug_kinv ? h->bufA : nullptr;
-  return launch_gemm<INIT_ZERO, EPI_GRAD>(h, h->tmU, h->tmU, g);
+  // Default: LAUUM stores the lower tiles of Ky^-1 (8 n^2 / 2 B, over T, which is dead by now) and a separate
+  // high-occupancy pass contracts W = alpha alpha' - Ky^-1 with the regenerated dK/dtheta tiles.  DGP_FUSED_GRAD=1
+  // selects the contraction fused into the LAUUM epilogue instead (no Ky^-1 round trip; measured 3-4 ms slower at
+  // n = 16384 because the epilogue's dependent FP64 chains wait behind the co-resident CTA's DMMA issue).
+  static const bool fused = getenv("DGP_FUSED_GRAD") != nullptr && atoi(getenv("DGP_FUSED_GRAD")) != 0;
+  if (fused) return launch_gemm<INIT_ZERO, EPI_GRAD>(h, h->tmU, h->tmU, g);
+  int rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmU, h->tmU, g);
+  if (rc) return rc;
+  k_grad_contract<<<g.ntiles, 128, 0, h->stream>>>(h->spec, h->theta, h->Xw, h->alpha, h->bufA, h->npad, h->n, h->gpart);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  return 0;
 }
 
 static int run_finish(dgp_handle h, int want_grad) {

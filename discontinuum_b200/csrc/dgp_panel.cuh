@@ -565,6 +565,82 @@ k_wgrad(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta,
   }
 }
 
+// ------------------------------------------------------------------ NLML gradient contraction as its own pass
+// part[tile][t] = -1/2 sum_{(i, j) in lower tile} wgt_ij (alpha_i alpha_j - Kinv_ij) dK_ij/dtheta_t  (+ -1/2 tr W on the
+// learned-noise slot), wgt = 2 below the diagonal, 1 on it.  Same tiling as the LAUUM launch that wrote Kinv
+// (128 x 64 lower tiles, tile -> (i, c) triangular), one thread per row, 4 columns side by side.  Unlike the fused
+// epilogue this runs with every warp of the SM on FP64 ALU work, so the pipe is not shared with DMMA issue.
+__global__ void __launch_bounds__(128, 4)
+k_grad_contract(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta, const double* __restrict__ Xw,
+                const double* __restrict__ alpha, const double* __restrict__ Kinv, long long ld, int n,
+                double* __restrict__ part) {
+  __shared__ CovC cc;
+  __shared__ double xaT[DGP_XS * 128];
+  __shared__ double xb[64 * DGP_XS];
+  __shared__ double al[64];
+  __shared__ double red[4 * DGP_MAX_TERMS * NSLOT + 4];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int tile = blockIdx.x;
+  int ib = (int)sqrt((double)(4 * tile + 1));
+  while (ib * ib > 4 * tile + 1) --ib;
+  while ((ib + 1) * (ib + 1) <= 4 * tile + 1) ++ib;
+  ib = (ib - 1) >> 1;
+  const int cb = tile - ib * (ib + 1);
+  const size_t r0 = (size_t)ib * 128, c0b = (size_t)cb * 64;
+  cov_compile(&cc, spec, theta, 0.0, t, 128);
+  for (int e = t; e < 128 * DGP_XS; e += 128) xaT[(e % DGP_XS) * 128 + e / DGP_XS] = Xw[r0 * DGP_XS + e];
+  for (int e = t; e < 64 * DGP_XS; e += 128) xb[e] = Xw[c0b * DGP_XS + e];
+  if (t < 64) al[t] = alpha[c0b + t];
+  __syncthreads();
+  const int grow = (int)r0 + t;
+  const double ai = alpha[grow];
+  const double* krow = Kinv + (size_t)grow * ld + c0b;
+  double trw = 0.0;
+  for (int term = 0; term < cc.nterms; term++) {
+    double sl[NSLOT];
+#pragma unroll
+    for (int k = 0; k < NSLOT; k++) sl[k] = 0.0;
+    const TermC& tc = cc.t[term];
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 4) {
+      if (grow >= n || (int)c0b + c0 > grow) continue;  // padding rows / strictly above the diagonal
+      const double2 k01 = *reinterpret_cast<const double2*>(krow + c0);
+      const double2 k23 = *reinterpret_cast<const double2*>(krow + c0 + 2);
+      const double kv[4] = {k01.x, k01.y, k23.x, k23.y};
+      double w[4];
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        const int gcol = (int)c0b + c0 + v;
+        const double wgt = (gcol < grow) ? 2.0 : (gcol == grow ? 1.0 : 0.0);
+        w[v] = wgt * (ai * al[c0 + v] - kv[v]);
+        if (term == 0 && gcol == grow) trw += w[v];
+      }
+      term_grad_accum_v<4>(tc, xaT, 128, t, xb + c0 * DGP_XS, w, sl);
+    }
+#pragma unroll
+    for (int k = 0; k < NSLOT; k++) {
+      double v = sl[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[(warp * DGP_MAX_TERMS + term) * NSLOT + k] = v;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) trw += __shfl_xor_sync(0xffffffffu, trw, o);
+  if (lane == 0) red[4 * DGP_MAX_TERMS * NSLOT + warp] = trw;
+  __syncthreads();
+  if (t < cc.ntheta) {
+    double s = 0.0;
+    for (int term = 0; term < cc.nterms; term++)
+      for (int k = 0; k < NSLOT; k++)
+        if (term_slot_theta(cc.t[term], k) == t)
+          for (int w4 = 0; w4 < 4; w4++) s += red[(w4 * DGP_MAX_TERMS + term) * NSLOT + k];
+    if (t == cc.noise_idx)
+      for (int w4 = 0; w4 < 4; w4++) s += red[4 * DGP_MAX_TERMS * NSLOT + w4];
+    part[(size_t)tile * DGP_MAX_THETA + t] = -0.5 * s;
+  }
+}
+
 // v[j] = sum_p c[p] Kx[p, j]   (p < mpad), grid = npad / 256
 __global__ void __launch_bounds__(256)
 k_colsum_weighted(const double* __restrict__ Kx, long long ld, const double* __restrict__ c, int mpad, double* __restrict__ v) {

@@ -94,11 +94,17 @@ def _finish_step(s: _SiteState):
         s.sched.step(s.history[-1])
 
 
-def _open_site(idx, tup, device, lr, scheduler, patience) -> _SiteState:
+def _open_site(idx, tup, device, lr, scheduler, patience, pool: Optional[List[capi.Engine]] = None) -> _SiteState:
     X, y = np.ascontiguousarray(tup[0], dtype=np.float64), np.ascontiguousarray(tup[1], dtype=np.float64)
     noise = np.ascontiguousarray(tup[2], dtype=np.float64) if len(tup) > 2 else np.full(y.shape[0], LOADEST_FIXED_NOISE)
     module = GPModule(loadest_spec(X.shape[1]))
-    eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device)
+    eng = None
+    if pool:  # reuse the workspace of a finished (larger) site: no cudaMalloc / cudaFree (a device-wide sync) mid-batch
+        k = next((i for i, e in enumerate(pool) if e.max_n >= X.shape[0]), None)
+        if k is not None:
+            eng = pool.pop(k)
+    if eng is None:
+        eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device)
     eng.set_train(module.spec.to_c(), X, y, noise)
     opt = torch.optim.Adam(module.raw_list(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
     sch = None
@@ -114,7 +120,7 @@ def _launch_step(s: _SiteState):
     s.engine.nlml_grad_launch(s.nat.detach().numpy().astype(np.float64))
 
 
-def _close_site(s: _SiteState, predict) -> dict:
+def _close_site(s: _SiteState, predict, pool: Optional[List[capi.Engine]] = None) -> dict:
     with torch.no_grad():
         theta = s.module.natural().numpy().astype(np.float64)
     res = {"theta": theta, "history": s.history, "objective": s.history[-1] if s.history else None, "failed": s.failed,
@@ -126,7 +132,10 @@ def _close_site(s: _SiteState, predict) -> dict:
                 break
         mu, var = s.engine.predict(predict[s.idx])
         res["mu"], res["var"] = mu, np.maximum(var, MIN_VARIANCE)
-    s.engine.close()
+    if pool is not None:
+        pool.append(s.engine)
+    else:
+        s.engine.close()
     return res
 
 
@@ -140,12 +149,13 @@ def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int 
     back the host does its optimiser step and enqueues its next evaluation, while the GPU works on the others; a
     finished site is predicted, closed and replaced by the next largest one (no group barrier)."""
     results: Dict[int, dict] = {}
-    queue = sorted(sites, key=lambda i: -sites[i][0].shape[0])
+    queue = sorted(sites, key=lambda i: -sites[i][0].shape[0])  # largest first: later sites fit the pooled workspaces
     active: List[_SiteState] = []
+    pool: List[capi.Engine] = []
 
     def refill():
         while queue and len(active) < max(1, concurrency):
-            s = _open_site(queue[0], sites[queue.pop(0)], device, lr, scheduler, patience)
+            s = _open_site(queue[0], sites[queue.pop(0)], device, lr, scheduler, patience, pool)
             if iterations > 0:
                 _launch_step(s)
             active.append(s)
@@ -159,8 +169,10 @@ def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int 
                 _launch_step(s)
                 continue
             active.remove(s)
-            results[s.idx] = _close_site(s, predict)
+            results[s.idx] = _close_site(s, predict, pool)
             refill()
+    for e in pool:
+        e.close()
     return results
 
 

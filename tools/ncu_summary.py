@@ -7,7 +7,7 @@ def launches(path):
     for row in csv.DictReader(lines):
         t = float(row["Metric Value"].replace(",", ""))
         t = t / 1e3 if row["Metric Unit"] == "ns" else (t * 1e3 if row["Metric Unit"] == "ms" else t)
-        m = re.search(r"k_gemm<\(int\)(\d), \(int\)(\d)>", row["Kernel Name"])
+        m = re.search(r"k_gemm<(?:\(int\))?(\d), (?:\(int\))?(\d)>", row["Kernel Name"])
         key = f"k_gemm<INIT={m.group(1)},EPI={m.group(2)}>" if m else row["Kernel Name"].split("(")[0]
         a = agg.setdefault(key, [0, 0.0]); a[0] += 1; a[1] += t; tot += t
     out = [f"{'kernel':34s} {'launches':>8s} {'total ms':>10s} {'share':>7s} {'avg us':>10s}"]
@@ -26,6 +26,21 @@ def raw(rep, wanted):
             out.append(f"{h:80s} {v:>22s} {u}")
     return "\n".join(out)
 
+def dram(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rd = wr = 0.0
+    n = 0
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"].lower()
+        v *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1.0)
+        if row["Metric Name"].startswith("dram__bytes_read"):
+            rd += v; n += 1
+        else:
+            wr += v
+    return f"launches {n}\ndram__bytes_read.sum  total {rd/1e9:.3f} GB\ndram__bytes_write.sum total {wr/1e9:.3f} GB\nsum {(rd+wr)/1e9:.3f} GB"
+
+
 WANTED = {"gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
           "sm__ops_path_tensor_src_fp64.sum.per_second", "sm__ops_path_tensor_src_fp64.avg.pct_of_peak_sustained_elapsed",
@@ -39,5 +54,7 @@ WANTED = {"gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.s
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         print(launches(sys.argv[2]))
+    elif sys.argv[1] == "dram":
+        print(dram(sys.argv[2]))
     else:
         print(raw(sys.argv[2], WANTED))
