@@ -67,8 +67,8 @@ def test_golden_vectors_through_cabi(cuda_device, fname):
 
 
 @pytest.mark.parametrize("model,n,kind", [("loadest", 127, 0), ("loadest", 128, 1), ("loadest", 129, 0), ("loadest", 300, 1),
-                                           ("loadest", 1000, 1), ("loadest", 2000, 0), ("rating", 200, 0), ("rating", 1000, 1),
-                                           ("rating", 2000, 1)])
+                                           ("loadest", 600, 0), ("loadest", 1000, 1), ("loadest", 1100, 1), ("loadest", 2000, 0),
+                                           ("rating", 200, 0), ("rating", 1000, 1), ("rating", 2000, 1)])
 def test_nlml_grad_alpha_chol_vs_oracle(cuda_device, model, n, kind):
     if model == "loadest":
         X, y, noise = synthetic.loadest_site(n, 1000 + n)
