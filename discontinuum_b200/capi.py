@@ -66,6 +66,16 @@ _SIGNATURES = [
     ("dgp_mean_functional_grad", C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     ("dgp_sample", C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_double, _P, C.c_int]),
     ("dgp_sample_ex", C.c_int, [_P, _P, C.c_int, _P, C.c_ulonglong, C.c_int, C.c_double, C.POINTER(DgpFluxReduce), _P, C.c_int]),
+    ("dgp_dist_dims", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
+    ("dgp_dist_begin", C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_ulonglong, C.c_double, C.c_int, C.c_int, _P, _P, _P, _P, C.POINTER(_P)]),
+    ("dgp_dist_vt_rows", C.c_int, [_P, C.c_int, C.c_int]),
+    ("dgp_dist_sigma", C.c_int, [_P]),
+    ("dgp_dist_panel_factor", C.c_int, [_P, C.c_int]),
+    ("dgp_dist_panel_unpack", C.c_int, [_P, C.c_int]),
+    ("dgp_dist_trail", C.c_int, [_P, C.c_int]),
+    ("dgp_dist_draws_partial", C.c_int, [_P]),
+    ("dgp_dist_finish", C.c_int, [_P, _P]),
+    ("dgp_dist_end", C.c_int, [_P]),
     ("dgp_get_alpha", C.c_int, [_P, _P, C.c_int]),
     ("dgp_get_chol", C.c_int, [_P, _P, C.c_int]),
     ("dgp_set_debug_kinv", C.c_int, [_P, C.c_int]),
@@ -140,6 +150,7 @@ class Engine:
             self._h = _P()
             raise DgpError(f"dgp_create failed ({rc}): {msg.decode() if msg else ''}")
         self.max_n, self.max_m, self.device = int(max_n), int(max_m), int(device)
+        self.stream = int(stream)  # 0: the handle created its own stream
         self.n = 0
         self.ntheta = 0
         self._keep = None
@@ -279,6 +290,28 @@ class Engine:
         info = self._check(self.lib.dgp_sample_ex(self._h, Xs.ctypes.data, m, zp, int(seed), int(S), float(jitter),
                                                   C.byref(red) if red is not None else None, out.ctypes.data, 0), "dgp_sample_ex")
         return out, info
+
+    # -- distributed sampling primitives (multisite.sample_sharded drives them)
+    def dist_dims(self, m: int, S: int, world: int) -> dict:
+        d = (C.c_longlong * 6)()
+        self._check(self.lib.dgp_dist_dims(self._h, int(m), int(S), int(world), d), "dgp_dist_dims")
+        return dict(mpad=int(d[0]), npad=int(d[1]), Spad=int(d[2]), panel_cols=int(d[3]), npanels=int(d[4]), rows_per_rank=int(d[5]))
+
+    def dist_begin(self, Xs, S: int, Z, seed: int, jitter: float, rank: int, world: int, VT, pack, Od, mu):
+        """VT / pack / Od / mu: CUDA float64 torch tensors owned by the caller (see include/dgp.h).  Returns a token."""
+        Xs = _f64(Xs)
+        zp = None
+        if Z is not None:
+            Z = _f64(Z)
+            zp = Z.ctypes.data
+        tok = _P()
+        self._check(self.lib.dgp_dist_begin(self._h, Xs.ctypes.data, int(Xs.shape[0]), int(S), zp, int(seed), float(jitter),
+                                            int(rank), int(world), VT.data_ptr(), pack.data_ptr(), Od.data_ptr(), mu.data_ptr(),
+                                            C.byref(tok)), "dgp_dist_begin")
+        return tok
+
+    def dist_call(self, name: str, tok, *args) -> int:
+        return self._check(getattr(self.lib, "dgp_dist_" + name)(tok, *args), "dgp_dist_" + name)
 
     # -- parity / debug
     def covmat(self, theta) -> np.ndarray:

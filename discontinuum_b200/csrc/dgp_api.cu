@@ -349,6 +349,58 @@ static int ensure_events(dgp_handle h, size_t count) {
 // Stream T runs the throughput-bound rank-(128 pw) update of everything right of the panel, split in two
 // launches: the next panel's columns first (all panel p+1 reads), then the rest, which overlaps panel p+1 on P.
 // The wide update reads/writes each trailing tile once per panel instead of once per block column.
+// one rank-(128 kb) update launch: block columns [o, o + w) (M_TRAIL_COL) or the lower triangle from block o (M_TRAIL)
+static int launch_trail(dgp_handle h, const CholBufs& b, int mode, int k0, int kb, int o, int w, int ntiles, bool first_touch,
+                        double jitter, cudaStream_t st) {
+  GemmArgs g = base_args(h, mode, k0);
+  g.nb = b.nb; g.ldc = b.ld;
+  g.aux0 = (mode == M_TRAIL_COL) ? (o | (w << 16)) : o;
+  g.aux1 = kb;
+  g.aux2 = first_touch ? 0 : 1;
+  g.C = b.A; g.ntiles = ntiles; g.sign = -1.0; g.jitter = jitter;
+  if (first_touch) return launch_gemm<INIT_COV, EPI_STORE>(h, *b.tL, *b.tL, g, st);
+  return launch_gemm<INIT_LOAD, EPI_STORE>(h, *b.tL, *b.tL, g, st);
+}
+
+// the latency-bound chain of one panel [pb, pe) on stream P:
+//   for s: potf2(s) -> TRSM(s) on every row below [-> forward substitution(s)] -> rank-128 update of columns (s, pe)
+static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool generate, double jitter, bool fwd, cudaStream_t P) {
+  const int nb = b.nb;
+  const long long ld = b.ld;
+  int rc;
+  for (int s = pb; s < pe; s++) {
+    const size_t off = (size_t)s * 128 * ld + (size_t)s * 128;
+    const bool inplace = (b.L == b.A);
+    k_potf2<<<1, PF_THREADS, PF_SMEM, P>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
+                                           b.DI + (size_t)s * 128 * 128, b.scal, s * 128, inplace ? nullptr : b.A + off);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    const int m = nb - s - 1;
+    if (m > 0) {
+      GemmArgs g = base_args(h, M_TRSM, s);
+      g.nb = nb; g.ldc = ld;
+      g.C = b.L; g.ntiles = 2 * m;
+      if (inplace) { g.C = b.P; g.ldc = 128; g.aux0 = 1; }  // both half-tiles read the whole block: stage, then copy
+      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, *b.tA, *b.tDI, g, P))) return rc;
+      if (inplace) {
+        k_copy_panel<<<m, 256, 0, P>>>(b.P, b.A, ld, s);
+        h->launches++;
+        CK(h, cudaGetLastError());
+      }
+    }
+    if (fwd) {
+      k_fwd_step<<<nb - s, 256, 0, P>>>(b.L, ld, b.DI, h->r, h->z, s);
+      h->launches++;
+      CK(h, cudaGetLastError());
+    }
+    if (s + 1 < pe) {  // in-panel rank-128 update: block columns (s, pe), rows >= s + 1
+      const int w = pe - s - 1;
+      if ((rc = launch_trail(h, b, M_TRAIL_COL, s, 1, s + 1, w, m * 2 * w, generate && s == 0, jitter, P))) return rc;
+    }
+  }
+  return 0;
+}
+
 static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jitter, bool fwd) {
   const int nb = b.nb;
   const long long ld = b.ld;
@@ -359,16 +411,6 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
   if ((rc = ensure_events(h, 2 * (size_t)npanels + 2))) return rc;
   auto ev_panel = [&](int p) { return h->evs[2 * p]; };
   auto ev_cols = [&](int p) { return h->evs[2 * p + 1]; };
-  auto trail = [&](int mode, int k0, int kb, int o, int w, int ntiles, bool first_touch, cudaStream_t st) {
-    GemmArgs g = base_args(h, mode, k0);
-    g.nb = nb; g.ldc = ld;
-    g.aux0 = (mode == M_TRAIL_COL) ? (o | (w << 16)) : o;
-    g.aux1 = kb;
-    g.aux2 = first_touch ? 0 : 1;
-    g.C = b.A; g.ntiles = ntiles; g.sign = -1.0; g.jitter = jitter;
-    if (first_touch) return launch_gemm<INIT_COV, EPI_STORE>(h, *b.tL, *b.tL, g, st);
-    return launch_gemm<INIT_LOAD, EPI_STORE>(h, *b.tL, *b.tL, g, st);
-  };
   if (generate) {
     k_cov_rect<<<dim3(nb * 4, 1), 256, 0, T>>>(h->spec, h->theta, h->Xw, h->Xw, h->noise, jitter, b.A, ld, h->n,
                                                h->n, 1, 1, nullptr, nullptr, 0);
@@ -382,46 +424,17 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
   for (int p = 0; p < npanels; p++) {
     const int pb = p * pw, pe = (pb + pw < nb) ? pb + pw : nb;
     if (P != T && p > 0) CK(h, cudaStreamWaitEvent(P, ev_cols(p), 0));
-    for (int s = pb; s < pe; s++) {
-      const size_t off = (size_t)s * 128 * ld + (size_t)s * 128;
-      const bool inplace = (b.L == b.A);
-      k_potf2<<<1, PF_THREADS, PF_SMEM, P>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
-                                             b.DI + (size_t)s * 128 * 128, b.scal, s * 128, inplace ? nullptr : b.A + off);
-      h->launches++;
-      CK(h, cudaGetLastError());
-      const int m = nb - s - 1;
-      if (m > 0) {
-        GemmArgs g = base_args(h, M_TRSM, s);
-        g.nb = nb; g.ldc = ld;
-        g.C = b.L; g.ntiles = 2 * m;
-        if (inplace) { g.C = b.P; g.ldc = 128; g.aux0 = 1; }  // both half-tiles read the whole block: stage, then copy
-        if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, *b.tA, *b.tDI, g, P))) return rc;
-        if (inplace) {
-          k_copy_panel<<<m, 256, 0, P>>>(b.P, b.A, ld, s);
-          h->launches++;
-          CK(h, cudaGetLastError());
-        }
-      }
-      if (fwd) {
-        k_fwd_step<<<nb - s, 256, 0, P>>>(b.L, ld, b.DI, h->r, h->z, s);
-        h->launches++;
-        CK(h, cudaGetLastError());
-      }
-      if (s + 1 < pe) {  // in-panel rank-128 update: block columns (s, pe), rows >= s + 1
-        const int w = pe - s - 1;
-        if ((rc = trail(M_TRAIL_COL, s, 1, s + 1, w, m * 2 * w, generate && s == 0, P))) return rc;
-      }
-    }
+    if ((rc = factor_panel(h, b, pb, pe, generate, jitter, fwd, P))) return rc;
     if (P != T) {
       CK(h, cudaEventRecord(ev_panel(p), P));
       CK(h, cudaStreamWaitEvent(T, ev_panel(p), 0));
     }
     if (pe < nb) {  // rank-(128 (pe - pb)) update right of the panel: next panel's columns, then the rest
       const int ne = (pe + pw < nb) ? pe + pw : nb, w = ne - pe, m = nb - pe;
-      if ((rc = trail(M_TRAIL_COL, pb, pe - pb, pe, w, m * 2 * w, generate && p == 0, T))) return rc;
+      if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, pe, w, m * 2 * w, generate && p == 0, jitter, T))) return rc;
       if (P != T) CK(h, cudaEventRecord(ev_cols(p + 1), T));
       const int m2 = nb - ne;
-      if (m2 > 0 && (rc = trail(M_TRAIL, pb, pe - pb, ne, 0, m2 * (m2 + 1), generate && p == 0, T))) return rc;
+      if (m2 > 0 && (rc = launch_trail(h, b, M_TRAIL, pb, pe - pb, ne, 0, m2 * (m2 + 1), generate && p == 0, jitter, T))) return rc;
     }
   }
   return 0;
@@ -866,6 +879,229 @@ int dgp_sample_ex(dgp_handle h, const double* Xs, int m, const double* Z, unsign
     CK(h, cudaMemcpyAsync(out, gout, (size_t)S * red->ngroups * 8, okind, h->stream));
   }
   CK(h, cudaMemcpyAsync(h->h_scal, scal2, SC_SIZE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return (int)h->h_scal[SC_INFO];
+}
+
+// ------------------------------------------------------------------ distributed joint posterior sampling
+// exact joint draws need the Cholesky factor of the m x m posterior covariance.  Across G ranks the block
+// columns are dealt out panel-cyclically (panel p -> rank p mod G); every rank holds the training factorisation and
+// keeps Sigma* in the same padded m x m layout, but only generates, updates and factors ITS panels' columns:
+//   V'   rows sharded over ranks              -> caller all-gathers V'        (m n^2 / G flop per rank)
+//   Sigma* columns of my panels               (m^2 n / G flop per rank)
+//   for p: owner factors panel p, packs its sub-diagonal rows -> caller broadcasts -> others unpack
+//          every rank applies the rank-(128 pw) update to its own panels right of p        (m^3 / 3G flop per rank)
+//   draws: partial Z[:, my columns] L[:, my columns]' -> caller all-reduces, adds the mean
+// The caller (multisite.sample_sharded: torch.distributed over NCCL) owns the exchanged buffers and the collectives;
+// this side is the per-rank kernels, all on the handle's stream.
+struct dgp_dist_s {
+  dgp_handle h = nullptr;
+  int m = 0, mpad = 0, mb = 0, S = 0, Spad = 0, pw = 0, npanels = 0, rank = 0, world = 1;
+  double jitter = 0.0;
+  double *VT = nullptr, *pack = nullptr, *Od = nullptr, *mu = nullptr;  // caller-owned device buffers
+  double *Xsd = nullptr, *Xws = nullptr, *means = nullptr, *dot = nullptr, *Sig = nullptr, *Pb = nullptr, *DI2 = nullptr;
+  double *Zd = nullptr, *zero = nullptr, *scal2 = nullptr;
+  CUtensorMap tVT, tSig, tDI2, tZ;
+  CholBufs bufs() { return CholBufs{Sig, Sig, nullptr, DI2, scal2, &tSig, &tSig, &tDI2, mb, mpad, Pb}; }
+  bool mine(int p) const { return p % world == rank; }
+};
+
+int dgp_dist_dims(dgp_handle h, int m, int S, int world, long long* dims) {
+  if (!h || !dims || m < 1 || S < 1 || world < 1) return -1;
+  if (!h->have_train) DGP_FAIL(h, -1, "dgp_dist_dims: no training data");
+  const long long mpad = round_up(m, 128), mb = mpad / 128;
+  const long long rows_per_rank = ((mb + world - 1) / world) * 128;
+  dims[0] = mpad; dims[1] = h->npad; dims[2] = round_up(S, 128); dims[3] = (long long)h->panel_blocks * 128;
+  dims[4] = (mb + h->panel_blocks - 1) / h->panel_blocks; dims[5] = rows_per_rank;
+  return 0;
+}
+
+int dgp_dist_begin(dgp_handle h, const double* Xs, int m, int S, const double* Z, unsigned long long seed, double jitter,
+                   int rank, int world, double* VT, double* pack, double* Od, double* mu, dgp_dist* out) {
+  if (!h) return -1;
+  if (!Xs || !VT || !pack || !Od || !mu || !out || m < 1 || S < 1 || world < 1 || rank < 0 || rank >= world)
+    DGP_FAIL(h, -1, "dgp_dist_begin: bad arguments");
+  if (!h->factorized || !h->have_T) DGP_FAIL(h, -1, "dgp_dist_begin: call dgp_factorize first");
+  CK(h, cudaSetDevice(h->device));
+  dgp_dist d = new dgp_dist_s();
+  d->h = h; d->m = m; d->mpad = round_up(m, 128); d->mb = d->mpad / 128; d->S = S; d->Spad = round_up(S, 128);
+  d->pw = h->panel_blocks; d->npanels = (d->mb + d->pw - 1) / d->pw; d->rank = rank; d->world = world; d->jitter = jitter;
+  d->VT = VT; d->pack = pack; d->Od = Od; d->mu = mu;
+  const size_t mpad = d->mpad;
+  cudaError_t r = cudaSuccess;
+  auto A = [&](double** p, size_t count) { if (r == cudaSuccess) r = cudaMalloc((void**)p, count * sizeof(double)); };
+  A(&d->Xsd, mpad * DGP_MAX_COLS); A(&d->Xws, mpad * DGP_XS); A(&d->means, mpad); A(&d->dot, (size_t)h->nb * mpad);
+  A(&d->Sig, mpad * mpad); A(&d->Pb, mpad * 128); A(&d->DI2, mpad * 128); A(&d->Zd, (size_t)d->Spad * mpad);
+  A(&d->zero, mpad); A(&d->scal2, SC_SIZE);
+  if (r != cudaSuccess) {
+    cudaGetLastError();
+    dgp_dist_end(d);
+    DGP_FAIL(h, -2, "dgp_dist_begin: workspace allocation failed for m=%d: %s", m, cudaGetErrorString(r));
+  }
+  cudaStream_t st = h->stream;
+  int rc;
+  CK(h, cudaMemsetAsync(d->zero, 0, mpad * 8, st));
+  CK(h, cudaMemsetAsync(d->scal2, 0, SC_SIZE * 8, st));
+  CK(h, cudaMemsetAsync(d->Zd, 0, (size_t)d->Spad * mpad * 8, st));
+  CK(h, cudaMemsetAsync(d->Od, 0, (size_t)d->Spad * mpad * 8, st));
+  CK(h, cudaMemsetAsync(d->mu, 0, mpad * 8, st));
+  CK(h, cudaMemsetAsync(d->Xsd, 0, mpad * DGP_MAX_COLS * 8, st));
+  CK(h, cudaMemcpyAsync(d->Xsd, Xs, (size_t)m * h->spec.ndim * 8, cudaMemcpyHostToDevice, st));
+  if (Z != nullptr) CK(h, cudaMemcpy2DAsync(d->Zd, mpad * 8, Z, (size_t)m * 8, (size_t)m * 8, S, cudaMemcpyHostToDevice, st));
+  else k_fill_normals<<<dim3((m + 255) / 256, S), 256, 0, st>>>(d->Zd, mpad, m, seed);
+  k_features<<<(d->mpad + 255) / 256, 256, 0, st>>>(h->spec, h->theta, d->Xsd, nullptr, d->Xws, nullptr, d->means, m, d->mpad, nullptr);
+  h->launches += 2;
+  CK(h, cudaGetLastError());
+  long long dims[6];
+  dgp_dist_dims(h, m, S, world, dims);
+  if ((rc = make_map(h, &d->tVT, VT, (int)(dims[5] * world), h->npad, h->npad))) { dgp_dist_end(d); return rc; }
+  if ((rc = make_map(h, &d->tSig, d->Sig, d->mpad, d->mpad, d->mpad))) { dgp_dist_end(d); return rc; }
+  if ((rc = make_map(h, &d->tDI2, d->DI2, d->mpad, 128, 128))) { dgp_dist_end(d); return rc; }
+  if ((rc = make_map(h, &d->tZ, d->Zd, d->Spad, d->mpad, d->mpad))) { dgp_dist_end(d); return rc; }
+  *out = d;
+  return 0;
+}
+
+int dgp_dist_end(dgp_dist d) {
+  if (!d) return 0;
+  if (d->h) { cudaSetDevice(d->h->device); cudaStreamSynchronize(d->h->stream); }
+  double* bufs[] = {d->Xsd, d->Xws, d->means, d->dot, d->Sig, d->Pb, d->DI2, d->Zd, d->zero, d->scal2};
+  for (double* p : bufs) if (p) cudaFree(p);
+  delete d;
+  return 0;
+}
+
+// rows [row0, row1) (multiples of 128) of V' = Kx T' and of the posterior mean
+int dgp_dist_vt_rows(dgp_dist d, int row0, int row1) {
+  if (!d) return -1;
+  dgp_handle h = d->h;
+  if (row0 < 0 || row0 % 128 || row1 % 128 || row1 < row0) DGP_FAIL(h, -1, "dgp_dist_vt_rows: bad row range");
+  if (row1 > d->mpad) row1 = d->mpad;
+  CK(h, cudaSetDevice(h->device));
+  int rc;
+  const int npad = h->npad;
+  for (int m0 = row0; m0 < row1; m0 += h->max_m) {
+    const int mc = (row1 - m0 < h->max_m) ? row1 - m0 : h->max_m;
+    const int mv = (d->m - m0 < mc) ? (d->m - m0 > 0 ? d->m - m0 : 0) : mc;
+    k_cov_rect<<<dim3(mc / 32, h->nb), 256, 0, h->stream>>>(h->spec, h->theta, d->Xws + (size_t)m0 * DGP_XS, h->Xw, h->noise,
+                                                           0.0, h->Kx, npad, mv, h->n, 0, 0, h->alpha, d->dot + m0, d->mpad);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    GemmArgs g = base_args(h, M_GENERIC, 0);
+    g.nb = mc / 128; g.n = mv; g.aux0 = 2 * h->nb; g.aux1 = npad / 16; g.aux2 = 1;
+    g.ntiles = (mc / 128) * 2 * h->nb; g.C = d->VT + (size_t)m0 * npad; g.ldc = npad;
+    if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmKx, h->tmA, g))) return rc;
+  }
+  if (row1 > row0) {
+    const int cnt = ((d->m < row1) ? d->m : row1) - row0;
+    if (cnt > 0) {
+      k_pred_finish<<<(cnt + 255) / 256, 256, 0, h->stream>>>(h->spec, h->theta, d->Xws + (size_t)row0 * DGP_XS, d->means + row0,
+                                                             d->dot + row0, h->nb, nullptr, 0, d->mpad, cnt, d->mu + row0, nullptr);
+      h->launches++;
+      CK(h, cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+// Sigma* = K** + jitter I - V'V on the block columns of this rank's panels (needs the complete V')
+int dgp_dist_sigma(dgp_dist d) {
+  if (!d) return -1;
+  dgp_handle h = d->h;
+  CK(h, cudaSetDevice(h->device));
+  int rc;
+  for (int p = d->rank; p < d->npanels; p += d->world) {
+    const int pb = p * d->pw, pe = (pb + d->pw < d->mb) ? pb + d->pw : d->mb, w = pe - pb;
+    GemmArgs g = base_args(h, M_TRAIL_COL, 0);
+    g.nb = d->mb; g.n = d->m; g.ldc = d->mpad;
+    g.aux0 = pb | (w << 16); g.aux1 = h->npad / 128; g.aux2 = 0;
+    g.C = d->Sig; g.ntiles = (d->mb - pb) * 2 * w; g.sign = -1.0;
+    g.Xw = d->Xws; g.noise = d->zero; g.jitter = d->jitter; g.latent = 1;
+    if ((rc = launch_gemm<INIT_COV, EPI_STORE>(h, d->tVT, d->tVT, g))) return rc;
+  }
+  return 0;
+}
+
+// owner of panel p: factor it in place and pack the rows below its diagonal blocks for the broadcast
+int dgp_dist_panel_factor(dgp_dist d, int p) {
+  if (!d) return -1;
+  dgp_handle h = d->h;
+  if (p < 0 || p >= d->npanels || !d->mine(p)) DGP_FAIL(h, -1, "dgp_dist_panel_factor: panel %d is not owned by rank %d", p, d->rank);
+  CK(h, cudaSetDevice(h->device));
+  const int pb = p * d->pw, pe = (pb + d->pw < d->mb) ? pb + d->pw : d->mb;
+  CholBufs b = d->bufs();
+  int rc = factor_panel(h, b, pb, pe, false, 0.0, false, h->stream);
+  if (rc) return rc;
+  const long long rows = (long long)(d->mb - pe) * 128;
+  if (rows > 0) {
+    k_pack_panel<<<(unsigned)(rows / 8), 256, 0, h->stream>>>(d->Sig, d->mpad, (long long)pe * 128, (long long)pb * 128, (pe - pb) * 128,
+                                                              d->pack, 0);
+    h->launches++;
+    CK(h, cudaGetLastError());
+  }
+  return 0;
+}
+
+// other ranks: put the received panel (rows below its diagonal blocks) in place
+int dgp_dist_panel_unpack(dgp_dist d, int p) {
+  if (!d) return -1;
+  dgp_handle h = d->h;
+  if (p < 0 || p >= d->npanels) DGP_FAIL(h, -1, "dgp_dist_panel_unpack: bad panel");
+  CK(h, cudaSetDevice(h->device));
+  const int pb = p * d->pw, pe = (pb + d->pw < d->mb) ? pb + d->pw : d->mb;
+  const long long rows = (long long)(d->mb - pe) * 128;
+  if (rows > 0) {
+    k_pack_panel<<<(unsigned)(rows / 8), 256, 0, h->stream>>>(d->Sig, d->mpad, (long long)pe * 128, (long long)pb * 128, (pe - pb) * 128,
+                                                              d->pack, 1);
+    h->launches++;
+    CK(h, cudaGetLastError());
+  }
+  return 0;
+}
+
+// rank-(128 pw) update of this rank's panels right of panel p
+int dgp_dist_trail(dgp_dist d, int p) {
+  if (!d) return -1;
+  dgp_handle h = d->h;
+  CK(h, cudaSetDevice(h->device));
+  const int pb = p * d->pw, pe = (pb + d->pw < d->mb) ? pb + d->pw : d->mb;
+  CholBufs b = d->bufs();
+  int rc;
+  for (int j = p + 1; j < d->npanels; j++) {
+    if (!d->mine(j)) continue;
+    const int jb = j * d->pw, je = (jb + d->pw < d->mb) ? jb + d->pw : d->mb, w = je - jb;
+    if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, jb, w, (d->mb - jb) * 2 * w, false, 0.0, h->stream))) return rc;
+  }
+  return 0;
+}
+
+// Od += Z[:, my columns] L[:, my columns]'   (partial sums of the draws; the caller all-reduces Od)
+int dgp_dist_draws_partial(dgp_dist d) {
+  if (!d) return -1;
+  dgp_handle h = d->h;
+  CK(h, cudaSetDevice(h->device));
+  int rc;
+  for (int p = d->rank; p < d->npanels; p += d->world) {
+    const int pb = p * d->pw, pe = (pb + d->pw < d->mb) ? pb + d->pw : d->mb;
+    GemmArgs g = base_args(h, M_ZL, pb);
+    g.nb = d->mb; g.n = d->S; g.aux1 = pe - pb;
+    g.ntiles = (d->Spad / 128) * 2 * (d->mb - pb); g.C = d->Od; g.ldc = d->mpad;
+    if ((rc = launch_gemm<INIT_LOAD, EPI_STORE>(h, d->tZ, d->tSig, g))) return rc;
+  }
+  return 0;
+}
+
+// after the all-reduce of Od and of mu: out[S, m] = Od + mu (host); returns the LAPACK-style info of THIS rank's panels
+int dgp_dist_finish(dgp_dist d, double* out) {
+  if (!d) return -1;
+  dgp_handle h = d->h;
+  if (!out) DGP_FAIL(h, -1, "dgp_dist_finish: out is NULL");
+  CK(h, cudaSetDevice(h->device));
+  k_add_rowvec<<<dim3((d->m + 255) / 256, d->S), 256, 0, h->stream>>>(d->Od, d->mpad, d->mu, d->m);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpy2DAsync(out, (size_t)d->m * 8, d->Od, (size_t)d->mpad * 8, (size_t)d->m * 8, d->S, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(h->h_scal, d->scal2, SC_SIZE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   return (int)h->h_scal[SC_INFO];
 }

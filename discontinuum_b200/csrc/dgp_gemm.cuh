@@ -26,7 +26,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_THREADS = 160;      // 4 consumer warps + 1 producer warp
 constexpr int WS = BN + 1;             // padded row stride of the W tile in the grad epilogue
 
-enum { M_TRSM = 0, M_TRAIL = 1, M_TRAIL_COL = 2, M_INV_M = 3, M_LAUUM = 4, M_PREDVAR = 5, M_GENERIC = 6, M_INV_U = 7 };
+enum { M_TRSM = 0, M_TRAIL = 1, M_TRAIL_COL = 2, M_INV_M = 3, M_LAUUM = 4, M_PREDVAR = 5, M_GENERIC = 6, M_INV_U = 7, M_ZL = 8 };
 enum { INIT_ZERO = 0, INIT_LOAD = 1, INIT_COV = 2 };
 enum { EPI_STORE = 0, EPI_GRAD = 1, EPI_SUMSQ = 2 };
 
@@ -143,6 +143,15 @@ __device__ __forceinline__ Job decode_job(const GemmArgs& g, int tile, int init_
       j.rowB = c * 64; j.kB = 0;
       j.nk = (c + 1) * 4;
       j.crow = i * 128; j.ccol = c * 64;
+    } break;
+    case M_ZL: {  // draws[:, c] += Z[:, K] L[c, K]^T for the block columns K = [step, step + aux1) of L (one panel of a
+                  // column-distributed factor), rows c of L from block `step` on; k limited to the row's own 64-block
+      const int ncb = 2 * (g.nb - s);
+      const int sb = tile / ncb, cbi = tile % ncb;
+      j.rowA = sb * 128; j.kA = s * 128;
+      j.rowB = (2 * s + cbi) * 64; j.kB = s * 128;
+      j.nk = min(8 * g.aux1, (cbi + 1) * 4);
+      j.crow = sb * 128; j.ccol = j.rowB;
     } break;
     default: {  // M_GENERIC: C[i, c] (+)= A[i, :] B[c, :]^T, aux0 = col blocks(64), aux1 = k steps,
                 // aux2 = 1: lower-triangular B (k <= row), 2: lower tiles only (SYRK), 0: dense

@@ -449,6 +449,20 @@ k_copy_panel(const double* __restrict__ P, double* __restrict__ A, long long ld,
   }
 }
 
+// Column panel [c0, c0 + w) of the rows >= r0 of A  <->  contiguous buffer P[rows][w]  (dir = 0: pack, 1: unpack).
+// grid = (rows / 8), block = 256; w multiple of 2.
+__global__ void __launch_bounds__(256)
+k_pack_panel(double* __restrict__ A, long long ld, long long r0, long long c0, int w, double* __restrict__ P, int dir) {
+  const int half = w >> 1;
+  for (int e = threadIdx.x; e < 8 * half; e += 256) {
+    const long long r = (long long)blockIdx.x * 8 + e / half;
+    const int c2 = (e % half) * 2;
+    double2* a = reinterpret_cast<double2*>(A + (r0 + r) * ld + c0 + c2);
+    double2* p = reinterpret_cast<double2*>(P + r * w + c2);
+    if (dir == 0) *p = *a; else *a = *p;
+  }
+}
+
 // out[s, i] += mu[i]  (rows s < S, cols i < m), grid = (ceil(m/256), S)
 __global__ void __launch_bounds__(256) k_add_rowvec(double* __restrict__ out, long long ld, const double* __restrict__ mu, int m) {
   const int i = blockIdx.x * 256 + threadIdx.x;

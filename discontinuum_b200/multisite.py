@@ -223,3 +223,78 @@ def predict_sharded(engine, Xs: np.ndarray, dist=None, want_var: bool = True):
     mu_all = np.concatenate([p[0] for p in parts])
     var_all = np.concatenate([p[1] for p in parts]) if want_var else None
     return mu_all, var_all
+
+
+# ---------------------------------------------------------------- joint posterior draws over a sharded grid
+def panel_owner(p: int, world: int) -> int:
+    """Panel-cyclic distribution of the posterior covariance's block columns."""
+    return p % world
+
+
+def sample_sharded(engine, Xs: np.ndarray, S: int, dist=None, seed: int = 0, jitter: float = 0.0, Z: Optional[np.ndarray] = None):
+    """Exact joint posterior draws [S, m] with the m x m posterior-covariance Cholesky distributed over the ranks of
+    `dist` (torch.distributed, NCCL).  Every rank holds the same training factorisation (`engine.factorize` at the same
+    theta) and calls this with the same arguments; every rank returns (draws, info).
+
+    Exchange steps (the only collectives): all_gather of V' (m x n), all_reduce of the mean, one broadcast of the
+    sub-diagonal rows of each factored panel from its owner, all_reduce of the partial draws.  The engine must have been
+    created on torch's current CUDA stream (`capi.Engine(stream=torch.cuda.current_stream().cuda_stream)`) so that kernel
+    and NCCL work are ordered by stream semantics."""
+    Xs = np.ascontiguousarray(Xs, dtype=np.float64)
+    m = Xs.shape[0]
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    dims = engine.dist_dims(m, S, world)
+    dev = torch.device("cuda", engine.device)
+    f64 = dict(dtype=torch.float64, device=dev)
+    rpr = dims["rows_per_rank"]
+    VT = torch.zeros((rpr * world, dims["npad"]), **f64)
+    pack = torch.empty((dims["mpad"], dims["panel_cols"]), **f64)
+    Od = torch.empty((dims["Spad"], dims["mpad"]), **f64)
+    mu = torch.empty((dims["mpad"],), **f64)
+    shared_stream = engine.stream != 0 and engine.stream == torch.cuda.current_stream(dev).cuda_stream
+
+    def fence():  # engine on a private stream: order kernels and collectives through the host instead
+        if world > 1 and not shared_stream:
+            torch.cuda.synchronize(dev)
+
+    tok = engine.dist_begin(Xs, S, Z, seed, jitter, rank, world, VT, pack, Od, mu)
+    try:
+        engine.dist_call("vt_rows", tok, rank * rpr, min((rank + 1) * rpr, dims["mpad"]))
+        if world > 1:
+            fence()
+            dist.all_gather_into_tensor(VT, VT[rank * rpr:(rank + 1) * rpr].clone())
+            dist.all_reduce(mu)
+            fence()
+        engine.dist_call("sigma", tok)
+        pw_blocks = dims["panel_cols"] // 128
+        mb = dims["mpad"] // 128
+        for p in range(dims["npanels"]):
+            owner = panel_owner(p, world)
+            pe = min((p + 1) * pw_blocks, mb)
+            rows = (mb - pe) * 128
+            if owner == rank:
+                engine.dist_call("panel_factor", tok, p)
+            if rows == 0:
+                continue  # last panel: nothing below it, nothing to update
+            if world > 1:
+                fence()
+                dist.broadcast(pack[:rows], src=owner)
+                fence()
+                if owner != rank:
+                    engine.dist_call("panel_unpack", tok, p)
+            engine.dist_call("trail", tok, p)
+        engine.dist_call("draws_partial", tok)
+        if world > 1:
+            fence()
+            dist.all_reduce(Od)
+            fence()
+        out = np.empty((S, m))
+        info = engine.dist_call("finish", tok, out.ctypes.data)
+        if world > 1:
+            t = torch.tensor([info if info > 0 else 2 ** 31 - 1], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)  # first failing pivot over all ranks
+            info = 0 if int(t) == 2 ** 31 - 1 else int(t)
+        return out, info
+    finally:
+        engine.dist_call("end", tok)

@@ -102,3 +102,26 @@ def test_concurrent_sites_match_single_site_fits(cuda_device):
         assert res[i]["failed"] is None
         assert np.max(np.abs(np.array(res[i]["history"]) - np.array(hist)) / np.abs(hist)) <= 1e-6
         assert res[i]["mu"].shape == (200,) and np.all(res[i]["var"] > 0)
+
+
+@pytest.mark.gpu
+def test_sample_sharded_single_rank_matches_engine_sample(cuda_device):
+    """world = 1: the panel-by-panel distributed schedule reproduces dgp_sample (same Philox normals)."""
+    import helpers as H
+    from discontinuum_b200 import capi, models, synthetic
+
+    n, m, S = 400, 1300, 12
+    X, y, noise = synthetic.loadest_site(n, 51)
+    Xs = synthetic.daily_grid(X, m) + np.array([0.0009, 0.0])
+    eng = capi.Engine(max_n=n, max_m=512)
+    eng.set_train(models.loadest_spec(2).to_c(), X, y, noise)
+    eng.factorize(H.loadest_theta1())
+    want, info = eng.sample_ex(Xs, S, Z=None, seed=99, jitter=1e-7)
+    got, info2 = multisite.sample_sharded(eng, Xs, S, dist=None, seed=99, jitter=1e-7)
+    assert info == 0 and info2 == 0
+    assert np.max(np.abs(got - want)) <= 1e-9 * np.max(np.abs(want))
+    eng.close()
+
+
+def test_panel_owner_cyclic():
+    assert [multisite.panel_owner(p, 4) for p in range(6)] == [0, 1, 2, 3, 0, 1]
