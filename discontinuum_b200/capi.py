@@ -67,12 +67,12 @@ _SIGNATURES = [
     ("dgp_sample", C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_double, _P, C.c_int]),
     ("dgp_sample_ex", C.c_int, [_P, _P, C.c_int, _P, C.c_ulonglong, C.c_int, C.c_double, C.POINTER(DgpFluxReduce), _P, C.c_int]),
     ("dgp_dist_dims", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
-    ("dgp_dist_begin", C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_ulonglong, C.c_double, C.c_int, C.c_int, _P, _P, _P, _P, C.POINTER(_P)]),
+    ("dgp_dist_begin", C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_ulonglong, C.c_double, C.c_int, C.c_int, _P, _P, _P, C.POINTER(_P)]),
     ("dgp_dist_vt_rows", C.c_int, [_P, C.c_int, C.c_int]),
     ("dgp_dist_sigma", C.c_int, [_P]),
-    ("dgp_dist_panel_factor", C.c_int, [_P, C.c_int]),
-    ("dgp_dist_panel_unpack", C.c_int, [_P, C.c_int]),
-    ("dgp_dist_trail", C.c_int, [_P, C.c_int]),
+    ("dgp_dist_panel_factor", C.c_int, [_P, C.c_int, _P, _P]),
+    ("dgp_dist_panel_unpack", C.c_int, [_P, C.c_int, _P]),
+    ("dgp_dist_trail", C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     ("dgp_dist_draws_partial", C.c_int, [_P]),
     ("dgp_dist_finish", C.c_int, [_P, _P]),
     ("dgp_dist_end", C.c_int, [_P]),
@@ -297,8 +297,8 @@ class Engine:
         self._check(self.lib.dgp_dist_dims(self._h, int(m), int(S), int(world), d), "dgp_dist_dims")
         return dict(mpad=int(d[0]), npad=int(d[1]), Spad=int(d[2]), panel_cols=int(d[3]), npanels=int(d[4]), rows_per_rank=int(d[5]))
 
-    def dist_begin(self, Xs, S: int, Z, seed: int, jitter: float, rank: int, world: int, VT, pack, Od, mu):
-        """VT / pack / Od / mu: CUDA float64 torch tensors owned by the caller (see include/dgp.h).  Returns a token."""
+    def dist_begin(self, Xs, S: int, Z, seed: int, jitter: float, rank: int, world: int, VT, Od, mu):
+        """VT / Od / mu: CUDA float64 torch tensors owned by the caller (see include/dgp.h).  Returns a token."""
         Xs = _f64(Xs)
         zp = None
         if Z is not None:
@@ -306,7 +306,7 @@ class Engine:
             zp = Z.ctypes.data
         tok = _P()
         self._check(self.lib.dgp_dist_begin(self._h, Xs.ctypes.data, int(Xs.shape[0]), int(S), zp, int(seed), float(jitter),
-                                            int(rank), int(world), VT.data_ptr(), pack.data_ptr(), Od.data_ptr(), mu.data_ptr(),
+                                            int(rank), int(world), VT.data_ptr(), Od.data_ptr(), mu.data_ptr(),
                                             C.byref(tok)), "dgp_dist_begin")
         return tok
 

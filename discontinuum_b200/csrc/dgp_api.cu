@@ -898,7 +898,7 @@ struct dgp_dist_s {
   dgp_handle h = nullptr;
   int m = 0, mpad = 0, mb = 0, S = 0, Spad = 0, pw = 0, npanels = 0, rank = 0, world = 1;
   double jitter = 0.0;
-  double *VT = nullptr, *pack = nullptr, *Od = nullptr, *mu = nullptr;  // caller-owned device buffers
+  double *VT = nullptr, *Od = nullptr, *mu = nullptr;  // caller-owned device buffers
   double *Xsd = nullptr, *Xws = nullptr, *means = nullptr, *dot = nullptr, *Sig = nullptr, *Pb = nullptr, *DI2 = nullptr;
   double *Zd = nullptr, *zero = nullptr, *scal2 = nullptr;
   CUtensorMap tVT, tSig, tDI2, tZ;
@@ -917,16 +917,16 @@ int dgp_dist_dims(dgp_handle h, int m, int S, int world, long long* dims) {
 }
 
 int dgp_dist_begin(dgp_handle h, const double* Xs, int m, int S, const double* Z, unsigned long long seed, double jitter,
-                   int rank, int world, double* VT, double* pack, double* Od, double* mu, dgp_dist* out) {
+                   int rank, int world, double* VT, double* Od, double* mu, dgp_dist* out) {
   if (!h) return -1;
-  if (!Xs || !VT || !pack || !Od || !mu || !out || m < 1 || S < 1 || world < 1 || rank < 0 || rank >= world)
+  if (!Xs || !VT || !Od || !mu || !out || m < 1 || S < 1 || world < 1 || rank < 0 || rank >= world)
     DGP_FAIL(h, -1, "dgp_dist_begin: bad arguments");
   if (!h->factorized || !h->have_T) DGP_FAIL(h, -1, "dgp_dist_begin: call dgp_factorize first");
   CK(h, cudaSetDevice(h->device));
   dgp_dist d = new dgp_dist_s();
   d->h = h; d->m = m; d->mpad = round_up(m, 128); d->mb = d->mpad / 128; d->S = S; d->Spad = round_up(S, 128);
   d->pw = h->panel_blocks; d->npanels = (d->mb + d->pw - 1) / d->pw; d->rank = rank; d->world = world; d->jitter = jitter;
-  d->VT = VT; d->pack = pack; d->Od = Od; d->mu = mu;
+  d->VT = VT; d->Od = Od; d->mu = mu;
   const size_t mpad = d->mpad;
   cudaError_t r = cudaSuccess;
   auto A = [&](double** p, size_t count) { if (r == cudaSuccess) r = cudaMalloc((void**)p, count * sizeof(double)); };
@@ -1022,20 +1022,22 @@ int dgp_dist_sigma(dgp_dist d) {
   return 0;
 }
 
-// owner of panel p: factor it in place and pack the rows below its diagonal blocks for the broadcast
-int dgp_dist_panel_factor(dgp_dist d, int p) {
+// owner of panel p: factor it in place and pack the rows below its diagonal blocks into `pack` for the broadcast.
+// stream: where to run (NULL: the handle's stream) -- a high-priority side stream lets the factorisation of the next
+// panel overlap this rank's trailing updates (look-ahead); the caller orders the streams with events.
+int dgp_dist_panel_factor(dgp_dist d, int p, double* pack, void* stream) {
   if (!d) return -1;
   dgp_handle h = d->h;
-  if (p < 0 || p >= d->npanels || !d->mine(p)) DGP_FAIL(h, -1, "dgp_dist_panel_factor: panel %d is not owned by rank %d", p, d->rank);
+  if (!pack || p < 0 || p >= d->npanels || !d->mine(p)) DGP_FAIL(h, -1, "dgp_dist_panel_factor: panel %d is not owned by rank %d", p, d->rank);
   CK(h, cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   const int pb = p * d->pw, pe = (pb + d->pw < d->mb) ? pb + d->pw : d->mb;
   CholBufs b = d->bufs();
-  int rc = factor_panel(h, b, pb, pe, false, 0.0, false, h->stream);
+  int rc = factor_panel(h, b, pb, pe, false, 0.0, false, st);
   if (rc) return rc;
   const long long rows = (long long)(d->mb - pe) * 128;
   if (rows > 0) {
-    k_pack_panel<<<(unsigned)(rows / 8), 256, 0, h->stream>>>(d->Sig, d->mpad, (long long)pe * 128, (long long)pb * 128, (pe - pb) * 128,
-                                                              d->pack, 0);
+    k_pack_panel<<<(unsigned)(rows / 8), 256, 0, st>>>(d->Sig, d->mpad, (long long)pe * 128, (long long)pb * 128, (pe - pb) * 128, pack, 0);
     h->launches++;
     CK(h, cudaGetLastError());
   }
@@ -1043,31 +1045,33 @@ int dgp_dist_panel_factor(dgp_dist d, int p) {
 }
 
 // other ranks: put the received panel (rows below its diagonal blocks) in place
-int dgp_dist_panel_unpack(dgp_dist d, int p) {
+int dgp_dist_panel_unpack(dgp_dist d, int p, double* pack) {
   if (!d) return -1;
   dgp_handle h = d->h;
-  if (p < 0 || p >= d->npanels) DGP_FAIL(h, -1, "dgp_dist_panel_unpack: bad panel");
+  if (!pack || p < 0 || p >= d->npanels) DGP_FAIL(h, -1, "dgp_dist_panel_unpack: bad panel");
   CK(h, cudaSetDevice(h->device));
   const int pb = p * d->pw, pe = (pb + d->pw < d->mb) ? pb + d->pw : d->mb;
   const long long rows = (long long)(d->mb - pe) * 128;
   if (rows > 0) {
     k_pack_panel<<<(unsigned)(rows / 8), 256, 0, h->stream>>>(d->Sig, d->mpad, (long long)pe * 128, (long long)pb * 128, (pe - pb) * 128,
-                                                              d->pack, 1);
+                                                              pack, 1);
     h->launches++;
     CK(h, cudaGetLastError());
   }
   return 0;
 }
 
-// rank-(128 pw) update of this rank's panels right of panel p
-int dgp_dist_trail(dgp_dist d, int p) {
+// rank-(128 pw) update, with panel p, of this rank's panels j in [j_first, j_last]
+int dgp_dist_trail(dgp_dist d, int p, int j_first, int j_last) {
   if (!d) return -1;
   dgp_handle h = d->h;
   CK(h, cudaSetDevice(h->device));
   const int pb = p * d->pw, pe = (pb + d->pw < d->mb) ? pb + d->pw : d->mb;
   CholBufs b = d->bufs();
   int rc;
-  for (int j = p + 1; j < d->npanels; j++) {
+  if (j_first < p + 1) j_first = p + 1;
+  if (j_last > d->npanels - 1) j_last = d->npanels - 1;
+  for (int j = j_first; j <= j_last; j++) {
     if (!d->mine(j)) continue;
     const int jb = j * d->pw, je = (jb + d->pw < d->mb) ? jb + d->pw : d->mb, w = je - jb;
     if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, jb, w, (d->mb - jb) * 2 * w, false, 0.0, h->stream))) return rc;

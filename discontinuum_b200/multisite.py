@@ -237,9 +237,11 @@ def sample_sharded(engine, Xs: np.ndarray, S: int, dist=None, seed: int = 0, jit
     theta) and calls this with the same arguments; every rank returns (draws, info).
 
     Exchange steps (the only collectives): all_gather of V' (m x n), all_reduce of the mean, one broadcast of the
-    sub-diagonal rows of each factored panel from its owner, all_reduce of the partial draws.  The engine must have been
-    created on torch's current CUDA stream (`capi.Engine(stream=torch.cuda.current_stream().cuda_stream)`) so that kernel
-    and NCCL work are ordered by stream semantics."""
+    sub-diagonal rows of each factored panel from its owner, all_reduce of the partial draws.  Look-ahead: the owner of
+    panel p+1 updates that panel first, factors it on a high-priority side stream and broadcasts it while every rank
+    is still applying panel p to the rest of its columns.  The engine must have been created on torch's current CUDA
+    stream (`capi.Engine(stream=torch.cuda.current_stream().cuda_stream)`); with a private engine stream the kernels and
+    collectives are ordered through host synchronisation instead (correct, no overlap)."""
     Xs = np.ascontiguousarray(Xs, dtype=np.float64)
     m = Xs.shape[0]
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
@@ -249,16 +251,23 @@ def sample_sharded(engine, Xs: np.ndarray, S: int, dist=None, seed: int = 0, jit
     f64 = dict(dtype=torch.float64, device=dev)
     rpr = dims["rows_per_rank"]
     VT = torch.zeros((rpr * world, dims["npad"]), **f64)
-    pack = torch.empty((dims["mpad"], dims["panel_cols"]), **f64)
+    packs = [torch.empty((dims["mpad"], dims["panel_cols"]), **f64) for _ in range(2)]
     Od = torch.empty((dims["Spad"], dims["mpad"]), **f64)
     mu = torch.empty((dims["mpad"],), **f64)
-    shared_stream = engine.stream != 0 and engine.stream == torch.cuda.current_stream(dev).cuda_stream
+    T = torch.cuda.current_stream(dev)
+    shared_stream = engine.stream != 0 and engine.stream == T.cuda_stream
+    side = torch.cuda.Stream(device=dev, priority=-1) if shared_stream else None  # look-ahead stream
 
     def fence():  # engine on a private stream: order kernels and collectives through the host instead
-        if world > 1 and not shared_stream:
+        if not shared_stream:
             torch.cuda.synchronize(dev)
 
-    tok = engine.dist_begin(Xs, S, Z, seed, jitter, rank, world, VT, pack, Od, mu)
+    pw_blocks, mb, npanels = dims["panel_cols"] // 128, dims["mpad"] // 128, dims["npanels"]
+
+    def rows_below(p):
+        return (mb - min((p + 1) * pw_blocks, mb)) * 128
+
+    tok = engine.dist_begin(Xs, S, Z, seed, jitter, rank, world, VT, Od, mu)
     try:
         engine.dist_call("vt_rows", tok, rank * rpr, min((rank + 1) * rpr, dims["mpad"]))
         if world > 1:
@@ -267,23 +276,39 @@ def sample_sharded(engine, Xs: np.ndarray, S: int, dist=None, seed: int = 0, jit
             dist.all_reduce(mu)
             fence()
         engine.dist_call("sigma", tok)
-        pw_blocks = dims["panel_cols"] // 128
-        mb = dims["mpad"] // 128
-        for p in range(dims["npanels"]):
-            owner = panel_owner(p, world)
-            pe = min((p + 1) * pw_blocks, mb)
-            rows = (mb - pe) * 128
+        # p = -1 bootstraps panel 0; iteration p leaves panel p+1 factored and in place on every rank
+        for p in range(-1, npanels - 1):
+            nxt = p + 1
+            owner = panel_owner(nxt, world)
+            buf = packs[nxt % 2]
+            rows = rows_below(nxt)
+            work = None
             if owner == rank:
-                engine.dist_call("panel_factor", tok, p)
-            if rows == 0:
-                continue  # last panel: nothing below it, nothing to update
-            if world > 1:
-                fence()
-                dist.broadcast(pack[:rows], src=owner)
-                fence()
-                if owner != rank:
-                    engine.dist_call("panel_unpack", tok, p)
-            engine.dist_call("trail", tok, p)
+                if p >= 0:
+                    engine.dist_call("trail", tok, p, nxt, nxt)          # panel p -> panel p+1 first
+                if side is not None:
+                    side.wait_event(T.record_event())
+                    engine.dist_call("panel_factor", tok, nxt, buf.data_ptr(), side.cuda_stream)
+                else:
+                    engine.dist_call("panel_factor", tok, nxt, buf.data_ptr(), None)
+            if world > 1 and rows > 0:
+                if side is not None:
+                    if owner != rank:
+                        side.wait_event(T.record_event())              # the receive buffer is free once T got here
+                    with torch.cuda.stream(side):
+                        work = dist.broadcast(buf[:rows], src=owner, async_op=True)
+                else:
+                    fence()
+                    dist.broadcast(buf[:rows], src=owner)
+                    fence()
+            if p >= 0:
+                engine.dist_call("trail", tok, p, nxt + 1, npanels - 1)  # ... then the rest, overlapping the above
+            if work is not None:
+                work.wait()                                                # T waits for the broadcast
+            elif side is not None and owner == rank:
+                T.wait_stream(side)
+            if owner != rank and rows > 0:
+                engine.dist_call("panel_unpack", tok, nxt, buf.data_ptr())
         engine.dist_call("draws_partial", tok)
         if world > 1:
             fence()

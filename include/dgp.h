@@ -169,23 +169,25 @@ int dgp_sample_ex(dgp_handle h, const double* Xs, int m, const double* Z, unsign
  * owns the collectives and the exchanged DEVICE buffers (row-major float64):
  *   VT   [rows_per_rank * world, npad]  V' = Kx T'; every rank fills its row shard, the caller all-gathers
  *   pack [mpad, panel_cols]             rows below a factored panel's diagonal blocks, broadcast from its owner
+ *                                       (passed per call: the caller may double-buffer it)
  *   Od   [Spad, mpad]                   partial draws, all-reduced (sum) by the caller
  *   mu   [mpad]                         posterior mean, each rank fills its rows (zeros elsewhere): all-reduce (sum)
  * dgp_dist_dims -> {mpad, npad, Spad, panel_cols, npanels, rows_per_rank}.  Call order per rank:
  *   begin -> vt_rows(my shard) -> [all_gather VT, all_reduce mu] -> sigma ->
- *   for p: (owner: panel_factor) -> [broadcast pack] -> (others: panel_unpack) -> trail(p)
+ *   for p: (owner: panel_factor) -> [broadcast pack] -> (others: panel_unpack) -> trail(p, p+1, npanels-1)
+ *          (look-ahead: trail(p, p+1, p+1) first, factor panel p+1 on a side stream while trail(p, p+2, ...) runs)
  *   -> draws_partial -> [all_reduce Od] -> finish(out host [S, m]) -> end.
  * Everything is enqueued on the handle's stream (pass the stream the collectives are ordered against to dgp_create).
  * Z: host base normals [S, m] or NULL for the Philox stream `seed` (identical on every rank). */
 typedef struct dgp_dist_s* dgp_dist;
 int dgp_dist_dims(dgp_handle h, int m, int S, int world, long long* dims6);
 int dgp_dist_begin(dgp_handle h, const double* Xs, int m, int S, const double* Z, unsigned long long seed, double jitter,
-                   int rank, int world, double* VT, double* pack, double* Od, double* mu, dgp_dist* out);
+                   int rank, int world, double* VT, double* Od, double* mu, dgp_dist* out);
 int dgp_dist_vt_rows(dgp_dist d, int row0, int row1);
 int dgp_dist_sigma(dgp_dist d);
-int dgp_dist_panel_factor(dgp_dist d, int p);
-int dgp_dist_panel_unpack(dgp_dist d, int p);
-int dgp_dist_trail(dgp_dist d, int p);
+int dgp_dist_panel_factor(dgp_dist d, int p, double* pack, void* stream);
+int dgp_dist_panel_unpack(dgp_dist d, int p, double* pack);
+int dgp_dist_trail(dgp_dist d, int p, int j_first, int j_last);
 int dgp_dist_draws_partial(dgp_dist d);
 int dgp_dist_finish(dgp_dist d, double* out);  /* > 0: first non-positive pivot met on THIS rank's panels */
 int dgp_dist_end(dgp_dist d);
