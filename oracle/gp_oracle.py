@@ -10,7 +10,9 @@ lives in gpytorch / linear_operator (unpinned in /root/reference/pyproject.toml:
 not installed in this image, and the reference's own tests assert no numbers on this path
 (tests/test_loadest_gp.py:77-85, tests/test_rating_gp.py:32-65).  The oracle is therefore pinned
 by (i) 40-digit mpmath known-answer vectors (oracle/make_golden.py -> tests/golden/*.json),
-(ii) analytic n=1 / n=2 closed forms and (iii) autograd-vs-closed-form gradient agreement.
+(ii) analytic n=1 / n=2 closed forms, (iii) autograd-vs-closed-form gradient agreement and (iv) scikit-learn's
+independent exact-GP implementation (covariance formulas, log marginal likelihood, its gradient, predictive mean and
+variance: tests/test_oracle_vs_sklearn.py) -- a third-party implementation of the same mathematics, not the reference.
 
 What each function follows (paths relative to /root/reference/src):
   loadest_cov / loadest_mean      loadest_gp/models/gpytorch.py:61-128 (covar_module :71, mean :70)
