@@ -155,8 +155,11 @@ def main():
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # torchrun exports OMP_NUM_THREADS=1; the per-site host steps (torch CPU ops) were measured faster with a few threads
+    torch.set_num_threads(max(1, min(8, (os.cpu_count() or 8) // max(world, 1))))
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
         import torch.distributed as dist_mod
 
         dist = dist_mod
