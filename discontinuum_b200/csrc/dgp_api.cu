@@ -61,9 +61,9 @@ struct dgp_handle_s {
   bool use_graphs = false;  // opt-in (DGP_GRAPHS=1): replay loses the stream priorities of the look-ahead, measured slower
   int max_n = 0, max_pad = 0, max_m = 0;
   int n = 0, npad = 0, nb = 0, sms = 148;
-  bool stagger = true;
   bool have_train = false, factorized = false, have_T = false, debug_kinv = false, timing = false;
-  dgp_spec spec;
+  dgp_spec spec;       // internal copy: the caller's spec + derived sin/cos feature columns of periodic factors
+  dgp_spec user_spec;  // as passed to dgp_set_train
   // device buffers
   double *bufA = nullptr, *bufL = nullptr, *bufU = nullptr, *DI = nullptr;
   double *X = nullptr, *y = nullptr, *noise = nullptr, *Xw = nullptr, *r = nullptr, *z = nullptr, *alpha = nullptr;
@@ -118,13 +118,14 @@ static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b,
                        cudaStream_t st = nullptr) {
   if (g.ntiles <= 0) return 0;
   if (st == nullptr) st = h->stream;
-  static bool attr_set = false;
+  static bool attr_set[64] = {false};  // per device: function attributes belong to the device's context
   static int smem_bytes = SM_TOTAL;
-  if (!attr_set) {
+  const int dev = (h->device >= 0 && h->device < 64) ? h->device : 0;
+  if (!attr_set[dev]) {
     const char* pad = getenv("DGP_SMEM_PAD");  // experiment knob: extra bytes force 1 CTA / SM
     if (pad) smem_bytes = SM_TOTAL + atoi(pad);
     CK(h, cudaFuncSetAttribute(k_gemm<INIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   k_gemm<INIT, EPI><<<g.ntiles, GEMM_THREADS, smem_bytes, st>>>(a, b, h->spec, g);
   h->launches++;
@@ -164,7 +165,6 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
     delete h; return -2;
   }
   h->sms = prop.multiProcessorCount;
-  { const char* sg = getenv("DGP_STAGGER"); if (sg) h->stagger = atoi(sg) != 0; }
   h->max_n = max_n;
   h->max_pad = round_up(max_n, 128);
   h->max_m = round_up(max_m > 0 ? max_m : 2048, 128);
@@ -264,6 +264,28 @@ static int check_spec(dgp_handle h, const dgp_spec* sp) {
   return 0;
 }
 
+// Append sinpi / cospi feature columns for periodic factors while the feature table has room (see dgp_cov.cuh).
+static void augment_spec(dgp_spec* sp) {
+  static const bool off = getenv("DGP_NO_SINCOS_COLS") != nullptr;
+  for (int t = 0; t < sp->nterms; t++)
+    for (int f = 0; f < sp->term[t].nfactors; f++) {
+      dgp_factor& fa = sp->term[t].factor[f];
+      fa.pad_ = 0;
+      if (off || fa.kind != DGP_PERIODIC) continue;
+      // reuse the pair of an earlier factor on the same column and period
+      for (int c = 0; c + 1 < sp->ncols && fa.pad_ == 0; c++)
+        if (sp->col[c].kind == DGP_COL_SINP && sp->col[c].src == fa.col[0] && sp->col[c].theta == fa.period) fa.pad_ = c + 1;
+      if (fa.pad_ == 0 && sp->ncols + 2 <= DGP_XS) {
+        const int c = sp->ncols;
+        sp->col[c].kind = DGP_COL_SINP; sp->col[c].src = fa.col[0]; sp->col[c].theta = fa.period; sp->col[c].pad_ = 0; sp->col[c].aux = 0.0;
+        sp->col[c + 1] = sp->col[c];
+        sp->col[c + 1].kind = DGP_COL_COSP;
+        sp->ncols += 2;
+        fa.pad_ = c + 1;
+      }
+    }
+}
+
 int dgp_set_train(dgp_handle h, const dgp_spec* spec, const double* X, const double* y, const double* noise, int n,
                   int on_device) {
   if (!h) return -1;
@@ -271,13 +293,15 @@ int dgp_set_train(dgp_handle h, const dgp_spec* spec, const double* X, const dou
   int rc = check_spec(h, spec);
   if (rc) return rc;
   CK(h, cudaSetDevice(h->device));
-  if (!h->have_train || n != h->n || memcmp(&h->spec, spec, sizeof(dgp_spec)) != 0) {
+  if (!h->have_train || n != h->n || memcmp(&h->user_spec, spec, sizeof(dgp_spec)) != 0) {
     for (auto& gs : h->graphs) {  // captured launch sequences bake in n and the spec
       if (gs.exec) cudaGraphExecDestroy(gs.exec);
       gs = dgp_handle_s::GraphSlot();
     }
   }
+  h->user_spec = *spec;
   h->spec = *spec;
+  augment_spec(&h->spec);
   h->n = n;
   h->npad = round_up(n, 128);
   h->nb = h->npad / 128;
@@ -484,7 +508,6 @@ static int run_trtri(dgp_handle h, bool want_T) {
 static int run_lauum_grad(dgp_handle h) {
   GemmArgs g = base_args(h, M_LAUUM, 0);
   g.C = h->bufA; g.ntiles = h->nb * (h->nb + 1);
-  g.aux0 = h->stagger ? 2 * h->sms : 0;  // 2 CTAs per SM in the first wave: stagger them (see decode_job)
   g.Kinv = h->debug_kinv ? h->bufA : nullptr;
   // Default: LAUUM stores the lower tiles of Ky^-1 (8 n^2 / 2 B, over T, which is dead by now) and a separate
   // high-occupancy pass contracts W = alpha alpha' - Ky^-1 with the regenerated dK/dtheta tiles.  DGP_FUSED_GRAD=1

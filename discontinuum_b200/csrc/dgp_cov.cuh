@@ -10,6 +10,11 @@
 #include "../../include/dgp.h"
 
 #define DGP_XS 8  // doubles per feature-table row (64 B)
+// internal feature-table column kinds appended by libdgp (never set by callers): sinpi / cospi of (feature column `src`)
+// / theta[`theta`] for a periodic factor, so that sin(pi (xa - xb) / p) = sa cb - ca sb costs two FMAs per entry
+// instead of a sincospi.  dgp_factor::pad_ of the internal spec copy holds 1 + the sin column (0: none).
+#define DGP_COL_SINP 100
+#define DGP_COL_COSP 101
 
 namespace dgp {
 
@@ -17,7 +22,7 @@ struct FactorC {
   int kind, ndims;
   int col[DGP_MAX_FDIMS];
   int ls_idx[DGP_MAX_FDIMS];
-  int period_idx, pad_;
+  int period_idx, sc_col;  // sc_col: feature column of sinpi(x / p) (cospi in the next one), -1: evaluate directly
   double inv_ls[DGP_MAX_FDIMS];
   double w;        // periodic: pi / period
   double inv_lam;  // periodic: 1 / lengthscale
@@ -69,6 +74,7 @@ __device__ __forceinline__ void cov_compile(CovC* cc, const dgp_spec& sp, const 
         fc.kind = sf.kind;
         fc.ndims = f < st.nfactors ? sf.ndims : 0;
         fc.period_idx = -1;
+        fc.sc_col = -1;
         fc.w = 0.0; fc.inv_lam = 0.0; fc.inv_p = 0.0;
         for (int d = 0; d < DGP_MAX_FDIMS; d++) {
           fc.col[d] = 0; fc.ls_idx[d] = -1; fc.inv_ls[d] = 0.0;
@@ -80,6 +86,7 @@ __device__ __forceinline__ void cov_compile(CovC* cc, const dgp_spec& sp, const 
         }
         if (f < st.nfactors && sf.kind == DGP_PERIODIC) {
           fc.period_idx = sf.period;
+          fc.sc_col = sf.pad_ > 0 ? sf.pad_ - 1 : -1;
           fc.inv_p = 1.0 / theta[sf.period];
           fc.w = 3.14159265358979323846 * fc.inv_p;
           fc.inv_lam = fc.inv_ls[0];
@@ -266,11 +273,20 @@ __device__ __forceinline__ void cov_vals(const CovC* cc, const double* __restric
     for (int f = 0; f < tc.nf; f++) {
       const FactorC& fc = tc.f[f];
       if (fc.kind == DGP_PERIODIC) {
-        const double xa = xaT[fc.col[0] * a_stride + a_idx];
+        if (fc.sc_col >= 0) {  // sin(pi (xa - xb) / p) from the per-point sin / cos columns
+          const double sa = xaT[fc.sc_col * a_stride + a_idx], ca = xaT[(fc.sc_col + 1) * a_stride + a_idx];
 #pragma unroll
-        for (int v = 0; v < V; v++) {
-          const double sn = sinpi((xa - xb[v * DGP_XS + fc.col[0]]) * fc.inv_p);
-          EX[v] = fma(2.0 * fc.inv_lam * sn, sn, EX[v]);
+          for (int v = 0; v < V; v++) {
+            const double sn = fma(sa, xb[v * DGP_XS + fc.sc_col + 1], -ca * xb[v * DGP_XS + fc.sc_col]);
+            EX[v] = fma(2.0 * fc.inv_lam * sn, sn, EX[v]);
+          }
+        } else {
+          const double xa = xaT[fc.col[0] * a_stride + a_idx];
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const double sn = sinpi((xa - xb[v * DGP_XS + fc.col[0]]) * fc.inv_p);
+            EX[v] = fma(2.0 * fc.inv_lam * sn, sn, EX[v]);
+          }
         }
       } else {
         double d2[V];
@@ -338,11 +354,19 @@ __device__ __forceinline__ void term_grad_accum_v(const TermC& tc, const double*
       const FactorC& fc = tc.f[f];
       if (fc.kind == DGP_PERIODIC) {
         const double xa = xaT[fc.col[0] * a_stride + a_idx];
+        double sa = 0.0, ca = 0.0;
+        if (fc.sc_col >= 0) { sa = xaT[fc.sc_col * a_stride + a_idx]; ca = xaT[(fc.sc_col + 1) * a_stride + a_idx]; }
 #pragma unroll
         for (int v = 0; v < V; v++) {
           const double x = (xa - xb[v * DGP_XS + fc.col[0]]) * fc.inv_p;
           double sn, cs;
-          sincospi(x, &sn, &cs);
+          if (fc.sc_col >= 0) {
+            const double sb = xb[v * DGP_XS + fc.sc_col], cb = xb[v * DGP_XS + fc.sc_col + 1];
+            sn = fma(sa, cb, -ca * sb);
+            cs = fma(ca, cb, sa * sb);
+          } else {
+            sincospi(x, &sn, &cs);
+          }
           EX[v] = fma(2.0 * fc.inv_lam * sn, sn, EX[v]);
           aux[f][v] = sn * cs * x;  // u / pi, folded into the period slot below
           poly[f][v] = sn * sn;     // reused for the lam slot (the factor's polynomial part is 1)

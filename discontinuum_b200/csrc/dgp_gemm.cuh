@@ -114,21 +114,6 @@ __device__ __forceinline__ Job decode_job(const GemmArgs& g, int tile, int init_
       j.crow = j.rowA; j.ccol = j.rowB;
     } break;
     case M_LAUUM: {  // Kinv[i, c] = sum_{k >= i} U[i, k] U[c, k]^T  (lower tiles, longest K first)
-      // Stagger: tiles are ordered by decreasing K, so the two CTAs sharing an SM would run equal-length tiles in
-      // lockstep and sit in their (gradient) epilogues at the same time, leaving the tensor pipe idle.  Half of the
-      // first 2 x SMs CTAs therefore take half-length tiles (i = nb / 2): whichever way the first wave is laid
-      // out (one CTA per SM first, or two), every SM gets one short and one long tile and stays half a tile apart.
-      const int W = g.aux0, hw = W >> 1;
-      const int ih = g.nb >> 1, Th = ih * (ih + 1);
-      if (W > 0 && (hw & 1) == 0 && Th >= W && g.ntiles >= Th + hw) {
-        if (tile < W) {
-          const bool first = tile < hw, odd = tile & 1;
-          const int r = (first ? 0 : (hw + 1) >> 1) + ((tile - (first ? 0 : hw)) >> 1);
-          tile = (first != odd) ? Th + r : r;  // short : long   (rank r among its kind)
-        } else if (tile < Th + hw) {
-          tile -= hw;
-        }
-      }
       const int i = (isqrt_floor(4 * tile + 1) - 1) >> 1;
       const int c = tile - i * (i + 1);
       j.rowA = i * 128; j.kA = i * 128;

@@ -30,7 +30,9 @@ __global__ void k_features(const __grid_constant__ dgp_spec spec, const double* 
     const double* x = X + (size_t)i * spec.ndim;
     for (int c = 0; c < spec.ncols; c++) {
       const dgp_col& sc = spec.col[c];
-      const double v = x[sc.src];
+      const double v = (sc.kind >= DGP_COL_SINP) ? 0.0 : x[sc.src];
+      if (sc.kind == DGP_COL_SINP) { row[c] = sinpi(row[sc.src] / theta[sc.theta]); continue; }  // src: feature column
+      if (sc.kind == DGP_COL_COSP) { row[c] = cospi(row[sc.src] / theta[sc.theta]); continue; }
       if (sc.kind == DGP_COL_COPY) row[c] = v;
       else if (sc.kind == DGP_COL_LOG) row[c] = log(v + sc.aux);
       else row[c] = 1.0 / (1.0 + exp(sc.aux * (v - theta[sc.theta])));
