@@ -21,6 +21,7 @@
 #include "dgp_cov.cuh"
 #include "dgp_gemm.cuh"
 #include "dgp_panel.cuh"
+#include "dgp_potf2.cuh"
 
 using namespace dgp;
 
@@ -56,6 +57,7 @@ struct dgp_handle_s {
   std::vector<cudaEvent_t> evs;      // look-ahead dependencies (no timing)
   bool lookahead = true;
   int panel_blocks = 4;              // block columns per panel of the two-level Cholesky
+  bool chain_half = true;            // 64-row half tiles for the panel chain's small launches (DGP_CHAIN_HALF=0: off)
   struct GraphSlot { cudaGraphExec_t exec = nullptr; double jitter = 0.0; bool seen = false; long long launches = 0; };
   GraphSlot graphs[3];               // per evaluation level (nlml / nlml+grad / factorize)
   bool use_graphs = false;  // opt-in (DGP_GRAPHS=1): replay loses the stream priorities of the look-ahead, measured slower
@@ -83,6 +85,10 @@ struct dgp_handle_s {
   bool pending = false;
   int pending_grad = 0;
   long long launches = 0;
+  // DGP_TRACE=<file>: one timing event before/after every launch of the factorisation, dumped per evaluation
+  struct TraceMark { cudaEvent_t ev; const char* tag; int lane; int arg; };
+  std::vector<TraceMark> trace;
+  const char* trace_path = nullptr;
   std::string err;
 };
 
@@ -100,6 +106,30 @@ struct dgp_handle_s {
     if (e_ != cudaSuccess) DGP_FAIL(h, -2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+static inline void trace_mark(dgp_handle h, cudaStream_t st, const char* tag, int arg) {
+  if (!h->trace_path) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  h->trace.push_back({e, tag, st == h->stream ? 0 : 1, arg});
+}
+
+static void trace_dump(dgp_handle h) {
+  if (!h->trace_path || h->trace.empty()) return;
+  FILE* f = fopen(h->trace_path, "a");
+  if (f) {
+    fprintf(f, "# evaluation n=%d\n", h->n);
+    for (auto& m : h->trace) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->trace[0].ev, m.ev);
+      fprintf(f, "%d,%s,%d,%.3f\n", m.lane, m.tag, m.arg, ms * 1e3);
+    }
+    fclose(f);
+  }
+  for (auto& m : h->trace) cudaEventDestroy(m.ev);
+  h->trace.clear();
+}
+
 static int make_map(dgp_handle h, CUtensorMap* m, double* base, int rows, int cols, long long ld) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) DGP_FAIL(h, -3, "cuTensorMapEncodeTiled entry point not available");
@@ -113,7 +143,7 @@ static int make_map(dgp_handle h, CUtensorMap* m, double* base, int rows, int co
   return 0;
 }
 
-template <int INIT, int EPI>
+template <int INIT, int EPI, int MT = 8>
 static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g,
                        cudaStream_t st = nullptr) {
   if (g.ntiles <= 0) return 0;
@@ -124,10 +154,10 @@ static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b,
   if (!attr_set[dev]) {
     const char* pad = getenv("DGP_SMEM_PAD");  // experiment knob: extra bytes force 1 CTA / SM
     if (pad) smem_bytes = SM_TOTAL + atoi(pad);
-    CK(h, cudaFuncSetAttribute(k_gemm<INIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CK(h, cudaFuncSetAttribute(k_gemm<INIT, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set[dev] = true;
   }
-  k_gemm<INIT, EPI><<<g.ntiles, GEMM_THREADS, smem_bytes, st>>>(a, b, h->spec, g);
+  k_gemm<INIT, EPI, MT><<<g.ntiles * (MT == 8 ? 1 : 2), GEMM_THREADS, smem_bytes, st>>>(a, b, h->spec, g);
   h->launches++;
   CK(h, cudaGetLastError());
   return 0;
@@ -178,6 +208,9 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
     if (la) h->lookahead = atoi(la) != 0;
     const char* ug = getenv("DGP_GRAPHS");
     if (ug) h->use_graphs = atoi(ug) != 0;
+    h->trace_path = getenv("DGP_TRACE");
+    const char* ch = getenv("DGP_CHAIN_HALF");
+    if (ch) h->chain_half = atoi(ch) != 0;
     const char* pb = getenv("DGP_PANEL_BLOCKS");
     if (pb && atoi(pb) >= 1 && atoi(pb) <= 64) h->panel_blocks = atoi(pb);
   }
@@ -203,6 +236,7 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
     return -2;
   }
   cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM);
+  cudaFuncSetAttribute(k_potf2_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM);
   *out = h;
   return 0;
 }
@@ -375,7 +409,7 @@ static int ensure_events(dgp_handle h, size_t count) {
 // The wide update reads/writes each trailing tile once per panel instead of once per block column.
 // one rank-(128 kb) update launch: block columns [o, o + w) (M_TRAIL_COL) or the lower triangle from block o (M_TRAIL)
 static int launch_trail(dgp_handle h, const CholBufs& b, int mode, int k0, int kb, int o, int w, int ntiles, bool first_touch,
-                        double jitter, cudaStream_t st) {
+                        double jitter, cudaStream_t st, bool half_tiles = false) {
   GemmArgs g = base_args(h, mode, k0);
   g.nb = b.nb; g.ldc = b.ld;
   g.aux0 = (mode == M_TRAIL_COL) ? (o | (w << 16)) : o;
@@ -383,6 +417,7 @@ static int launch_trail(dgp_handle h, const CholBufs& b, int mode, int k0, int k
   g.aux2 = first_touch ? 0 : 1;
   g.C = b.A; g.ntiles = ntiles; g.sign = -1.0; g.jitter = jitter;
   if (first_touch) return launch_gemm<INIT_COV, EPI_STORE>(h, *b.tL, *b.tL, g, st);
+  if (half_tiles) return launch_gemm<INIT_LOAD, EPI_STORE, 4>(h, *b.tL, *b.tL, g, st);
   return launch_gemm<INIT_LOAD, EPI_STORE>(h, *b.tL, *b.tL, g, st);
 }
 
@@ -395,22 +430,32 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
   for (int s = pb; s < pe; s++) {
     const size_t off = (size_t)s * 128 * ld + (size_t)s * 128;
     const bool inplace = (b.L == b.A);
-    k_potf2<<<1, PF_THREADS, PF_SMEM, P>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
-                                           b.DI + (size_t)s * 128 * 128, b.scal, s * 128, inplace ? nullptr : b.A + off);
+    trace_mark(h, P, "potf2<", s);
+    static const bool potf2_v1 = getenv("DGP_POTF2_V1") != nullptr && atoi(getenv("DGP_POTF2_V1")) != 0;
+    if (potf2_v1)
+      k_potf2<<<1, PF_THREADS, PF_SMEM, P>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
+                                             b.DI + (size_t)s * 128 * 128, b.scal, s * 128, inplace ? nullptr : b.A + off);
+    else
+      k_potf2_v2<<<1, P2_THREADS, P2_SMEM, P>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
+                                                b.DI + (size_t)s * 128 * 128, b.scal, s * 128, inplace ? nullptr : b.A + off);
     h->launches++;
     CK(h, cudaGetLastError());
+    trace_mark(h, P, "potf2>", s);
     const int m = nb - s - 1;
     if (m > 0) {
       GemmArgs g = base_args(h, M_TRSM, s);
       g.nb = nb; g.ldc = ld;
       g.C = b.L; g.ntiles = 2 * m;
       if (inplace) { g.C = b.P; g.ldc = 128; g.aux0 = 1; }  // both half-tiles read the whole block: stage, then copy
-      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, *b.tA, *b.tDI, g, P))) return rc;
+      // half tiles while the launch is smaller than the GPU (chain_half: 2 m 64x64-row CTAs fit the 2 x SMs slots)
+      if (h->chain_half && 4 * m <= 2 * h->sms) { if ((rc = launch_gemm<INIT_ZERO, EPI_STORE, 4>(h, *b.tA, *b.tDI, g, P))) return rc; }
+      else if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, *b.tA, *b.tDI, g, P))) return rc;
       if (inplace) {
         k_copy_panel<<<m, 256, 0, P>>>(b.P, b.A, ld, s);
         h->launches++;
         CK(h, cudaGetLastError());
       }
+      trace_mark(h, P, "trsm>", s);
     }
     if (fwd) {
       k_fwd_step<<<nb - s, 256, 0, P>>>(b.L, ld, b.DI, h->r, h->z, s);
@@ -419,7 +464,9 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
     }
     if (s + 1 < pe) {  // in-panel rank-128 update: block columns (s, pe), rows >= s + 1
       const int w = pe - s - 1;
-      if ((rc = launch_trail(h, b, M_TRAIL_COL, s, 1, s + 1, w, m * 2 * w, generate && s == 0, jitter, P))) return rc;
+      if ((rc = launch_trail(h, b, M_TRAIL_COL, s, 1, s + 1, w, m * 2 * w, generate && s == 0, jitter, P,
+                             h->chain_half && 4 * m * w <= 2 * h->sms))) return rc;
+      trace_mark(h, P, "inpanel>", s);
     }
   }
   return 0;
@@ -455,10 +502,13 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
     }
     if (pe < nb) {  // rank-(128 (pe - pb)) update right of the panel: next panel's columns, then the rest
       const int ne = (pe + pw < nb) ? pe + pw : nb, w = ne - pe, m = nb - pe;
+      trace_mark(h, T, "cols<", p);
       if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, pe, w, m * 2 * w, generate && p == 0, jitter, T))) return rc;
+      trace_mark(h, T, "cols>", p);
       if (P != T) CK(h, cudaEventRecord(ev_cols(p + 1), T));
       const int m2 = nb - ne;
       if (m2 > 0 && (rc = launch_trail(h, b, M_TRAIL, pb, pe - pb, ne, 0, m2 * (m2 + 1), generate && p == 0, jitter, T))) return rc;
+      trace_mark(h, T, "rest>", p);
     }
   }
   return 0;
@@ -599,6 +649,7 @@ static int evaluate_wait(dgp_handle h, double* nlml_out, double* grad_out) {
   CK(h, cudaSetDevice(h->device));
   CK(h, cudaStreamSynchronize(h->stream));
   h->pending = false;
+  trace_dump(h);
   const int level = h->pending_grad;
   if (h->timing) {
     float ms;

@@ -203,10 +203,13 @@ constexpr int SMG_PART = SMG_AL + (BM + BN) * 8;            // [4 warps][8 terms
 constexpr int SMG_END = SMG_PART + (4 * DGP_MAX_TERMS * NSLOT + 4) * 8;
 static_assert(SMG_END <= STAGES * STAGE_BYTES, "grad epilogue does not fit the stage ring");
 
-template <int INIT, int EPI>
+// MT = 8-row fragments per consumer warp along M: 8 -> the 128x64 tile; 4 -> 64x64 half tiles (blockIdx = 2 tile + half)
+// for the short launches of the panel chain, whose few tiles leave most SMs idle: twice the CTAs, half the DMMA time.
+template <int INIT, int EPI, int MT = 8>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
        const __grid_constant__ dgp_spec spec, const GemmArgs g) {
+  static_assert(MT == 8 || (MT == 4 && INIT != INIT_COV && EPI == EPI_STORE), "half tiles: plain load/store tiles only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + SM_BAR);
@@ -214,8 +217,9 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   CovC* cc = (CovC*)(smem + SM_COVC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const Job job = decode_job(g, blockIdx.x, INIT);
+  Job job = decode_job(g, MT == 8 ? blockIdx.x : (blockIdx.x >> 1), INIT);
   if (!job.valid) return;
+  if (MT == 4) { job.rowA += 64 * (blockIdx.x & 1); job.crow += 64 * (blockIdx.x & 1); }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
@@ -232,9 +236,9 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
         const int s = it % STAGES;
         if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
         uint8_t* st = smem + SM_STAGES + s * STAGE_BYTES;
-        mbar_expect_tx(&full[s], STAGE_BYTES);
+        mbar_expect_tx(&full[s], MT == 8 ? STAGE_BYTES : STAGE_BYTES - 64 * BK * 8);
         tma_load_2d(st, &tmA, &full[s], job.kA + it * BK, job.rowA);
-        tma_load_2d(st + 64 * BK * 8, &tmA, &full[s], job.kA + it * BK, job.rowA + 64);
+        if (MT == 8) tma_load_2d(st + 64 * BK * 8, &tmA, &full[s], job.kA + it * BK, job.rowA + 64);
         tma_load_2d(st + A_BYTES, &tmB, &full[s], job.kB + it * BK, job.rowB);
       }
     }
@@ -244,10 +248,13 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   // -------------------------------------------------------------- DMMA consumers
   const int g8 = lane >> 2, q = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;
-  double acc[8][4][2];
+  double acc[MT][4][2];
+  constexpr int WROWS = 8 * MT;  // rows per consumer warp
 
   // ---- accumulator initialisation
-  if (INIT == INIT_COV && job.init == INIT_COV) {
+  bool acc_ready = false;
+  if constexpr (INIT == INIT_COV) if (job.init == INIT_COV) {
+    acc_ready = true;
     // Thread t generates row t of the tile, 8 columns at a time (cov_vals<8>), into a padded tile in the ring;
     // the fragments are then read back in the DMMA accumulator layout.
     double* xaT = (double*)(smem + SM_XS);          // [DGP_XS][128] row-point features, column-major
@@ -285,10 +292,12 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
         acc[mi][ni][1] = wp[1];
       }
     asm volatile("bar.sync 2, 160;" ::: "memory");  // release the ring to the producer
+  }
+  if (acc_ready) {
   } else if ((INIT == INIT_LOAD || INIT == INIT_COV) && job.init == INIT_LOAD) {
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++) {
-      const double* crow = g.C + (size_t)(job.crow + 64 * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
+    for (int mi = 0; mi < MT; mi++) {
+      const double* crow = g.C + (size_t)(job.crow + WROWS * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
 #pragma unroll
       for (int ni = 0; ni < 4; ni++) {
         const double2 v = *reinterpret_cast<const double2*>(crow + 8 * ni);
@@ -298,7 +307,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
     }
   } else {
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++)
+    for (int mi = 0; mi < MT; mi++)
 #pragma unroll
       for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
   }
@@ -307,7 +316,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   // ch of that row is stored at chunk (ch ^ (r & 7)) (TMA 128B swizzle).  Lane (g8, q) takes, for the
   // s-th k4 step of a stage, k = (q>>1)*8 + 2s + (q&1), i.e. chunk (q>>1)*4 + s, word q&1: the 16
   // lanes of each half warp then hit 16 distinct 8-byte bank pairs.
-  const uint32_t a_off = (uint32_t)((64 * wm + g8) * 128 + (q & 1) * 8);
+  const uint32_t a_off = (uint32_t)((WROWS * wm + g8) * 128 + (q & 1) * 8);
   const uint32_t b_off = (uint32_t)(A_BYTES + (32 * wn + g8) * 128 + (q & 1) * 8);
   const uint32_t chq = (uint32_t)((q >> 1) * 4);
   const uint32_t sbase = smem_u32(smem + SM_STAGES);
@@ -326,25 +335,25 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
       const uint32_t sw = ((chq + ks) ^ (uint32_t)g8) << 4;
-      double a[8], b[4];
+      double a[MT], b[4];
 #pragma unroll
-      for (int mi = 0; mi < 8; mi++)
+      for (int mi = 0; mi < MT; mi++)
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[mi]) : "r"(st + a_off + mi * 1024 + sw));
 #pragma unroll
       for (int ni = 0; ni < 4; ni++)
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[ni]) : "r"(st + b_off + ni * 1024 + sw));
 #pragma unroll
-      for (int mi = 0; mi < 8; mi++)
+      for (int mi = 0; mi < MT; mi++)
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni], a[mi], b[ni]);
     }
   }
 
   // ---- epilogue
-  if (EPI == EPI_STORE) {
+  if constexpr (EPI == EPI_STORE) {
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++) {
-      double* crow = g.C + (size_t)(job.crow + 64 * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
+    for (int mi = 0; mi < MT; mi++) {
+      double* crow = g.C + (size_t)(job.crow + WROWS * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
 #pragma unroll
       for (int ni = 0; ni < 4; ni++) {
         double2 v;
@@ -353,7 +362,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
         *reinterpret_cast<double2*>(crow + 8 * ni) = v;
       }
     }
-  } else if (EPI == EPI_SUMSQ) {
+  } else if constexpr (EPI == EPI_SUMSQ) {
     // row sums of squares of the tile -> part[cblock][row]
     const int cb = job.ccol / 64;
     double rs[8];

@@ -1,0 +1,377 @@
+// Diagonal block of the blocked Cholesky, second generation: L_ss, T_ss = L_ss^-1 and U_ss = L_ss^-T of one 128x128
+// block in one CTA that is small enough (95 KB of shared memory, <= 144 registers) to share an SM with one CTA of the
+// DMMA tile engine.  Written around one measured fact: a dependent FP64 operation costs ~40 cycles on B200 (DMMA ~64),
+// so the kernel is a latency chain, not a throughput problem, and everything that can leave the chain does.
+//
+// The block is held as the 10 lower 32x32 sub-blocks B[i][j] (i >= j), row stride 36 doubles: with that stride the
+// A (row g8, k = q), B^T (row g8, k = q), B (k = q, column g8) and C fragments of DMMA.8x8x4 are all conflict free.
+// The factorisation runs in L D L^T form (unit-lower Lu, pivots d, w = 1/d): no square root, no logarithm and no
+// division is on the chain; L = Lu sqrt(D), T = D^-1/2 Lu^-1 are scaled on the way out.  Step k = 0..3:
+//   A  warp 0 factors the diagonal sub-block, lane = row, rows in registers.  Every lane evaluates the next pivot
+//      redundantly from the two exchanged columns, d' = a' - l^2 w, so that the recurrence is one FMA plus a reciprocal
+//      (MUFU.RCP64H and two Newton steps arranged as three dependent operations); the shared-memory exchange of the
+//      column and the updates of the row run beside it.  Warps 1-7 meanwhile finish row k-1 of the inverse,
+//      Tu[k-1][j] = -Tu_kk sum_l Lu[k-1][l] Tu[l][j] (in place over the dead row of L), and stream finished rows out.
+//   B  unit-lower forward substitution by columns, one row per lane: warp 0 on the identity (-> Tu_kk), warps 1.. on
+//      the rows below (-> u[i][k] = Lu[i][k] D_k); warp 7 takes 1/sqrt(d), log d and writes L_kk.
+//   C  results back into shared memory (Tu_kk over Lu_kk).
+//   D  B[i][j] -= (u[i][k] W_k) u[j][k]^T by DMMA in 16x32 jobs (8 independent accumulator chains per warp).
+#pragma once
+#include <cuda_runtime.h>
+#include "dgp_gemm.cuh"
+
+namespace dgp {
+
+constexpr int P2_THREADS = 256;
+constexpr int P2_LD = 36;
+constexpr int P2_BLK = 32 * P2_LD;
+constexpr int P2_OFF_EX = 10 * P2_BLK;          // [2][2][32] exchange buffers of the diagonal factorisation
+constexpr int P2_OFF_W = P2_OFF_EX + 128;       // [128] w = 1 / d
+constexpr int P2_OFF_D = P2_OFF_W + 128;        // [128] pivots d
+constexpr int P2_OFF_RS = P2_OFF_D + 128;       // [128] 1 / sqrt(d) = 1 / L_ii
+constexpr int P2_OFF_SQ = P2_OFF_RS + 128;      // [128] sqrt(d)
+constexpr int P2_SMEM = (P2_OFF_SQ + 128) * 8;  // 97 280 B
+
+#ifdef P2_TIMING
+__device__ long long p2_ts[64];
+#define P2_STAMP(i) do { if (threadIdx.x == 0) p2_ts[i] = clock64(); } while (0)
+#else
+#define P2_STAMP(i) do { } while (0)
+#endif
+
+// 1 / d: MUFU.RCP64H seed (20 bits) and two Newton steps, the second one on e^2 so that only three operations depend
+// on each other (e ; x1 and e^2 ; x2).  d > 0 normal; the result is within an ulp or two of 1 / d.
+__device__ __forceinline__ double rcp_newton(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  const double e = fma(-d, x, 1.0);
+  const double x1 = fma(x, e, x);
+  const double e2 = e * e;
+  return fma(x1, e2, x1);
+}
+
+__device__ __forceinline__ double* p2_blk(double* sm, int i, int j) { return sm + ((i * (i + 1)) / 2 + j) * P2_BLK; }
+
+// acc (16 x 32: rows g8 and 8 + g8, columns 8 ni + 2q, +1) += sum over nks k4-steps of A[row][4 ks + q] * Bop
+//   NN = false: Bop = Bm[8 ni + g8][4 ks + q]   (A Bm^T);   NN = true: Bop = Bm[4 ks + q][8 ni + g8]   (A Bm)
+//   SCALE: A[row][k] is multiplied by wk[k] on the way in;  NEG: the product is subtracted
+template <bool NN, bool NEG, bool SCALE, int NKS>
+__device__ __forceinline__ void p2_strip2(double (&acc)[2][4][2], const double* A, const double* Bm,
+                                          const double* wk, int g8, int q) {
+  const double* ap = A + g8 * P2_LD + q;
+  const double* bp = NN ? Bm + q * P2_LD + g8 : Bm + g8 * P2_LD + q;
+#pragma unroll
+  for (int ks = 0; ks < NKS; ks++) {
+    double a0 = ap[4 * ks], a1 = ap[8 * P2_LD + 4 * ks];
+    if (SCALE) { const double w = wk[4 * ks + q]; a0 *= w; a1 *= w; }
+    if (NEG) { a0 = -a0; a1 = -a1; }
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+      const double b = NN ? bp[4 * ks * P2_LD + 8 * ni] : bp[8 * ni * P2_LD + 4 * ks];
+      dmma(acc[0][ni], a0, b);
+      dmma(acc[1][ni], a1, b);
+    }
+  }
+}
+
+__device__ __forceinline__ void p2_zero(double (&acc)[2][4][2]) {
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) { acc[h][ni][0] = 0.0; acc[h][ni][1] = 0.0; }
+}
+
+__device__ __forceinline__ void p2_store2(double* C, const double (&acc)[2][4][2], int g8, int q) {
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+      double2 v; v.x = acc[h][ni][0]; v.y = acc[h][ni][1];
+      *reinterpret_cast<double2*>(C + (8 * h + g8) * P2_LD + 8 * ni + 2 * q) = v;
+    }
+}
+
+// Row R (>= 1) of the unit inverse, jobs (j, half) = 16 x 32 halves of block (R, j), one per warp (2 R <= nw):
+//   p2_inv_m: M[R][j] = sum_{l = j}^{R-1} Lu[R][l] Tu[l][j], Lu[R][l] = u[R][l] W_l   (accumulators only)
+//   p2_inv_t: Tu[R][j] = -Tu_RR M[R][j]   (Tu_RR unit lower triangular: k <= row)
+__device__ __forceinline__ void p2_inv_m(double (&acc)[2][4][2], double* sm, int R, int job, int g8, int q) {
+  p2_zero(acc);
+  if (job < 2 * R) {
+    const int j = job >> 1, mh = job & 1;
+    for (int l = j; l < R; l++)
+      p2_strip2<true, false, true, 8>(acc, p2_blk(sm, R, l) + 16 * mh * P2_LD, p2_blk(sm, l, j), sm + P2_OFF_W + 32 * l, g8, q);
+  }
+}
+__device__ __forceinline__ void p2_inv_t(double (&acc)[2][4][2], double* sm, int R, int job, int g8, int q) {
+  p2_zero(acc);
+  if (job < 2 * R) {
+    const int j = job >> 1, mh = job & 1;
+    if (mh == 0) p2_strip2<true, true, false, 4>(acc, p2_blk(sm, R, R), p2_blk(sm, R, j), nullptr, g8, q);
+    else p2_strip2<true, true, false, 8>(acc, p2_blk(sm, R, R) + 16 * P2_LD, p2_blk(sm, R, j), nullptr, g8, q);
+  }
+}
+__device__ __forceinline__ void p2_inv_store(const double (&acc)[2][4][2], double* sm, int R, int job, int g8, int q) {
+  if (job < 2 * R) p2_store2(p2_blk(sm, R, job >> 1) + 16 * (job & 1) * P2_LD, acc, g8, q);
+}
+
+// Row R of T = D^-1/2 Tu -> DIblk, Tblk (rows 32 R .., row-major) and U = T^T (columns 32 R ..), by nt threads.
+__device__ __forceinline__ void p2_out_row(double* sm, int R, int t, int nt, double* DIblk, double* Tblk, double* Ublk, long long ld) {
+  const double* rs = sm + P2_OFF_RS + 32 * R;
+  for (int e = t; e < (R + 1) * 512; e += nt) {
+    const int j = e >> 9, r = (e >> 4) & 31, c2 = (e & 15) * 2;
+    double2 v = *reinterpret_cast<const double2*>(p2_blk(sm, R, j) + r * P2_LD + c2);
+    const double s = rs[r];
+    v.x *= s; v.y *= s;
+    *reinterpret_cast<double2*>(DIblk + (32 * R + r) * 128 + 32 * j + c2) = v;
+    if (Tblk != nullptr) *reinterpret_cast<double2*>(Tblk + (size_t)(32 * R + r) * ld + 32 * j + c2) = v;
+  }
+  if (Ublk != nullptr)
+    for (int e = t; e < (R + 1) * 512; e += nt) {
+      const int j = e >> 9, c = (e >> 4) & 31, r2 = (e & 15) * 2;
+      const double* tb = p2_blk(sm, R, j) + r2 * P2_LD + c;
+      double2 v; v.x = tb[0] * rs[r2]; v.y = tb[P2_LD] * rs[r2 + 1];
+      *reinterpret_cast<double2*>(Ublk + (size_t)(32 * j + c) * ld + 32 * R + r2) = v;
+    }
+}
+
+// Zero sub-blocks: above the diagonal in L, L^-1 (both copies), below it in U.
+__device__ __forceinline__ void p2_out_zeros(int t, int nt, double* Lblk, double* DIblk, double* Tblk, double* Ublk, long long ld) {
+  double2 z; z.x = 0.0; z.y = 0.0;
+  for (int e = t; e < 6 * 512; e += nt) {
+    const int b = e >> 9, r = (e >> 4) & 31, c2 = (e & 15) * 2;
+    const int j = (b >= 3) ? 3 : (b >= 1) ? 2 : 1, i = b - (j * (j - 1)) / 2;  // i < j
+    *reinterpret_cast<double2*>(Lblk + (size_t)(32 * i + r) * ld + 32 * j + c2) = z;
+    *reinterpret_cast<double2*>(DIblk + (32 * i + r) * 128 + 32 * j + c2) = z;
+    if (Tblk != nullptr) *reinterpret_cast<double2*>(Tblk + (size_t)(32 * i + r) * ld + 32 * j + c2) = z;
+    if (Ublk != nullptr) *reinterpret_cast<double2*>(Ublk + (size_t)(32 * j + r) * ld + 32 * i + c2) = z;
+  }
+}
+
+#define P2_BAR7() asm volatile("bar.sync 1, 224;" ::: "memory")
+
+// Same contract as k_potf2 (dgp_panel.cuh): Lblk <- L (zeros above the diagonal), Ublk <- L^-T (upper, optional),
+// DIblk <- L^-1 ([128][128] contiguous), Tblk <- L^-1 (optional, leading dimension ld; may alias Ablk: the block is
+// staged in shared memory before anything is written), scal[SC_LOGDET] += sum log L_ii, first bad pivot -> scal[SC_INFO].
+__global__ void __maxnreg__(144)
+k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double* __restrict__ DIblk,
+           double* __restrict__ scal, int base, double* Tblk) {
+  extern __shared__ __align__(16) double p2_smem[];
+  double* sm = p2_smem;
+  double* ex = sm + P2_OFF_EX;
+  double* wv = sm + P2_OFF_W;
+  double* dvs = sm + P2_OFF_D;
+  double* rsv = sm + P2_OFF_RS;
+  double* sqv = sm + P2_OFF_SQ;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g8 = lane >> 2, q = lane & 3;
+  P2_STAMP(0);
+
+  // ---- stage the lower sub-blocks (upper triangles of the diagonal sub-blocks zeroed): 20 independent 16-byte loads
+  {
+    double2 v[20];
+#pragma unroll
+    for (int u = 0; u < 20; u++) {
+      const int e = u * P2_THREADS + tid;          // 0 .. 5119 = 10 blocks x 32 rows x 16 pairs
+      const int b = e >> 9, r = (e >> 4) & 31, c2 = (e & 15) * 2;
+      const int i = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0, j = b - (i * (i + 1)) / 2;
+      v[u] = *reinterpret_cast<const double2*>(Ablk + (size_t)(32 * i + r) * ld + 32 * j + c2);
+    }
+    p2_out_zeros(tid, P2_THREADS, Lblk, DIblk, Tblk, Ublk, ld);  // independent of the loads in flight (other sub-blocks)
+#pragma unroll
+    for (int u = 0; u < 20; u++) {
+      const int e = u * P2_THREADS + tid;
+      const int b = e >> 9, r = (e >> 4) & 31, c2 = (e & 15) * 2;
+      const int i = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0, j = b - (i * (i + 1)) / 2;
+      double2 w = v[u];
+      if (i == j) { if (c2 > r) w.x = 0.0; if (c2 + 1 > r) w.y = 0.0; }
+      *reinterpret_cast<double2*>(sm + b * P2_BLK + r * P2_LD + c2) = w;
+    }
+  }
+  __syncthreads();
+  P2_STAMP(1);
+
+  int bad = 0;
+  double logacc = 0.0;
+
+#pragma unroll 1
+  for (int k = 0; k < 4; k++) {
+    double* Bkk = p2_blk(sm, k, k);
+    // ---------------------------------------------------------------- phase A
+    if (warp == 0) {
+      double a[32];
+#pragma unroll
+      for (int p = 0; p < 16; p++) {
+        const double2 v = *reinterpret_cast<const double2*>(Bkk + lane * P2_LD + 2 * p);
+        a[2 * p] = v.x; a[2 * p + 1] = v.y;
+      }
+      ex[lane] = a[0];
+      ex[32 + lane] = a[1];
+      __syncwarp();
+      double d = ex[0];
+#pragma unroll
+      for (int c = 0; c < 32; c++) {
+        const double* cA = ex + (c & 1) * 64;
+        const double* cB = cA + 32;
+        double lc1sq = 0.0, cb1 = 0.0;
+        if (c + 1 < 32) { const double lc1 = cA[c + 1]; lc1sq = lc1 * lc1; cb1 = cB[c + 1]; }
+        if (!(d > 0.0) && bad == 0) bad = 32 * k + c + 1;
+        const double w = rcp_newton(d);
+        const double dnext = fma(-lc1sq, w, cb1);
+        if (lane == 0) { wv[32 * k + c] = w; dvs[32 * k + c] = d; }
+        const double tfac = a[c] * w;
+        if (c < lane) Bkk[lane * P2_LD + c] = tfac;  // Lu[lane][c]
+        if (c + 1 < 32) {
+#pragma unroll
+          for (int p = (c + 1) / 2; p < 16; p++) {
+            const double2 v = *reinterpret_cast<const double2*>(cA + 2 * p);
+            if (2 * p >= c + 1) a[2 * p] = fma(-tfac, v.x, a[2 * p]);
+            a[2 * p + 1] = fma(-tfac, v.y, a[2 * p + 1]);
+          }
+          double* nA = ex + ((c + 1) & 1) * 64;
+          nA[lane] = a[c + 1];
+          if (c + 2 < 32) nA[32 + lane] = a[c + 2];
+          __syncwarp();
+          d = dnext;
+        }
+      }
+      P2_STAMP(2 + 6 * k);
+    } else {
+      const int t7 = tid - 32, w7 = (warp < 4) ? warp - 1 : (warp == 4 ? 7 : warp - 2);  // jobs 0..5 avoid warp 4
+      double acc[2][4][2];
+      if (k == 1) p2_out_row(sm, 0, t7, 224, DIblk, Tblk, Ublk, ld);
+      if (k >= 2) {
+        const int R = k - 1;
+        p2_inv_m(acc, sm, R, w7, g8, q);
+        P2_BAR7();
+        p2_inv_store(acc, sm, R, w7, g8, q);
+        P2_BAR7();
+        p2_inv_t(acc, sm, R, w7, g8, q);
+        P2_BAR7();
+        p2_inv_store(acc, sm, R, w7, g8, q);
+        P2_BAR7();
+        p2_out_row(sm, R, t7, 224, DIblk, Tblk, Ublk, ld);
+        if (k == 3) {  // M[3][j] needs nothing of the last diagonal sub-block: only the product with Tu_33 stays behind
+          p2_inv_m(acc, sm, 3, w7, g8, q);
+          P2_BAR7();
+          p2_inv_store(acc, sm, 3, w7, g8, q);
+        }
+      }
+    }
+    P2_STAMP(3 + 6 * k);
+    __syncthreads();
+    P2_STAMP(4 + 6 * k);
+
+    // ---------------------------------------------------------------- phase B: x <- Lu_kk^-1 x by columns
+    double x[32];
+    const bool active = warp <= 3 - k;
+    if (active) {
+      if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) x[c] = (c == lane) ? 1.0 : 0.0;
+      } else {
+        const double* row = p2_blk(sm, k + warp, k) + lane * P2_LD;
+#pragma unroll
+        for (int p = 0; p < 16; p++) {
+          const double2 v = *reinterpret_cast<const double2*>(row + 2 * p);
+          x[2 * p] = v.x; x[2 * p + 1] = v.y;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 31; c++) {
+#pragma unroll
+        for (int c2 = c + 1; c2 < 32; c2++) x[c2] = fma(-x[c], Bkk[c2 * P2_LD + c], x[c2]);
+      }
+    } else if (warp == 7) {
+      // scalings of this sub-block, log-determinant, and L_kk = Lu_kk sqrt(D_k) -> global
+      const double d = dvs[32 * k + lane];
+      const double rs = rsqrt(d), sq = d * rs;
+      rsv[32 * k + lane] = rs;
+      sqv[32 * k + lane] = sq;
+      logacc += 0.5 * log(d);
+      __syncwarp();
+      double* Lrow = Lblk + (size_t)(32 * k + lane) * ld + 32 * k;
+#pragma unroll
+      for (int p = 0; p < 16; p++) {
+        const double2 l2 = *reinterpret_cast<const double2*>(Bkk + lane * P2_LD + 2 * p);
+        const double2 s2 = *reinterpret_cast<const double2*>(sqv + 32 * k + 2 * p);
+        double2 v;
+        v.x = (2 * p < lane) ? l2.x * s2.x : (2 * p == lane ? sq : 0.0);
+        v.y = (2 * p + 1 < lane) ? l2.y * s2.y : (2 * p + 1 == lane ? sq : 0.0);
+        *reinterpret_cast<double2*>(Lrow + 2 * p) = v;
+      }
+    }
+    __syncthreads();
+    P2_STAMP(5 + 6 * k);
+    // ---------------------------------------------------------------- phase C
+    if (active) {
+      if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) Bkk[c * P2_LD + lane] = (c >= lane) ? x[c] : 0.0;  // Tu_kk[c][lane]
+      } else {
+        double* row = p2_blk(sm, k + warp, k) + lane * P2_LD;
+#pragma unroll
+        for (int p = 0; p < 16; p++) {
+          double2 v; v.x = x[2 * p]; v.y = x[2 * p + 1];
+          *reinterpret_cast<double2*>(row + 2 * p) = v;
+        }
+      }
+    }
+    __syncthreads();
+    P2_STAMP(6 + 6 * k);
+    // ---------------------------------------------------------------- phase D
+    if (k < 3) {
+      // L[i][k] = u[i][k] D_k^-1/2, i > k -> global: one pass of the CTA per sub-block (row = tid / 8, 4 columns per thread)
+      for (int i = k + 1; i < 4; i++) {
+        const int r = tid >> 3, c4 = (tid & 7) * 4;
+        const double* src = p2_blk(sm, i, k) + r * P2_LD + c4;
+        const double* rk = rsv + 32 * k + c4;
+        double* dst = Lblk + (size_t)(32 * i + r) * ld + 32 * k + c4;
+        double2 v0 = *reinterpret_cast<const double2*>(src), v1 = *reinterpret_cast<const double2*>(src + 2);
+        v0.x *= rk[0]; v0.y *= rk[1]; v1.x *= rk[2]; v1.y *= rk[3];
+        *reinterpret_cast<double2*>(dst) = v0;
+        *reinterpret_cast<double2*>(dst + 2) = v1;
+      }
+      // B[i][j] -= (u[i][k] W_k) u[j][k]^T, k < j <= i: jobs (tile, half)
+      const int rem = 3 - k, njobs = rem * (rem + 1);
+      for (int job = warp; job < njobs; job += 8) {
+        const int t = job >> 1, mh = job & 1;
+        int ii = 0;
+        while ((ii + 1) * (ii + 2) / 2 <= t) ii++;
+        const int jj = t - ii * (ii + 1) / 2;
+        const int i = k + 1 + ii, j = k + 1 + jj;
+        double* Cst = p2_blk(sm, i, j) + 16 * mh * P2_LD;
+        double acc[2][4][2];
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) {
+            const double2 v = *reinterpret_cast<const double2*>(Cst + (8 * h + g8) * P2_LD + 8 * ni + 2 * q);
+            acc[h][ni][0] = v.x; acc[h][ni][1] = v.y;
+          }
+        p2_strip2<false, true, true, 8>(acc, p2_blk(sm, i, k) + 16 * mh * P2_LD, p2_blk(sm, j, k), wv + 32 * k, g8, q);
+        p2_store2(Cst, acc, g8, q);
+      }
+      __syncthreads();
+    }
+    P2_STAMP(7 + 6 * k);
+  }
+  // ---- row 3 of the inverse: Tu[3][j] = -Tu_33 M[3][j], all warps (6 jobs)
+  {
+    double acc[2][4][2];
+    p2_inv_t(acc, sm, 3, warp, g8, q);
+    __syncthreads();
+    p2_inv_store(acc, sm, 3, warp, g8, q);
+    __syncthreads();
+  }
+  P2_STAMP(26);
+  p2_out_row(sm, 3, tid, P2_THREADS, DIblk, Tblk, Ublk, ld);
+  if (warp == 7) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) logacc += __shfl_xor_sync(0xffffffffu, logacc, o);
+    if (lane == 0) scal[SC_LOGDET] += logacc;
+  }
+  if (tid == 0 && bad != 0 && scal[SC_INFO] == 0.0) scal[SC_INFO] = (double)(base + bad);
+  P2_STAMP(27);
+}
+
+}  // namespace dgp
