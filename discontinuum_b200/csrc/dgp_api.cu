@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/dgp.h"
@@ -57,6 +58,7 @@ struct dgp_handle_s {
   std::vector<cudaEvent_t> evs;      // look-ahead dependencies (no timing)
   bool lookahead = true;
   int panel_blocks = 4;              // block columns per panel of the two-level Cholesky
+  bool pdl = true;                   // programmatic dependent launch along the panel chain (DGP_PDL=0: off)
   bool chain_half = true;            // 64-row half tiles for the panel chain's small launches (DGP_CHAIN_HALF=0: off)
   struct GraphSlot { cudaGraphExec_t exec = nullptr; double jitter = 0.0; bool seen = false; long long launches = 0; };
   GraphSlot graphs[3];               // per evaluation level (nlml / nlml+grad / factorize)
@@ -64,6 +66,7 @@ struct dgp_handle_s {
   int max_n = 0, max_pad = 0, max_m = 0;
   int n = 0, npad = 0, nb = 0, sms = 148;
   bool have_train = false, factorized = false, have_T = false, debug_kinv = false, timing = false;
+  bool lu_zeroed = false;  // bufL / bufU cleared for the current leading dimension (see k_potf2_v2, zero_lu)
   dgp_spec spec;       // internal copy: the caller's spec + derived sin/cos feature columns of periodic factors
   dgp_spec user_spec;  // as passed to dgp_set_train
   // device buffers
@@ -143,9 +146,25 @@ static int make_map(dgp_handle h, CUtensorMap* m, double* base, int rows, int co
   return 0;
 }
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still in its
+// tail (after the predecessor's griddepcontrol.launch_dependents); it blocks in griddepcontrol.wait, before its
+// first global access, until the predecessor has completed and flushed.  Hides the launch latency between the short,
+// strictly dependent kernels of the panel chain.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_ex(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int INIT, int EPI, int MT = 8>
 static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g,
-                       cudaStream_t st = nullptr) {
+                       cudaStream_t st = nullptr, bool pdl = false) {
   if (g.ntiles <= 0) return 0;
   if (st == nullptr) st = h->stream;
   static bool attr_set[64] = {false};  // per device: function attributes belong to the device's context
@@ -157,9 +176,8 @@ static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b,
     CK(h, cudaFuncSetAttribute(k_gemm<INIT, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set[dev] = true;
   }
-  k_gemm<INIT, EPI, MT><<<g.ntiles * (MT == 8 ? 1 : 2), GEMM_THREADS, smem_bytes, st>>>(a, b, h->spec, g);
+  CK(h, launch_ex(k_gemm<INIT, EPI, MT>, g.ntiles * (MT == 8 ? 1 : 2), GEMM_THREADS, (size_t)smem_bytes, st, pdl, a, b, h->spec, g));
   h->launches++;
-  CK(h, cudaGetLastError());
   return 0;
 }
 
@@ -209,6 +227,9 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
     const char* ug = getenv("DGP_GRAPHS");
     if (ug) h->use_graphs = atoi(ug) != 0;
     h->trace_path = getenv("DGP_TRACE");
+    const char* pd = getenv("DGP_PDL");
+    if (pd) h->pdl = atoi(pd) != 0;
+    if (h->use_graphs) h->pdl = false;
     const char* ch = getenv("DGP_CHAIN_HALF");
     if (ch) h->chain_half = atoi(ch) != 0;
     const char* pb = getenv("DGP_PANEL_BLOCKS");
@@ -342,6 +363,9 @@ int dgp_set_train(dgp_handle h, const dgp_spec* spec, const double* X, const dou
   h->factorized = false;
   h->have_T = false;
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CK(h, cudaMemsetAsync(h->bufL, 0, (size_t)h->npad * h->npad * 8, h->stream));
+  CK(h, cudaMemsetAsync(h->bufU, 0, (size_t)h->npad * h->npad * 8, h->stream));
+  h->lu_zeroed = true;
   CK(h, cudaMemsetAsync(h->noise, 0, (size_t)h->npad * 8, h->stream));
   CK(h, cudaMemcpyAsync(h->X, X, (size_t)n * spec->ndim * 8, kind, h->stream));
   CK(h, cudaMemcpyAsync(h->y, y, (size_t)n * 8, kind, h->stream));
@@ -409,35 +433,45 @@ static int ensure_events(dgp_handle h, size_t count) {
 // The wide update reads/writes each trailing tile once per panel instead of once per block column.
 // one rank-(128 kb) update launch: block columns [o, o + w) (M_TRAIL_COL) or the lower triangle from block o (M_TRAIL)
 static int launch_trail(dgp_handle h, const CholBufs& b, int mode, int k0, int kb, int o, int w, int ntiles, bool first_touch,
-                        double jitter, cudaStream_t st, bool half_tiles = false) {
+                        double jitter, cudaStream_t st, bool half_tiles = false, bool pdl = false) {
   GemmArgs g = base_args(h, mode, k0);
   g.nb = b.nb; g.ldc = b.ld;
   g.aux0 = (mode == M_TRAIL_COL) ? (o | (w << 16)) : o;
   g.aux1 = kb;
   g.aux2 = first_touch ? 0 : 1;
   g.C = b.A; g.ntiles = ntiles; g.sign = -1.0; g.jitter = jitter;
-  if (first_touch) return launch_gemm<INIT_COV, EPI_STORE>(h, *b.tL, *b.tL, g, st);
-  if (half_tiles) return launch_gemm<INIT_LOAD, EPI_STORE, 4>(h, *b.tL, *b.tL, g, st);
-  return launch_gemm<INIT_LOAD, EPI_STORE>(h, *b.tL, *b.tL, g, st);
+  if (first_touch) return launch_gemm<INIT_COV, EPI_STORE>(h, *b.tL, *b.tL, g, st, pdl);
+  if (half_tiles) return launch_gemm<INIT_LOAD, EPI_STORE, 4>(h, *b.tL, *b.tL, g, st, pdl);
+  return launch_gemm<INIT_LOAD, EPI_STORE>(h, *b.tL, *b.tL, g, st, pdl);
 }
 
 // the latency-bound chain of one panel [pb, pe) on stream P:
 //   for s: potf2(s) -> TRSM(s) on every row below [-> forward substitution(s)] -> rank-128 update of columns (s, pe)
-static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool generate, double jitter, bool fwd, cudaStream_t P) {
+// mid_wait: event the in-panel update of the first block column has to wait for (the trailing update of the panel's
+// other columns, which stream T applies while the first column is already being factored)
+static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool generate, double jitter, bool fwd, cudaStream_t P,
+                        cudaEvent_t mid_wait = nullptr) {
   const int nb = b.nb;
   const long long ld = b.ld;
   int rc;
+  const bool pdl = h->pdl && !h->trace_path;  // the trace's events would sit between the kernels
   for (int s = pb; s < pe; s++) {
     const size_t off = (size_t)s * 128 * ld + (size_t)s * 128;
     const bool inplace = (b.L == b.A);
     trace_mark(h, P, "potf2<", s);
     static const bool potf2_v1 = getenv("DGP_POTF2_V1") != nullptr && atoi(getenv("DGP_POTF2_V1")) != 0;
+    // T_ss is read by the panel solve from the diagonal block of the work matrix: the contiguous copy in DI is only
+    // written for the in-place factorisation and for the forward-substitution kernel of the NLML-only path
+    const bool t_in_a = !potf2_v1 && !inplace && !fwd;
+    // the zero sub-blocks of bufL / bufU were cleared by dgp_set_train and only this kernel ever writes them
+    const bool lu_clean = !inplace && h->lu_zeroed && b.L == h->bufL && (b.U == nullptr || b.U == h->bufU);
     if (potf2_v1)
       k_potf2<<<1, PF_THREADS, PF_SMEM, P>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
                                              b.DI + (size_t)s * 128 * 128, b.scal, s * 128, inplace ? nullptr : b.A + off);
-    else
-      k_potf2_v2<<<1, P2_THREADS, P2_SMEM, P>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
-                                                b.DI + (size_t)s * 128 * 128, b.scal, s * 128, inplace ? nullptr : b.A + off);
+    else  // dependent launch behind the in-panel update of the previous block column (same stream, nothing in between)
+      CK(h, launch_ex(k_potf2_v2, 1, P2_THREADS, (size_t)P2_SMEM, P, pdl && s > pb && !inplace && !fwd, (const double*)(b.A + off), b.L + off,
+                      b.U ? b.U + off : (double*)nullptr, ld, t_in_a ? (double*)nullptr : b.DI + (size_t)s * 128 * 128, b.scal, s * 128,
+                      inplace ? (double*)nullptr : b.A + off, lu_clean ? 0 : 1));
     h->launches++;
     CK(h, cudaGetLastError());
     trace_mark(h, P, "potf2>", s);
@@ -447,9 +481,11 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
       g.nb = nb; g.ldc = ld;
       g.C = b.L; g.ntiles = 2 * m;
       if (inplace) { g.C = b.P; g.ldc = 128; g.aux0 = 1; }  // both half-tiles read the whole block: stage, then copy
+      g.aux1 = t_in_a ? 1 : 0;
+      const CUtensorMap& tB = t_in_a ? *b.tA : *b.tDI;
       // half tiles while the launch is smaller than the GPU (chain_half: 2 m 64x64-row CTAs fit the 2 x SMs slots)
-      if (h->chain_half && 4 * m <= 2 * h->sms) { if ((rc = launch_gemm<INIT_ZERO, EPI_STORE, 4>(h, *b.tA, *b.tDI, g, P))) return rc; }
-      else if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, *b.tA, *b.tDI, g, P))) return rc;
+      if (h->chain_half && 4 * m <= 2 * h->sms) { if ((rc = launch_gemm<INIT_ZERO, EPI_STORE, 4>(h, *b.tA, tB, g, P, pdl && !potf2_v1))) return rc; }
+      else if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, *b.tA, tB, g, P, pdl && !potf2_v1))) return rc;
       if (inplace) {
         k_copy_panel<<<m, 256, 0, P>>>(b.P, b.A, ld, s);
         h->launches++;
@@ -464,8 +500,10 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
     }
     if (s + 1 < pe) {  // in-panel rank-128 update: block columns (s, pe), rows >= s + 1
       const int w = pe - s - 1;
+      const bool waited = (s == pb && mid_wait != nullptr);
+      if (waited) CK(h, cudaStreamWaitEvent(P, mid_wait, 0));
       if ((rc = launch_trail(h, b, M_TRAIL_COL, s, 1, s + 1, w, m * 2 * w, generate && s == 0, jitter, P,
-                             h->chain_half && 4 * m * w <= 2 * h->sms))) return rc;
+                             h->chain_half && 4 * m * w <= 2 * h->sms, pdl && !inplace && !fwd && !waited))) return rc;
       trace_mark(h, P, "inpanel>", s);
     }
   }
@@ -479,9 +517,10 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
   cudaStream_t T = h->stream, P = h->lookahead ? h->stream_hi : h->stream;
   const int pw = h->panel_blocks;
   const int npanels = (nb + pw - 1) / pw;
-  if ((rc = ensure_events(h, 2 * (size_t)npanels + 2))) return rc;
-  auto ev_panel = [&](int p) { return h->evs[2 * p]; };
-  auto ev_cols = [&](int p) { return h->evs[2 * p + 1]; };
+  if ((rc = ensure_events(h, 3 * (size_t)npanels + 3))) return rc;
+  auto ev_panel = [&](int p) { return h->evs[3 * p]; };
+  auto ev_cols = [&](int p) { return h->evs[3 * p + 1]; };   // all columns of panel p have the updates of panels < p
+  auto ev_col0 = [&](int p) { return h->evs[3 * p + 2]; };   // ... its first block column has them
   if (generate) {
     k_cov_rect<<<dim3(nb * 4, 1), 256, 0, T>>>(h->spec, h->theta, h->Xw, h->Xw, h->noise, jitter, b.A, ld, h->n,
                                                h->n, 1, 1, nullptr, nullptr, 0);
@@ -494,20 +533,27 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
   }
   for (int p = 0; p < npanels; p++) {
     const int pb = p * pw, pe = (pb + pw < nb) ? pb + pw : nb;
-    if (P != T && p > 0) CK(h, cudaStreamWaitEvent(P, ev_cols(p), 0));
-    if ((rc = factor_panel(h, b, pb, pe, generate, jitter, fwd, P))) return rc;
+    if (P != T && p > 0) CK(h, cudaStreamWaitEvent(P, ev_col0(p), 0));
+    if ((rc = factor_panel(h, b, pb, pe, generate, jitter, fwd, P, (P != T && p > 0) ? ev_cols(p) : nullptr))) return rc;
     if (P != T) {
       CK(h, cudaEventRecord(ev_panel(p), P));
       CK(h, cudaStreamWaitEvent(T, ev_panel(p), 0));
     }
     if (pe < nb) {  // rank-(128 (pe - pb)) update right of the panel: next panel's columns, then the rest
       const int ne = (pe + pw < nb) ? pe + pw : nb, w = ne - pe, m = nb - pe;
+      // the first column of the next panel is all its diagonal block and panel solve wait for: update it on its own
       trace_mark(h, T, "cols<", p);
-      if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, pe, w, m * 2 * w, generate && p == 0, jitter, T))) return rc;
+      // (half tiles while a launch has fewer tiles than the GPU has CTA slots: a K = 512 tile is 34 us on its own)
+      const int slots = 2 * h->sms;
+      if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, pe, 1, m * 2, generate && p == 0, jitter, T, h->chain_half && m * 2 <= slots))) return rc;
+      if (P != T) CK(h, cudaEventRecord(ev_col0(p + 1), T));
+      if (w > 1 && (rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, pe + 1, w - 1, (m - 1) * 2 * (w - 1), generate && p == 0, jitter, T,
+                                      h->chain_half && (m - 1) * 2 * (w - 1) <= slots))) return rc;
       trace_mark(h, T, "cols>", p);
       if (P != T) CK(h, cudaEventRecord(ev_cols(p + 1), T));
       const int m2 = nb - ne;
-      if (m2 > 0 && (rc = launch_trail(h, b, M_TRAIL, pb, pe - pb, ne, 0, m2 * (m2 + 1), generate && p == 0, jitter, T))) return rc;
+      if (m2 > 0 && (rc = launch_trail(h, b, M_TRAIL, pb, pe - pb, ne, 0, m2 * (m2 + 1), generate && p == 0, jitter, T,
+                                       h->chain_half && m2 * (m2 + 1) <= slots))) return rc;
       trace_mark(h, T, "rest>", p);
     }
   }

@@ -65,10 +65,11 @@ __device__ __forceinline__ Job decode_job(const GemmArgs& g, int tile, int init_
   j.valid = 1;
   const int s = g.step;
   switch (g.mode) {
-    case M_TRSM: {  // L[i, s] = A[i, s] * Linv_s^T            A: work panel, B: diagonal-inverse table
+    case M_TRSM: {  // L[i, s] = A[i, s] * Linv_s^T            A: work panel, B: diagonal-inverse table, or (aux1 = 1)
+                    // the diagonal block of the work matrix itself, where the diagonal-block kernel left T_ss
       const int i = s + 1 + (tile >> 1), h = tile & 1;
       j.rowA = i * 128; j.kA = s * 128;
-      j.rowB = s * 128 + h * 64; j.kB = 0;
+      j.rowB = s * 128 + h * 64; j.kB = g.aux1 ? s * 128 : 0;
       j.nk = h ? 8 : 4;
       j.crow = i * 128; j.ccol = (g.aux0 ? 0 : s * 128) + h * 64;  // aux0 = 1: into a [rows][128] panel buffer
     } break;
@@ -226,6 +227,8 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
     fence_mbar_init();
   }
   __syncthreads();
+  // dependent launch (panel chain): everything above overlapped the predecessor's tail; no global access before this
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 4) {
     // ------------------------------------------------------------ TMA producer
@@ -242,6 +245,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
         tma_load_2d(st + A_BYTES, &tmB, &full[s], job.kB + it * BK, job.rowB);
       }
     }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     return;
   }
 
@@ -350,6 +354,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   }
 
   // ---- epilogue
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if constexpr (EPI == EPI_STORE) {
 #pragma unroll
     for (int mi = 0; mi < MT; mi++) {

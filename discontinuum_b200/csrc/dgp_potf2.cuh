@@ -30,12 +30,20 @@ constexpr int P2_OFF_W = P2_OFF_EX + 128;       // [128] w = 1 / d
 constexpr int P2_OFF_D = P2_OFF_W + 128;        // [128] pivots d
 constexpr int P2_OFF_RS = P2_OFF_D + 128;       // [128] 1 / sqrt(d) = 1 / L_ii
 constexpr int P2_OFF_SQ = P2_OFF_RS + 128;      // [128] sqrt(d)
-constexpr int P2_SMEM = (P2_OFF_SQ + 128) * 8;  // 97 280 B
+constexpr int P2_OFF_PROG = P2_OFF_SQ + 128;   // int: pivots published so far
+#ifdef P2_TIMING
+constexpr int P2_SMEM = (P2_OFF_PROG + 2 + 128) * 8;
+#else
+constexpr int P2_SMEM = (P2_OFF_PROG + 2) * 8;  // 97 296 B
+#endif
 
 #ifdef P2_TIMING
 __device__ long long p2_ts[64];
-#define P2_STAMP(i) do { if (threadIdx.x == 0) p2_ts[i] = clock64(); } while (0)
+#define P2_STAMP(i) do { if (threadIdx.x == 0) reinterpret_cast<long long*>(p2_smem + P2_OFF_PROG + 2)[i] = clock64(); } while (0)
+#define P2_WSTAMP(b, k) do { if ((threadIdx.x & 31) == 0) reinterpret_cast<long long*>(p2_smem + P2_OFF_PROG + 2)[64 + (b) * 32 + (k) * 8 + (threadIdx.x >> 5)] = clock64(); } while (0)
+__device__ long long p2_wts[64];
 #else
+#define P2_WSTAMP(b, k) do { } while (0)
 #define P2_STAMP(i) do { } while (0)
 #endif
 
@@ -91,17 +99,20 @@ __device__ __forceinline__ void p2_store2(double* C, const double (&acc)[2][4][2
     }
 }
 
-// Row R (>= 1) of the unit inverse, jobs (j, half) = 16 x 32 halves of block (R, j), one per warp (2 R <= nw):
-//   p2_inv_m: M[R][j] = sum_{l = j}^{R-1} Lu[R][l] Tu[l][j], Lu[R][l] = u[R][l] W_l   (accumulators only)
-//   p2_inv_t: Tu[R][j] = -Tu_RR M[R][j]   (Tu_RR unit lower triangular: k <= row)
-__device__ __forceinline__ void p2_inv_m(double (&acc)[2][4][2], double* sm, int R, int job, int g8, int q) {
-  p2_zero(acc);
-  if (job < 2 * R) {
-    const int j = job >> 1, mh = job & 1;
-    for (int l = j; l < R; l++)
-      p2_strip2<true, false, true, 8>(acc, p2_blk(sm, R, l) + 16 * mh * P2_LD, p2_blk(sm, l, j), sm + P2_OFF_W + 32 * l, g8, q);
-  }
+// The unit inverse Tu = Lu^-1 is built right-looking, in place over the dead blocks of u, one row per step:
+//   M[i][j] = sum_{l = j}^{i-1} Lu[i][l] Tu[l][j]   accumulates as the rows l of Tu become final (Lu[i][l] = u[i][l] W_l),
+//   Tu[R][j] = -Tu_RR M[R][j]                        closes row R once Tu_RR is known (Tu_RR unit lower: k <= row).
+// Jobs are 16 x 32 halves (mh) of a 32x32 block.
+__device__ __forceinline__ void p2_load2(double (&acc)[2][4][2], const double* C, int g8, int q) {
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+      const double2 v = *reinterpret_cast<const double2*>(C + (8 * h + g8) * P2_LD + 8 * ni + 2 * q);
+      acc[h][ni][0] = v.x; acc[h][ni][1] = v.y;
+    }
 }
+// job (j, mh), j < R: acc = -Tu_RR[rows of mh] M[R][j]
 __device__ __forceinline__ void p2_inv_t(double (&acc)[2][4][2], double* sm, int R, int job, int g8, int q) {
   p2_zero(acc);
   if (job < 2 * R) {
@@ -110,8 +121,33 @@ __device__ __forceinline__ void p2_inv_t(double (&acc)[2][4][2], double* sm, int
     else p2_strip2<true, true, false, 8>(acc, p2_blk(sm, R, R) + 16 * P2_LD, p2_blk(sm, R, j), nullptr, g8, q);
   }
 }
-__device__ __forceinline__ void p2_inv_store(const double (&acc)[2][4][2], double* sm, int R, int job, int g8, int q) {
+__device__ __forceinline__ void p2_inv_t_store(const double (&acc)[2][4][2], double* sm, int R, int job, int g8, int q) {
   if (job < 2 * R) p2_store2(p2_blk(sm, R, job >> 1) + 16 * (job & 1) * P2_LD, acc, g8, q);
+}
+// M[i][j] += Lu[i][R] Tu[R][j] for i > R, j < R  (each job reads and writes its own 16 rows of block (i, j))
+__device__ __forceinline__ void p2_inv_update(double* sm, int R, int hx, int nh, int g8, int q) {
+  const int njobs = (3 - R) * R * 2;
+  for (int job = hx; job < njobs; job += nh) {
+    const int mh = job & 1, t = job >> 1, j = t % R, i = R + 1 + t / R;
+    double acc[2][4][2];
+    double* C = p2_blk(sm, i, j) + 16 * mh * P2_LD;
+    p2_load2(acc, C, g8, q);
+    p2_strip2<true, false, true, 8>(acc, p2_blk(sm, i, R) + 16 * mh * P2_LD, p2_blk(sm, R, j), sm + P2_OFF_W + 32 * R, g8, q);
+    p2_store2(C, acc, g8, q);
+  }
+}
+// M[i][R] = Lu[i][R] Tu_RR for i > R, in place over u[i][R] (a job reads only its own 16 rows of it)
+__device__ __forceinline__ void p2_inv_first(double* sm, int R, int hx, int nh, int g8, int q) {
+  const int njobs = (3 - R) * 2;
+  for (int job = hx; job < njobs; job += nh) {
+    const int mh = job & 1, i = R + 1 + (job >> 1);
+    double acc[2][4][2];
+    double* C = p2_blk(sm, i, R) + 16 * mh * P2_LD;
+    p2_zero(acc);
+    p2_strip2<true, false, true, 8>(acc, C, p2_blk(sm, R, R), sm + P2_OFF_W + 32 * R, g8, q);
+    __syncwarp();
+    p2_store2(C, acc, g8, q);
+  }
 }
 
 // Row R of T = D^-1/2 Tu -> DIblk, Tblk (rows 32 R .., row-major) and U = T^T (columns 32 R ..), by nt threads.
@@ -122,7 +158,7 @@ __device__ __forceinline__ void p2_out_row(double* sm, int R, int t, int nt, dou
     double2 v = *reinterpret_cast<const double2*>(p2_blk(sm, R, j) + r * P2_LD + c2);
     const double s = rs[r];
     v.x *= s; v.y *= s;
-    *reinterpret_cast<double2*>(DIblk + (32 * R + r) * 128 + 32 * j + c2) = v;
+    if (DIblk != nullptr) *reinterpret_cast<double2*>(DIblk + (32 * R + r) * 128 + 32 * j + c2) = v;
     if (Tblk != nullptr) *reinterpret_cast<double2*>(Tblk + (size_t)(32 * R + r) * ld + 32 * j + c2) = v;
   }
   if (Ublk != nullptr)
@@ -134,27 +170,42 @@ __device__ __forceinline__ void p2_out_row(double* sm, int R, int t, int nt, dou
     }
 }
 
-// Zero sub-blocks: above the diagonal in L, L^-1 (both copies), below it in U.
-__device__ __forceinline__ void p2_out_zeros(int t, int nt, double* Lblk, double* DIblk, double* Tblk, double* Ublk, long long ld) {
+// Zero sub-blocks: above the diagonal in L^-1 (both copies, when present) and, with zero_lu, in L, below it in U.
+__device__ __forceinline__ void p2_out_zeros(int t, int nt, double* Lblk, double* DIblk, double* Tblk, double* Ublk, long long ld,
+                                             int zero_lu) {
   double2 z; z.x = 0.0; z.y = 0.0;
   for (int e = t; e < 6 * 512; e += nt) {
     const int b = e >> 9, r = (e >> 4) & 31, c2 = (e & 15) * 2;
     const int j = (b >= 3) ? 3 : (b >= 1) ? 2 : 1, i = b - (j * (j - 1)) / 2;  // i < j
-    *reinterpret_cast<double2*>(Lblk + (size_t)(32 * i + r) * ld + 32 * j + c2) = z;
-    *reinterpret_cast<double2*>(DIblk + (32 * i + r) * 128 + 32 * j + c2) = z;
+    if (zero_lu) *reinterpret_cast<double2*>(Lblk + (size_t)(32 * i + r) * ld + 32 * j + c2) = z;
+    if (DIblk != nullptr) *reinterpret_cast<double2*>(DIblk + (32 * i + r) * 128 + 32 * j + c2) = z;
     if (Tblk != nullptr) *reinterpret_cast<double2*>(Tblk + (size_t)(32 * i + r) * ld + 32 * j + c2) = z;
-    if (Ublk != nullptr) *reinterpret_cast<double2*>(Ublk + (size_t)(32 * j + r) * ld + 32 * i + c2) = z;
+    if (zero_lu && Ublk != nullptr) *reinterpret_cast<double2*>(Ublk + (size_t)(32 * j + r) * ld + 32 * i + c2) = z;
   }
 }
 
-#define P2_BAR7() asm volatile("bar.sync 1, 224;" ::: "memory")
+__device__ __forceinline__ int p2_ld_prog(const int* prog) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(prog)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void p2_st_prog(int* prog, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(prog)), "r"(v) : "memory");
+}
 
-// Same contract as k_potf2 (dgp_panel.cuh): Lblk <- L (zeros above the diagonal), Ublk <- L^-T (upper, optional),
-// DIblk <- L^-1 ([128][128] contiguous), Tblk <- L^-1 (optional, leading dimension ld; may alias Ablk: the block is
-// staged in shared memory before anything is written), scal[SC_LOGDET] += sum log L_ii, first bad pivot -> scal[SC_INFO].
+#define P2_BARH(nh) asm volatile("bar.sync 1, %0;" ::"r"((nh) * 32) : "memory")
+
+// Same contract as k_potf2 (dgp_panel.cuh): Lblk <- L, Ublk <- L^-T (upper, optional), DIblk <- L^-1 ([128][128]
+// contiguous, optional), Tblk <- L^-1 (optional, leading dimension ld; may alias Ablk: the block is staged in shared
+// memory before anything is written), scal[SC_LOGDET] += sum log L_ii, first bad pivot -> scal[SC_INFO].
+// zero_lu = 0: the 32x32 sub-blocks above the diagonal of Lblk / below the diagonal of Ublk are known to be zero already.
+//
+// Warp roles in phase A of step k: warp 0 pivots; warps 1..3-k follow with the rows of the sub-blocks below and warp 5
+// with the rows of the identity (one pivot behind, through the published columns of Lu); warp 4 waits for the last pivot
+// and takes the scalings; the helpers (warps 6, 7; at k = 3 warps 1, 2, 3, 6, 7) finish the previous row of the inverse.
 __global__ void __maxnreg__(144)
-k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double* __restrict__ DIblk,
-           double* __restrict__ scal, int base, double* Tblk) {
+k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double* DIblk, double* __restrict__ scal, int base,
+           double* Tblk, int zero_lu) {
   extern __shared__ __align__(16) double p2_smem[];
   double* sm = p2_smem;
   double* ex = sm + P2_OFF_EX;
@@ -162,9 +213,11 @@ k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double*
   double* dvs = sm + P2_OFF_D;
   double* rsv = sm + P2_OFF_RS;
   double* sqv = sm + P2_OFF_SQ;
+  int* prog = reinterpret_cast<int*>(sm + P2_OFF_PROG);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g8 = lane >> 2, q = lane & 3;
   P2_STAMP(0);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- stage the lower sub-blocks (upper triangles of the diagonal sub-blocks zeroed): 20 independent 16-byte loads
   {
@@ -176,7 +229,7 @@ k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double*
       const int i = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0, j = b - (i * (i + 1)) / 2;
       v[u] = *reinterpret_cast<const double2*>(Ablk + (size_t)(32 * i + r) * ld + 32 * j + c2);
     }
-    p2_out_zeros(tid, P2_THREADS, Lblk, DIblk, Tblk, Ublk, ld);  // independent of the loads in flight (other sub-blocks)
+    if (tid == 0) p2_st_prog(prog, 0);
 #pragma unroll
     for (int u = 0; u < 20; u++) {
       const int e = u * P2_THREADS + tid;
@@ -191,11 +244,13 @@ k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double*
   P2_STAMP(1);
 
   int bad = 0;
-  double logacc = 0.0;
 
 #pragma unroll 1
   for (int k = 0; k < 4; k++) {
     double* Bkk = p2_blk(sm, k, k);
+    const bool row_follower = warp >= 1 && warp <= 3 - k;
+    const bool follower = row_follower || warp == 5;
+    double x[32];
     // ---------------------------------------------------------------- phase A
     if (warp == 0) {
       double a[32];
@@ -230,64 +285,38 @@ k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double*
           double* nA = ex + ((c + 1) & 1) * 64;
           nA[lane] = a[c + 1];
           if (c + 2 < 32) nA[32 + lane] = a[c + 2];
-          __syncwarp();
-          d = dnext;
         }
+        __syncwarp();
+        if (lane == 0) p2_st_prog(prog, 32 * k + c + 1);  // column c of Lu, w_c, d_c are out
+        d = dnext;
       }
       P2_STAMP(2 + 6 * k);
-    } else {
-      const int t7 = tid - 32, w7 = (warp < 4) ? warp - 1 : (warp == 4 ? 7 : warp - 2);  // jobs 0..5 avoid warp 4
-      double acc[2][4][2];
-      if (k == 1) p2_out_row(sm, 0, t7, 224, DIblk, Tblk, Ublk, ld);
-      if (k >= 2) {
-        const int R = k - 1;
-        p2_inv_m(acc, sm, R, w7, g8, q);
-        P2_BAR7();
-        p2_inv_store(acc, sm, R, w7, g8, q);
-        P2_BAR7();
-        p2_inv_t(acc, sm, R, w7, g8, q);
-        P2_BAR7();
-        p2_inv_store(acc, sm, R, w7, g8, q);
-        P2_BAR7();
-        p2_out_row(sm, R, t7, 224, DIblk, Tblk, Ublk, ld);
-        if (k == 3) {  // M[3][j] needs nothing of the last diagonal sub-block: only the product with Tu_33 stays behind
-          p2_inv_m(acc, sm, 3, w7, g8, q);
-          P2_BAR7();
-          p2_inv_store(acc, sm, 3, w7, g8, q);
-        }
-      }
-    }
-    P2_STAMP(3 + 6 * k);
-    __syncthreads();
-    P2_STAMP(4 + 6 * k);
-
-    // ---------------------------------------------------------------- phase B: x <- Lu_kk^-1 x by columns
-    double x[32];
-    const bool active = warp <= 3 - k;
-    if (active) {
-      if (warp == 0) {
-#pragma unroll
-        for (int c = 0; c < 32; c++) x[c] = (c == lane) ? 1.0 : 0.0;
-      } else {
+    } else if (follower) {
+      // x <- Lu_kk^-1 x by columns, column c as soon as the pivot warp has published it
+      if (row_follower) {
         const double* row = p2_blk(sm, k + warp, k) + lane * P2_LD;
 #pragma unroll
         for (int p = 0; p < 16; p++) {
           const double2 v = *reinterpret_cast<const double2*>(row + 2 * p);
           x[2 * p] = v.x; x[2 * p + 1] = v.y;
         }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c++) x[c] = (c == lane) ? 1.0 : 0.0;
       }
 #pragma unroll
       for (int c = 0; c < 31; c++) {
+        while (p2_ld_prog(prog) < 32 * k + c + 1) { }
 #pragma unroll
         for (int c2 = c + 1; c2 < 32; c2++) x[c2] = fma(-x[c], Bkk[c2 * P2_LD + c], x[c2]);
       }
-    } else if (warp == 7) {
-      // scalings of this sub-block, log-determinant, and L_kk = Lu_kk sqrt(D_k) -> global
+    } else if (warp == 4) {
+      // scalings of this sub-block, log-determinant, and L_kk = Lu_kk sqrt(D_k) -> global, once the last pivot is out
+      while (p2_ld_prog(prog) < 32 * k + 32) { }
       const double d = dvs[32 * k + lane];
       const double rs = rsqrt(d), sq = d * rs;
       rsv[32 * k + lane] = rs;
       sqv[32 * k + lane] = sq;
-      logacc += 0.5 * log(d);
       __syncwarp();
       double* Lrow = Lblk + (size_t)(32 * k + lane) * ld + 32 * k;
 #pragma unroll
@@ -299,12 +328,46 @@ k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double*
         v.y = (2 * p + 1 < lane) ? l2.y * s2.y : (2 * p + 1 == lane ? sq : 0.0);
         *reinterpret_cast<double2*>(Lrow + 2 * p) = v;
       }
+    } else if (warp >= 6 || warp >= 4 - k) {
+      // helpers (warps 6, 7 and the follower warps already out of work: 2 + k of them): global stores that nothing on
+      // the chain waits for, and the inverse: close row R = k-1, push its contributions into the rows below
+      const int nh = 2 + k;
+      const int hx = (warp >= 6) ? k + warp - 6 : warp - (4 - k);
+      const int ht = hx * 32 + lane, nht = nh * 32;
+      if (k == 0) { p2_out_zeros(ht, nht, Lblk, DIblk, Tblk, Ublk, ld, zero_lu); goto phase_a_done; }
+      const int R = k - 1;
+      // L[i][R] = u[i][R] D_R^-1/2, i > R
+      for (int e = ht; e < (3 - R) * 256; e += nht) {
+        const int i = R + 1 + (e >> 8), r = (e >> 3) & 31, c4 = (e & 7) * 4;
+        const double* src = p2_blk(sm, i, R) + r * P2_LD + c4;
+        const double* rk = rsv + 32 * R + c4;
+        double* dst = Lblk + (size_t)(32 * i + r) * ld + 32 * R + c4;
+        double2 v0 = *reinterpret_cast<const double2*>(src), v1 = *reinterpret_cast<const double2*>(src + 2);
+        v0.x *= rk[0]; v0.y *= rk[1]; v1.x *= rk[2]; v1.y *= rk[3];
+        *reinterpret_cast<double2*>(dst) = v0;
+        *reinterpret_cast<double2*>(dst + 2) = v1;
+      }
+      if (R >= 1) {
+        double acc[2][4][2];
+        p2_inv_t(acc, sm, R, hx, g8, q);
+        P2_BARH(nh);
+        p2_inv_t_store(acc, sm, R, hx, g8, q);
+        P2_BARH(nh);
+        p2_inv_update(sm, R, hx, nh, g8, q);
+      }
+      P2_BARH(nh);  // every read of u[i][R] above is done
+      p2_inv_first(sm, R, hx, nh, g8, q);
+      p2_out_row(sm, R, ht, nht, DIblk, Tblk, Ublk, ld);
     }
+  phase_a_done:
+    P2_STAMP(3 + 6 * k);
+    P2_WSTAMP(0, k);
     __syncthreads();
+    P2_STAMP(4 + 6 * k);
     P2_STAMP(5 + 6 * k);
-    // ---------------------------------------------------------------- phase C
-    if (active) {
-      if (warp == 0) {
+    // ---------------------------------------------------------------- phase C: followers' results back
+    if (follower) {
+      if (!row_follower) {
 #pragma unroll
         for (int c = 0; c < 32; c++) Bkk[c * P2_LD + lane] = (c >= lane) ? x[c] : 0.0;  // Tu_kk[c][lane]
       } else {
@@ -316,21 +379,11 @@ k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double*
         }
       }
     }
+    P2_WSTAMP(1, k);
     __syncthreads();
     P2_STAMP(6 + 6 * k);
     // ---------------------------------------------------------------- phase D
     if (k < 3) {
-      // L[i][k] = u[i][k] D_k^-1/2, i > k -> global: one pass of the CTA per sub-block (row = tid / 8, 4 columns per thread)
-      for (int i = k + 1; i < 4; i++) {
-        const int r = tid >> 3, c4 = (tid & 7) * 4;
-        const double* src = p2_blk(sm, i, k) + r * P2_LD + c4;
-        const double* rk = rsv + 32 * k + c4;
-        double* dst = Lblk + (size_t)(32 * i + r) * ld + 32 * k + c4;
-        double2 v0 = *reinterpret_cast<const double2*>(src), v1 = *reinterpret_cast<const double2*>(src + 2);
-        v0.x *= rk[0]; v0.y *= rk[1]; v1.x *= rk[2]; v1.y *= rk[3];
-        *reinterpret_cast<double2*>(dst) = v0;
-        *reinterpret_cast<double2*>(dst + 2) = v1;
-      }
       // B[i][j] -= (u[i][k] W_k) u[j][k]^T, k < j <= i: jobs (tile, half)
       const int rem = 3 - k, njobs = rem * (rem + 1);
       for (int job = warp; job < njobs; job += 8) {
@@ -355,23 +408,33 @@ k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double*
     }
     P2_STAMP(7 + 6 * k);
   }
-  // ---- row 3 of the inverse: Tu[3][j] = -Tu_33 M[3][j], all warps (6 jobs)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the panel solve may start its prologue
+  // ---- row 3 of the inverse: Tu[3][j] = -Tu_33 M[3][j], 6 jobs on warps 0..5
   {
     double acc[2][4][2];
     p2_inv_t(acc, sm, 3, warp, g8, q);
     __syncthreads();
-    p2_inv_store(acc, sm, 3, warp, g8, q);
+    p2_inv_t_store(acc, sm, 3, warp, g8, q);
+    if (tid < 128) {  // log-determinant: one logarithm per thread, summed in a fixed order
+      double lg = 0.5 * log(dvs[tid]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+      if (lane == 0) ex[warp] = lg;
+    }
     __syncthreads();
   }
   P2_STAMP(26);
   p2_out_row(sm, 3, tid, P2_THREADS, DIblk, Tblk, Ublk, ld);
-  if (warp == 7) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) logacc += __shfl_xor_sync(0xffffffffu, logacc, o);
-    if (lane == 0) scal[SC_LOGDET] += logacc;
+  if (tid == 0) {
+    scal[SC_LOGDET] += (ex[0] + ex[1]) + (ex[2] + ex[3]);
+    if (bad != 0 && scal[SC_INFO] == 0.0) scal[SC_INFO] = (double)(base + bad);
   }
-  if (tid == 0 && bad != 0 && scal[SC_INFO] == 0.0) scal[SC_INFO] = (double)(base + bad);
   P2_STAMP(27);
+#ifdef P2_TIMING
+  __syncthreads();
+  if (tid < 64) p2_ts[tid] = reinterpret_cast<long long*>(p2_smem + P2_OFF_PROG + 2)[tid];
+  if (tid < 64) p2_wts[tid] = reinterpret_cast<long long*>(p2_smem + P2_OFF_PROG + 2)[64 + tid];
+#endif
 }
 
 }  // namespace dgp

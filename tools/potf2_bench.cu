@@ -43,7 +43,7 @@ int main() {
       cudaEventRecord(e0);
       for (int it = 0; it < iters; it++) {
         if (v == 0) k_potf2<<<1, PF_THREADS, PF_SMEM>>>(dA, dL[v], dU[v], ld, dDI[v], scal, 0, dT[v]);
-        else k_potf2_v2<<<1, P2_THREADS, P2_SMEM>>>(dA, dL[v], dU[v], ld, dDI[v], scal, 0, dT[v]);
+        else k_potf2_v2<<<1, P2_THREADS, P2_SMEM>>>(dA, dL[v], dU[v], ld, getenv("P2_FULL") ? dDI[v] : nullptr, scal, 0, dT[v], getenv("P2_FULL") ? 1 : 0);
       }
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -76,6 +76,14 @@ int main() {
            ts[3 + 6 * k] - ts[2 + 6 * k], ts[4 + 6 * k] - ts[3 + 6 * k], ts[5 + 6 * k] - ts[4 + 6 * k], ts[6 + 6 * k] - ts[5 + 6 * k],
            ts[7 + 6 * k] - ts[6 + 6 * k]);
   printf(" inv row 3 %lld  outputs %lld  total %lld\n", ts[26] - ts[25], ts[27] - ts[26], ts[27] - ts[0]);
+  long long wts[64];
+  cudaMemcpyFromSymbol(wts, p2_wts, sizeof(wts));
+  for (int b = 0; b < 2; b++)
+    for (int k = 0; k < 4; k++) {
+      printf(" barrier %d k=%d arrival of warps 0..7 (cycles after phase A start):", b, k);
+      for (int w = 0; w < 8; w++) printf(" %lld", wts[b * 32 + k * 8 + w] - (k ? ts[7 + 6 * (k - 1)] : ts[1]));
+      printf("\n");
+    }
 #endif
   return 0;
 }
