@@ -32,7 +32,7 @@ struct FactorC {
 struct TermC {
   double scale;
   double gate_a;
-  int scale_idx, gate, gate_col, gate_theta, nf, pad_;
+  int scale_idx, gate, gate_col, gate_theta, nf, shape;  // shape: SH_* code of (factor kinds, dimensions), 0 = generic
   FactorC f[DGP_MAX_FACTORS];
 };
 
@@ -48,6 +48,49 @@ constexpr int SLOT_GATE = 1;
 constexpr int SLOT_F0 = 2;                       // + f * SLOT_PER_F + d  (d < 4: lengthscale d; d == 4: period)
 constexpr int SLOT_PER_F = DGP_MAX_FDIMS + 1;
 constexpr int NSLOT = SLOT_F0 + DGP_MAX_FACTORS * SLOT_PER_F;  // 17
+
+// Term shapes with straight-line evaluators.  The V-wide evaluators below are written once, against a shape class:
+// ShapeRT reads the factor kinds / dimension counts from the term at run time (an interpreter: ~70 % of its
+// instructions are loop and branch bookkeeping), Shape<...> fixes them at compile time so that the same code folds to
+// the arithmetic of that one product of factors.  cov_compile() tags every term; unknown products stay generic.
+enum { SH_GENERIC = 0, SH_PER_M52 = 1, SH_RBF1 = 2, SH_M32_2 = 3, SH_M52_1 = 4, SH_M52_M32 = 5, SH_M52_M52 = 6, SH_RBF2 = 7,
+       SH_M32_1 = 8, SH_M52_2 = 9 };
+
+struct ShapeRT {
+  static constexpr bool fixed = false;
+  static constexpr int nf = 0, k0 = 0, n0 = 0, k1 = 0, n1 = 0;
+};
+template <int NF, int K0, int N0, int K1 = 0, int N1 = 0>
+struct Shape {
+  static constexpr bool fixed = true;
+  static constexpr int nf = NF, k0 = K0, n0 = N0, k1 = K1, n1 = N1;
+};
+template <class S> __device__ __forceinline__ int sh_nf(const TermC& tc) { if constexpr (S::fixed) return S::nf; else return tc.nf; }
+template <class S> __device__ __forceinline__ int sh_kind(const TermC& tc, int f) {
+  if constexpr (S::fixed) return f == 0 ? S::k0 : S::k1; else return tc.f[f].kind;
+}
+template <class S> __device__ __forceinline__ int sh_nd(const TermC& tc, int f) {
+  if constexpr (S::fixed) return f == 0 ? S::n0 : (f == 1 ? S::n1 : 0); else return tc.f[f].ndims;
+}
+
+__device__ __forceinline__ int term_shape(const dgp_term& st) {
+  const int nf = st.nfactors;
+  const dgp_factor& a = st.factor[0];
+  const dgp_factor& b = st.factor[1];
+  if (nf == 1) {
+    if (a.kind == DGP_RBF && a.ndims == 1) return SH_RBF1;
+    if (a.kind == DGP_RBF && a.ndims == 2) return SH_RBF2;
+    if (a.kind == DGP_MATERN32 && a.ndims == 1) return SH_M32_1;
+    if (a.kind == DGP_MATERN32 && a.ndims == 2) return SH_M32_2;
+    if (a.kind == DGP_MATERN52 && a.ndims == 1) return SH_M52_1;
+    if (a.kind == DGP_MATERN52 && a.ndims == 2) return SH_M52_2;
+  } else if (nf == 2) {
+    if (a.kind == DGP_PERIODIC && b.kind == DGP_MATERN52 && b.ndims == 1) return SH_PER_M52;
+    if (a.kind == DGP_MATERN52 && a.ndims == 1 && b.kind == DGP_MATERN32 && b.ndims == 1) return SH_M52_M32;
+    if (a.kind == DGP_MATERN52 && a.ndims == 1 && b.kind == DGP_MATERN52 && b.ndims == 1) return SH_M52_M52;
+  }
+  return SH_GENERIC;
+}
 
 // Fold (spec, theta) into shared memory.  Call with all threads of the CTA; ends with a barrier
 // only if `sync` is set (callers that have their own barrier pass false).
@@ -68,6 +111,7 @@ __device__ __forceinline__ void cov_compile(CovC* cc, const dgp_spec& sp, const 
         tc.gate_a = sp.col[st.gate_col].aux;
       }
       tc.nf = st.nfactors;
+      tc.shape = term_shape(st);
       for (int f = 0; f < DGP_MAX_FACTORS; f++) {
         FactorC& fc = tc.f[f];
         const dgp_factor& sf = st.factor[f];
@@ -93,7 +137,7 @@ __device__ __forceinline__ void cov_compile(CovC* cc, const dgp_spec& sp, const 
         }
       }
     } else {
-      tc.nf = 0; tc.scale = 0.0; tc.scale_idx = -1; tc.gate = 0;
+      tc.nf = 0; tc.scale = 0.0; tc.scale_idx = -1; tc.gate = 0; tc.shape = SH_GENERIC;
     }
   }
   if (tid == 0) {
@@ -250,35 +294,36 @@ __device__ __forceinline__ double fast_sqrt_nonneg(double d2) {
   return d2 > 0.0 ? d2 * rsqrt(d2) : 0.0;
 }
 
-template <int V>
-__device__ __forceinline__ void cov_vals(const CovC* cc, const double* __restrict__ xaT, int a_stride, int a_idx,
-                                         const double* __restrict__ xb, double (&out)[V]) {
+// out[v] += value of term tc for the V entries
+template <int V, class S>
+__device__ __forceinline__ void term_vals_v(const TermC& tc, const double* __restrict__ xaT, int a_stride, int a_idx,
+                                            const double* __restrict__ xb, double (&out)[V]) {
+  double P[V], EX[V];
 #pragma unroll
-  for (int v = 0; v < V; v++) out[v] = 0.0;
-  for (int t = 0; t < cc->nterms; t++) {
-    const TermC& tc = cc->t[t];
-    double P[V], EX[V];
+  for (int v = 0; v < V; v++) { P[v] = tc.scale; EX[v] = 0.0; }
+  if (tc.gate != DGP_GATE_NONE) {
+    double ga = xaT[tc.gate_col * a_stride + a_idx];
+    if (tc.gate == DGP_GATE_INV_SIGMOID) ga = 1.0 - ga;
 #pragma unroll
-    for (int v = 0; v < V; v++) { P[v] = tc.scale; EX[v] = 0.0; }
-    if (tc.gate != DGP_GATE_NONE) {
-      double ga = xaT[tc.gate_col * a_stride + a_idx];
-      if (tc.gate == DGP_GATE_INV_SIGMOID) ga = 1.0 - ga;
-#pragma unroll
-      for (int v = 0; v < V; v++) {
-        double gb = xb[v * DGP_XS + tc.gate_col];
-        if (tc.gate == DGP_GATE_INV_SIGMOID) gb = 1.0 - gb;
-        P[v] *= ga * gb;
-      }
+    for (int v = 0; v < V; v++) {
+      double gb = xb[v * DGP_XS + tc.gate_col];
+      if (tc.gate == DGP_GATE_INV_SIGMOID) gb = 1.0 - gb;
+      P[v] *= ga * gb;
     }
-    for (int f = 0; f < tc.nf; f++) {
+  }
+#pragma unroll
+  for (int f = 0; f < DGP_MAX_FACTORS; f++) {
+    if (f < sh_nf<S>(tc)) {
       const FactorC& fc = tc.f[f];
-      if (fc.kind == DGP_PERIODIC) {
+      const int kind = sh_kind<S>(tc, f);
+      if (kind == DGP_PERIODIC) {
         if (fc.sc_col >= 0) {  // sin(pi (xa - xb) / p) from the per-point sin / cos columns
           const double sa = xaT[fc.sc_col * a_stride + a_idx], ca = xaT[(fc.sc_col + 1) * a_stride + a_idx];
+          const double c2 = 2.0 * fc.inv_lam;
 #pragma unroll
           for (int v = 0; v < V; v++) {
             const double sn = fma(sa, xb[v * DGP_XS + fc.sc_col + 1], -ca * xb[v * DGP_XS + fc.sc_col]);
-            EX[v] = fma(2.0 * fc.inv_lam * sn, sn, EX[v]);
+            EX[v] = fma(c2 * sn, sn, EX[v]);
           }
         } else {
           const double xa = xaT[fc.col[0] * a_stride + a_idx];
@@ -292,18 +337,21 @@ __device__ __forceinline__ void cov_vals(const CovC* cc, const double* __restric
         double d2[V];
 #pragma unroll
         for (int v = 0; v < V; v++) d2[v] = 0.0;
-        for (int d = 0; d < fc.ndims; d++) {
-          const double xa = xaT[fc.col[d] * a_stride + a_idx];
 #pragma unroll
-          for (int v = 0; v < V; v++) {
-            const double z = (xa - xb[v * DGP_XS + fc.col[d]]) * fc.inv_ls[d];
-            d2[v] = fma(z, z, d2[v]);
+        for (int d = 0; d < DGP_MAX_FDIMS; d++) {
+          if (d < sh_nd<S>(tc, f)) {
+            const double xa = xaT[fc.col[d] * a_stride + a_idx];
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+              const double z = (xa - xb[v * DGP_XS + fc.col[d]]) * fc.inv_ls[d];
+              d2[v] = fma(z, z, d2[v]);
+            }
           }
         }
-        if (fc.kind == DGP_RBF) {
+        if (kind == DGP_RBF) {
 #pragma unroll
           for (int v = 0; v < V; v++) EX[v] = fma(0.5, d2[v], EX[v]);
-        } else if (fc.kind == DGP_MATERN32) {
+        } else if (kind == DGP_MATERN32) {
 #pragma unroll
           for (int v = 0; v < V; v++) {
             const double a = 1.7320508075688772 * fast_sqrt_nonneg(d2[v]);
@@ -320,14 +368,40 @@ __device__ __forceinline__ void cov_vals(const CovC* cc, const double* __restric
         }
       }
     }
+  }
 #pragma unroll
-    for (int v = 0; v < V; v++) out[v] = fma(P[v], exp(-EX[v]), out[v]);
+  for (int v = 0; v < V; v++) out[v] = fma(P[v], exp(-EX[v]), out[v]);
+}
+
+// shape dispatch (uniform over the CTA): one switch per term and group of V entries
+#define DGP_SHAPE_SWITCH(shape, CALL)                                             \
+  switch (shape) {                                                                \
+    case SH_PER_M52: { using S = Shape<2, DGP_PERIODIC, 1, DGP_MATERN52, 1>; CALL; } break; \
+    case SH_RBF1: { using S = Shape<1, DGP_RBF, 1>; CALL; } break;                \
+    case SH_RBF2: { using S = Shape<1, DGP_RBF, 2>; CALL; } break;                \
+    case SH_M32_1: { using S = Shape<1, DGP_MATERN32, 1>; CALL; } break;          \
+    case SH_M32_2: { using S = Shape<1, DGP_MATERN32, 2>; CALL; } break;          \
+    case SH_M52_1: { using S = Shape<1, DGP_MATERN52, 1>; CALL; } break;          \
+    case SH_M52_2: { using S = Shape<1, DGP_MATERN52, 2>; CALL; } break;          \
+    case SH_M52_M32: { using S = Shape<2, DGP_MATERN52, 1, DGP_MATERN32, 1>; CALL; } break; \
+    case SH_M52_M52: { using S = Shape<2, DGP_MATERN52, 1, DGP_MATERN52, 1>; CALL; } break; \
+    default: { using S = ShapeRT; CALL; } break;                                  \
+  }
+
+template <int V>
+__device__ __forceinline__ void cov_vals(const CovC* cc, const double* __restrict__ xaT, int a_stride, int a_idx,
+                                         const double* __restrict__ xb, double (&out)[V]) {
+#pragma unroll
+  for (int v = 0; v < V; v++) out[v] = 0.0;
+  for (int t = 0; t < cc->nterms; t++) {
+    const TermC& tc = cc->t[t];
+    DGP_SHAPE_SWITCH(tc.shape, (term_vals_v<V, S>(tc, xaT, a_stride, a_idx, xb, out)))
   }
 }
 
 // Accumulate w[v] * d(term)/d(param) over V entries into acc[NSLOT] (same slot layout as term_grad_accum).
-template <int V>
-__device__ __forceinline__ void term_grad_accum_v(const TermC& tc, const double* __restrict__ xaT, int a_stride, int a_idx,
+template <int V, class S>
+__device__ __forceinline__ void term_grad_accum_s(const TermC& tc, const double* __restrict__ xaT, int a_stride, int a_idx,
                                                   const double* __restrict__ xb, const double (&w)[V], double (&acc)[NSLOT]) {
   double G[V], dG[V], EX[V];
   double poly[DGP_MAX_FACTORS][V], aux[DGP_MAX_FACTORS][V];  // aux: Matern a | periodic sin*cos*u
@@ -350,9 +424,10 @@ __device__ __forceinline__ void term_grad_accum_v(const TermC& tc, const double*
   for (int f = 0; f < DGP_MAX_FACTORS; f++) {
 #pragma unroll
     for (int v = 0; v < V; v++) { poly[f][v] = 1.0; aux[f][v] = 0.0; }
-    if (f < tc.nf) {
+    if (f < sh_nf<S>(tc)) {
       const FactorC& fc = tc.f[f];
-      if (fc.kind == DGP_PERIODIC) {
+      const int kind = sh_kind<S>(tc, f);
+      if (kind == DGP_PERIODIC) {
         const double xa = xaT[fc.col[0] * a_stride + a_idx];
         double sa = 0.0, ca = 0.0;
         if (fc.sc_col >= 0) { sa = xaT[fc.sc_col * a_stride + a_idx]; ca = xaT[(fc.sc_col + 1) * a_stride + a_idx]; }
@@ -375,18 +450,21 @@ __device__ __forceinline__ void term_grad_accum_v(const TermC& tc, const double*
         double d2[V];
 #pragma unroll
         for (int v = 0; v < V; v++) d2[v] = 0.0;
-        for (int d = 0; d < fc.ndims; d++) {
-          const double xa = xaT[fc.col[d] * a_stride + a_idx];
 #pragma unroll
-          for (int v = 0; v < V; v++) {
-            const double z = (xa - xb[v * DGP_XS + fc.col[d]]) * fc.inv_ls[d];
-            d2[v] = fma(z, z, d2[v]);
+        for (int d = 0; d < DGP_MAX_FDIMS; d++) {
+          if (d < sh_nd<S>(tc, f)) {
+            const double xa = xaT[fc.col[d] * a_stride + a_idx];
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+              const double z = (xa - xb[v * DGP_XS + fc.col[d]]) * fc.inv_ls[d];
+              d2[v] = fma(z, z, d2[v]);
+            }
           }
         }
-        if (fc.kind == DGP_RBF) {
+        if (kind == DGP_RBF) {
 #pragma unroll
           for (int v = 0; v < V; v++) EX[v] = fma(0.5, d2[v], EX[v]);
-        } else if (fc.kind == DGP_MATERN32) {
+        } else if (kind == DGP_MATERN32) {
 #pragma unroll
           for (int v = 0; v < V; v++) {
             const double a = 1.7320508075688772 * fast_sqrt_nonneg(d2[v]);
@@ -409,7 +487,7 @@ __device__ __forceinline__ void term_grad_accum_v(const TermC& tc, const double*
     F[v] = E[v];
 #pragma unroll
     for (int f = 0; f < DGP_MAX_FACTORS; f++)
-      if (f < tc.nf && tc.f[f].kind != DGP_PERIODIC) F[v] *= poly[f][v];
+      if (f < sh_nf<S>(tc) && sh_kind<S>(tc, f) != DGP_PERIODIC) F[v] *= poly[f][v];
   }
 #pragma unroll
   for (int v = 0; v < V; v++) {
@@ -419,18 +497,19 @@ __device__ __forceinline__ void term_grad_accum_v(const TermC& tc, const double*
   // pass 2: per-parameter derivative factors (the factor's own exponential is already inside E)
 #pragma unroll
   for (int f = 0; f < DGP_MAX_FACTORS; f++) {
-    if (f < tc.nf) {
+    if (f < sh_nf<S>(tc)) {
       const FactorC& fc = tc.f[f];
+      const int kind = sh_kind<S>(tc, f);
       double wo[V];  // w * scale * gate * E * prod_{g != f} poly_g
 #pragma unroll
       for (int v = 0; v < V; v++) {
         double o = w[v] * tc.scale * G[v] * E[v];
 #pragma unroll
         for (int g = 0; g < DGP_MAX_FACTORS; g++)
-          if (g != f && g < tc.nf && tc.f[g].kind != DGP_PERIODIC) o *= poly[g][v];
+          if (g != f && g < sh_nf<S>(tc) && sh_kind<S>(tc, g) != DGP_PERIODIC) o *= poly[g][v];
         wo[v] = o;
       }
-      if (fc.kind == DGP_PERIODIC) {
+      if (kind == DGP_PERIODIC) {
         const double cl = 2.0 * fc.inv_lam * fc.inv_lam;                        // d/d lam   : val * 2 s^2 / lam^2
         const double cp = 4.0 * 3.14159265358979323846 * fc.inv_lam * fc.inv_p;  // d/d period: val * (4/lam) s c u / p
 #pragma unroll
@@ -442,10 +521,10 @@ __device__ __forceinline__ void term_grad_accum_v(const TermC& tc, const double*
         double cm[V];  // d factor / d ls_d = cm * z_d^2 / ls_d  (exponential excluded)
 #pragma unroll
         for (int v = 0; v < V; v++)
-          cm[v] = wo[v] * (fc.kind == DGP_RBF ? 1.0 : (fc.kind == DGP_MATERN32 ? 3.0 : (5.0 / 3.0) * (1.0 + aux[f][v])));
+          cm[v] = wo[v] * (kind == DGP_RBF ? 1.0 : (kind == DGP_MATERN32 ? 3.0 : (5.0 / 3.0) * (1.0 + aux[f][v])));
 #pragma unroll
         for (int d = 0; d < DGP_MAX_FDIMS; d++) {
-          if (d < fc.ndims) {
+          if (d < sh_nd<S>(tc, f)) {
             const double xa = xaT[fc.col[d] * a_stride + a_idx];
             double sd = 0.0;
 #pragma unroll
@@ -459,6 +538,12 @@ __device__ __forceinline__ void term_grad_accum_v(const TermC& tc, const double*
       }
     }
   }
+}
+
+template <int V>
+__device__ __forceinline__ void term_grad_accum_v(const TermC& tc, const double* __restrict__ xaT, int a_stride, int a_idx,
+                                                  const double* __restrict__ xb, const double (&w)[V], double (&acc)[NSLOT]) {
+  DGP_SHAPE_SWITCH(tc.shape, (term_grad_accum_s<V, S>(tc, xaT, a_stride, a_idx, xb, w, acc)))
 }
 
 // theta index of a slot of term tc (-1: unused)
