@@ -136,7 +136,7 @@ def main():
     ap.add_argument("--n", type=int, default=N_TRAIN, help="development only; the judged workload is n=16384")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
     ap.add_argument("--no-extra", action="store_true", help="skip the predictive-points/s and sites/s legs (development)")
-    ap.add_argument("--sites-per-gpu", type=int, default=8, help="sites of the NWQN-style batch fitted per GPU in the sites/s leg")
+    ap.add_argument("--sites-per-gpu", type=int, default=16, help="sites of the NWQN-style batch fitted per GPU in the sites/s leg")
     ap.add_argument("--site-iterations", type=int, default=100)
     ap.add_argument("--predict-m", type=int, default=32768, help="grid points of the predictive-points/s leg")
     args = ap.parse_args()

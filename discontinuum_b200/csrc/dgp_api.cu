@@ -48,6 +48,20 @@ PFN_encodeTiled get_encode() {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// ---- green contexts (driver API, resolved at run time like the tensor-map encoder: libdgp does not link libcuda)
+template <typename F>
+F driver_fn(const char* name) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+  return (F)p;
+}
+struct SmPartitions {
+  int parts = 0, sms = 0;
+  std::vector<CUgreenCtx> ctx;
+};
+SmPartitions g_partitions[64];
+
 }  // namespace
 
 struct dgp_handle_s {
@@ -259,6 +273,76 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
   cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM);
   cudaFuncSetAttribute(k_potf2_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM);
   *out = h;
+  return 0;
+}
+
+int dgp_partition_device(int device, int parts, int* sms_out) {
+  if (device < 0 || device >= 64 || parts < 1) DGP_FAIL((dgp_handle) nullptr, -1, "dgp_partition_device: bad arguments");
+  SmPartitions& P = g_partitions[device];
+  if (P.parts > 0) { if (sms_out) *sms_out = P.sms; return P.parts; }  // one split per device and process
+  if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess)
+    DGP_FAIL((dgp_handle) nullptr, -2, "dgp_partition_device: no CUDA device %d", device);
+  typedef CUresult (*PFN_devres)(CUdevice, CUdevResource*, CUdevResourceType);
+  typedef CUresult (*PFN_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+  typedef CUresult (*PFN_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+  typedef CUresult (*PFN_gcreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+  typedef CUresult (*PFN_devget)(CUdevice*, int);
+  PFN_devres f_res = driver_fn<PFN_devres>("cuDeviceGetDevResource");
+  PFN_split f_split = driver_fn<PFN_split>("cuDevSmResourceSplitByCount");
+  PFN_desc f_desc = driver_fn<PFN_desc>("cuDevResourceGenerateDesc");
+  PFN_gcreate f_create = driver_fn<PFN_gcreate>("cuGreenCtxCreate");
+  PFN_devget f_dev = driver_fn<PFN_devget>("cuDeviceGet");
+  if (!f_res || !f_split || !f_desc || !f_create || !f_dev)
+    DGP_FAIL((dgp_handle) nullptr, -3, "dgp_partition_device: green-context entry points not available in this driver");
+  CUdevice dev;
+  CUresult r = f_dev(&dev, device);
+  CUdevResource all;
+  if (r == CUDA_SUCCESS) r = f_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM);
+  if (r != CUDA_SUCCESS) DGP_FAIL((dgp_handle) nullptr, -3, "cuDeviceGetDevResource failed (%d)", (int)r);
+  const int total = (int)all.sm.smCount;
+  int per = total / parts / 8 * 8;  // partitions are multiples of 8 SMs on sm_90+
+  if (per < 8) DGP_FAIL((dgp_handle) nullptr, -1, "dgp_partition_device: %d partitions of >= 8 SMs do not fit %d SMs", parts, total);
+  std::vector<CUdevResource> groups((size_t)parts);
+  unsigned int nb = (unsigned int)parts;
+  CUdevResource rest;
+  r = f_split(groups.data(), &nb, &all, &rest, 0, (unsigned int)per);
+  if (r != CUDA_SUCCESS || nb < 1) DGP_FAIL((dgp_handle) nullptr, -3, "cuDevSmResourceSplitByCount failed (%d)", (int)r);
+  P.ctx.clear();
+  for (unsigned int i = 0; i < nb; i++) {
+    CUdevResourceDesc desc;
+    CUgreenCtx g;
+    r = f_desc(&desc, &groups[i], 1);
+    if (r == CUDA_SUCCESS) r = f_create(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM);
+    if (r != CUDA_SUCCESS) DGP_FAIL((dgp_handle) nullptr, -3, "cuGreenCtxCreate failed for partition %u (%d)", i, (int)r);
+    P.ctx.push_back(g);
+  }
+  P.parts = (int)P.ctx.size();
+  P.sms = (int)groups[0].sm.smCount;
+  if (sms_out) *sms_out = P.sms;
+  return P.parts;
+}
+
+int dgp_create_partitioned(dgp_handle* out, int device, int max_n, int max_m, int part) {
+  if (device < 0 || device >= 64) DGP_FAIL((dgp_handle) nullptr, -1, "dgp_create_partitioned: bad device");
+  SmPartitions& P = g_partitions[device];
+  if (part < 0 || part >= P.parts) DGP_FAIL((dgp_handle) nullptr, -1, "dgp_create_partitioned: partition %d of %d (call dgp_partition_device first)", part, P.parts);
+  typedef CUresult (*PFN_gstream)(CUstream*, CUgreenCtx, unsigned int, int);
+  PFN_gstream f_stream = driver_fn<PFN_gstream>("cuGreenCtxStreamCreate");
+  if (!f_stream) DGP_FAIL((dgp_handle) nullptr, -3, "cuGreenCtxStreamCreate not available");
+  if (cudaSetDevice(device) != cudaSuccess) DGP_FAIL((dgp_handle) nullptr, -2, "no CUDA device %d", device);
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  CUstream st = nullptr, st_hi = nullptr;
+  CUresult r = f_stream(&st, P.ctx[(size_t)part], CU_STREAM_NON_BLOCKING, lo);
+  if (r == CUDA_SUCCESS) r = f_stream(&st_hi, P.ctx[(size_t)part], CU_STREAM_NON_BLOCKING, hi);
+  if (r != CUDA_SUCCESS) DGP_FAIL((dgp_handle) nullptr, -3, "cuGreenCtxStreamCreate failed (%d)", (int)r);
+  int rc = dgp_create(out, device, max_n, max_m, (void*)st);
+  if (rc != 0) { cudaStreamDestroy((cudaStream_t)st); cudaStreamDestroy((cudaStream_t)st_hi); return rc; }
+  dgp_handle h = *out;
+  cudaStreamDestroy(h->stream_hi);          // the look-ahead stream must live in the partition as well
+  h->stream_hi = (cudaStream_t)st_hi;
+  h->own_stream = true;                     // both streams are the handle's to destroy
+  h->sms = P.sms;
   return 0;
 }
 
@@ -731,6 +815,15 @@ int dgp_nlml_grad(dgp_handle h, const double* theta, double jitter, double* nlml
 
 int dgp_nlml_grad_launch(dgp_handle h, const double* theta, double jitter) { return evaluate_launch(h, theta, jitter, 1); }
 int dgp_nlml_grad_wait(dgp_handle h, double* nlml_out, double* grad_out) { return evaluate_wait(h, nlml_out, grad_out); }
+int dgp_nlml_grad_ready(dgp_handle h) {
+  if (!h) return -1;
+  if (!h->pending) DGP_FAIL(h, -1, "no evaluation in flight");
+  CK(h, cudaSetDevice(h->device));
+  const cudaError_t e = cudaStreamQuery(h->stream);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) return 0;
+  DGP_FAIL(h, -2, "cudaStreamQuery failed: %s", cudaGetErrorString(e));
+}
 
 int dgp_factorize(dgp_handle h, const double* theta, double jitter, double* nlml_out) {
   int rc = evaluate_launch(h, theta, jitter, 2);

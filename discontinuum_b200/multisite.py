@@ -8,6 +8,7 @@ panel steps of one site overlap the trailing updates of the others.  The only co
 """
 from __future__ import annotations
 
+import time
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -94,7 +95,8 @@ def _finish_step(s: _SiteState):
         s.sched.step(s.history[-1])
 
 
-def _open_site(idx, tup, device, lr, scheduler, patience, pool: Optional[List[capi.Engine]] = None) -> _SiteState:
+def _open_site(idx, tup, device, lr, scheduler, patience, pool: Optional[List[capi.Engine]] = None,
+               free_parts: Optional[List[int]] = None) -> _SiteState:
     X, y = np.ascontiguousarray(tup[0], dtype=np.float64), np.ascontiguousarray(tup[1], dtype=np.float64)
     noise = np.ascontiguousarray(tup[2], dtype=np.float64) if len(tup) > 2 else np.full(y.shape[0], LOADEST_FIXED_NOISE)
     module = GPModule(loadest_spec(X.shape[1]))
@@ -104,7 +106,16 @@ def _open_site(idx, tup, device, lr, scheduler, patience, pool: Optional[List[ca
         if k is not None:
             eng = pool.pop(k)
     if eng is None:
-        eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device)
+        if free_parts is not None:  # one engine per SM partition: take a free partition, or rebuild a pooled engine's
+            if not free_parts:
+                old = pool.pop(0)
+                free_parts.append(old.partition)
+                old.close()
+            part = free_parts.pop(0)
+            eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device, partition=part)
+            eng.partition = part
+        else:
+            eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device)
     eng.set_train(module.spec.to_c(), X, y, noise)
     opt = torch.optim.Adam(module.raw_list(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
     sch = None
@@ -141,28 +152,44 @@ def _close_site(s: _SiteState, predict, pool: Optional[List[capi.Engine]] = None
 
 def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int = 0, concurrency: int = 4,
                     predict: Optional[Dict[int, np.ndarray]] = None, lr: float = 0.05, scheduler: bool = True,
-                    patience: int = 60) -> Dict[int, dict]:
+                    patience: int = 60, partitions: Optional[int] = None) -> Dict[int, dict]:
     """Fit the loadest-gp model on every site of this rank.  sites: {index: (X, y[, noise])} in model space.
     Returns {index: {"theta", "objective", "history", "mu", "var"}}.
 
     `concurrency` sites are in flight at any time, each a pipeline of its own: as soon as a site's evaluation is
     back the host does its optimiser step and enqueues its next evaluation, while the GPU works on the others; a
-    finished site is predicted, closed and replaced by the next largest one (no group barrier)."""
+    finished site is predicted, closed and replaced by the next largest one (no group barrier).  Sites are served in
+    completion order (`dgp_nlml_grad_ready`), not in a fixed round: their costs differ by up to (n_max / n_min)^3, and
+    a round would make every site advance at the pace of the largest one in flight.
+
+    partitions: split the GPU's SMs into that many disjoint partitions (`capi.partition_device`) and run one site per
+    partition (concurrency = partitions).  Sites sharing all SMs slow each other down 3-4x (the short dependent kernels
+    of one site's panel chain wait behind the long tiles of another's inverse); on its own slice a site of this size is
+    work-bound and nobody waits."""
     results: Dict[int, dict] = {}
     queue = sorted(sites, key=lambda i: -sites[i][0].shape[0])  # largest first: later sites fit the pooled workspaces
     active: List[_SiteState] = []
     pool: List[capi.Engine] = []
+    free_parts: Optional[List[int]] = None
+    if partitions and partitions > 1:
+        nparts, _ = capi.partition_device(device, partitions)
+        concurrency = nparts
+        free_parts = list(range(nparts))
 
     def refill():
         while queue and len(active) < max(1, concurrency):
-            s = _open_site(queue[0], sites[queue.pop(0)], device, lr, scheduler, patience, pool)
+            s = _open_site(queue[0], sites[queue.pop(0)], device, lr, scheduler, patience, pool, free_parts)
             if iterations > 0:
                 _launch_step(s)
             active.append(s)
 
     refill()
     while active:
+        served = False
         for s in list(active):
+            if iterations > 0 and not s.engine.nlml_grad_ready():
+                continue
+            served = True
             if iterations > 0:
                 _finish_step(s)
             if s.failed is None and len(s.history) < iterations:
@@ -171,6 +198,8 @@ def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int 
             active.remove(s)
             results[s.idx] = _close_site(s, predict, pool)
             refill()
+        if not served:
+            time.sleep(0)  # nothing finished yet: yield, then poll again
     for e in pool:
         e.close()
     return results

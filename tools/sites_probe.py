@@ -17,12 +17,34 @@ for s, n in enumerate(ns):
     sites[s] = (X, y, noise)
     grids[s] = synthetic.daily_grid(X, m)
 t0 = time.perf_counter()
-res = multisite.fit_sites_local(sites, iterations=iters, device=0, concurrency=conc, predict=grids)
+parts = int(os.environ.get("PARTS", "0")) or None
+res = multisite.fit_sites_local(sites, iterations=iters, device=0, concurrency=conc, predict=grids, partitions=parts)
 dt = time.perf_counter() - t0
 flop = sum(float(n) ** 3 * iters for n in ns)
 print(f"sites={S} iters={iters} conc={conc} m={m} n=[{ns.min()}..{ns.max()}] wall={dt:.2f}s sites/s={S/dt:.3f} "
       f"fit TF/s={flop/dt/1e12:.2f} failed={[k for k, r in res.items() if r['failed']]}", flush=True)
 print("final objectives:", [round(res[k]["objective"], 5) for k in sorted(res)][:8])
+
+if os.environ.get("PHASES"):
+    # per-phase device time of every evaluation under contention (events on each site's stream)
+    acc = {}
+    o0 = multisite._open_site
+    def o1(*a, **k):
+        st = o0(*a, **k); st.engine.set_timing(True); return st
+    multisite._open_site = o1
+    f0 = multisite._finish_step
+    def f1(st):
+        f0(st)
+        ms = st.engine.last_timing()
+        a = acc.setdefault(st.X.shape[0], [0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += ms[0]; a[2] += ms[1]; a[3] += ms[2]
+    multisite._finish_step = f1
+    t0 = time.perf_counter()
+    multisite.fit_sites_local(sites, iterations=iters, device=0, concurrency=conc, predict=grids, partitions=parts)
+    print("phases run total", round(time.perf_counter() - t0, 2))
+    for n in sorted(acc):
+        c, a, b, d = acc[n]
+        print(f"  n={n}: per evaluation potrf {a/c:.2f} ms  trtri {b/c:.2f} ms  lauum+grad {d/c:.2f} ms  sum {(a+b+d)/c:.2f}  ({n**3/((a+b+d)/c)/1e9:.1f} TF if alone)")
 
 if os.environ.get("BREAKDOWN"):
     import collections
