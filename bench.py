@@ -307,8 +307,8 @@ def main():
         dev_ms = sum(phase)
         achieved = flop / (dev_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": 77.5e9 if n == N_TRAIN else None,
-                "traffic_note": "dram__bytes_read+write summed over the 439 launches of one evaluation (ncu, profiles/dram_n16384_r01c_summary.txt)",
+                "traffic": 80.8e9 if n == N_TRAIN else None,
+                "traffic_note": "dram__bytes_read+write summed over the 471 launches of one evaluation (ncu, profiles/dram_n16384_r01d_summary.txt)",
                 "kernel": "dgp::k_gemm (FP64 DMMA tile engine): every launch of one evaluation",
                 "algorithmic_flop_per_eval": flop, "peak_source": "of measured: " + peak_src,
                 "phases_ms": {"potrf": phase[0], "trtri": phase[1], "lauum_grad": phase[2], "rest": phase[3]},

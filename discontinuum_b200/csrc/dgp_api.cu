@@ -61,6 +61,8 @@ struct SmPartitions {
   std::vector<CUgreenCtx> ctx;
 };
 SmPartitions g_partitions[64];
+struct ChainSplit { bool made = false; CUgreenCtx chain = nullptr, work = nullptr; int chain_sms = 0, work_sms = 0; };
+ChainSplit g_chain_split[64];
 
 }  // namespace
 
@@ -68,6 +70,10 @@ struct dgp_handle_s {
   int device = 0;
   cudaStream_t stream = nullptr;     // trailing updates and everything outside the factorisation
   cudaStream_t stream_hi = nullptr;  // look-ahead: diagonal block + panel solve of the next block column (high priority)
+  cudaStream_t stream_lo = nullptr;  // inverse, LAUUM and gradient contraction (lowest priority, own streams only): grids are
+                                     // served in priority, then launch order, so that the trailing updates of one site's
+                                     // factorisation do not wait for the dispatch of another site's multi-millisecond grids
+  cudaEvent_t ev_lo[2] = {nullptr, nullptr};
   bool own_stream = false;
   std::vector<cudaEvent_t> evs;      // look-ahead dependencies (no timing)
   bool lookahead = true;
@@ -230,11 +236,22 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
   h->max_n = max_n;
   h->max_pad = round_up(max_n, 128);
   h->max_m = round_up(max_m > 0 ? max_m : 2048, 128);
-  if (stream) { h->stream = (cudaStream_t)stream; }
-  else { cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking); h->own_stream = true; }
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (stream) { h->stream = (cudaStream_t)stream; }
+    else {
+      const char* p3 = getenv("DGP_PRIO3");
+      if (p3 == nullptr || atoi(p3) != 0) {
+        cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, (lo + hi) / 2);
+        cudaStreamCreateWithPriority(&h->stream_lo, cudaStreamNonBlocking, lo);
+        cudaEventCreateWithFlags(&h->ev_lo[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_lo[1], cudaEventDisableTiming);
+      } else {
+        cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+      }
+      h->own_stream = true;
+    }
     cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, hi);
     const char* la = getenv("DGP_LOOKAHEAD");
     if (la) h->lookahead = atoi(la) != 0;
@@ -322,6 +339,68 @@ int dgp_partition_device(int device, int parts, int* sms_out) {
   return P.parts;
 }
 
+int dgp_chain_split_device(int device, int chain_sms, int* work_sms_out) {
+  if (device < 0 || device >= 64 || chain_sms < 8) DGP_FAIL((dgp_handle) nullptr, -1, "dgp_chain_split_device: bad arguments");
+  ChainSplit& S = g_chain_split[device];
+  if (S.made) { if (work_sms_out) *work_sms_out = S.work_sms; return S.chain_sms; }
+  if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess)
+    DGP_FAIL((dgp_handle) nullptr, -2, "dgp_chain_split_device: no CUDA device %d", device);
+  typedef CUresult (*PFN_devres)(CUdevice, CUdevResource*, CUdevResourceType);
+  typedef CUresult (*PFN_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+  typedef CUresult (*PFN_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+  typedef CUresult (*PFN_gcreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+  typedef CUresult (*PFN_devget)(CUdevice*, int);
+  PFN_devres f_res = driver_fn<PFN_devres>("cuDeviceGetDevResource");
+  PFN_split f_split = driver_fn<PFN_split>("cuDevSmResourceSplitByCount");
+  PFN_desc f_desc = driver_fn<PFN_desc>("cuDevResourceGenerateDesc");
+  PFN_gcreate f_create = driver_fn<PFN_gcreate>("cuGreenCtxCreate");
+  PFN_devget f_dev = driver_fn<PFN_devget>("cuDeviceGet");
+  if (!f_res || !f_split || !f_desc || !f_create || !f_dev)
+    DGP_FAIL((dgp_handle) nullptr, -3, "dgp_chain_split_device: green-context entry points not available in this driver");
+  CUdevice dev;
+  CUresult r = f_dev(&dev, device);
+  CUdevResource all, first, rest;
+  if (r == CUDA_SUCCESS) r = f_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM);
+  unsigned int nb = 1;
+  if (r == CUDA_SUCCESS) r = f_split(&first, &nb, &all, &rest, 0, (unsigned int)(chain_sms / 8 * 8));
+  if (r != CUDA_SUCCESS || nb != 1 || rest.sm.smCount < 8) DGP_FAIL((dgp_handle) nullptr, -3, "SM split failed (%d)", (int)r);
+  CUdevResourceDesc d0, d1;
+  r = f_desc(&d0, &first, 1);
+  if (r == CUDA_SUCCESS) r = f_desc(&d1, &rest, 1);
+  if (r == CUDA_SUCCESS) r = f_create(&S.chain, d0, dev, CU_GREEN_CTX_DEFAULT_STREAM);
+  if (r == CUDA_SUCCESS) r = f_create(&S.work, d1, dev, CU_GREEN_CTX_DEFAULT_STREAM);
+  if (r != CUDA_SUCCESS) DGP_FAIL((dgp_handle) nullptr, -3, "cuGreenCtxCreate failed (%d)", (int)r);
+  S.made = true;
+  S.chain_sms = (int)first.sm.smCount;
+  S.work_sms = (int)rest.sm.smCount;
+  if (work_sms_out) *work_sms_out = S.work_sms;
+  return S.chain_sms;
+}
+
+int dgp_create_chain_split(dgp_handle* out, int device, int max_n, int max_m) {
+  if (device < 0 || device >= 64 || !g_chain_split[device].made)
+    DGP_FAIL((dgp_handle) nullptr, -1, "dgp_create_chain_split: call dgp_chain_split_device first");
+  ChainSplit& S = g_chain_split[device];
+  typedef CUresult (*PFN_gstream)(CUstream*, CUgreenCtx, unsigned int, int);
+  PFN_gstream f_stream = driver_fn<PFN_gstream>("cuGreenCtxStreamCreate");
+  if (!f_stream) DGP_FAIL((dgp_handle) nullptr, -3, "cuGreenCtxStreamCreate not available");
+  if (cudaSetDevice(device) != cudaSuccess) DGP_FAIL((dgp_handle) nullptr, -2, "no CUDA device %d", device);
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  CUstream st = nullptr, st_hi = nullptr;
+  CUresult r = f_stream(&st, S.work, CU_STREAM_NON_BLOCKING, lo);
+  if (r == CUDA_SUCCESS) r = f_stream(&st_hi, S.chain, CU_STREAM_NON_BLOCKING, hi);
+  if (r != CUDA_SUCCESS) DGP_FAIL((dgp_handle) nullptr, -3, "cuGreenCtxStreamCreate failed (%d)", (int)r);
+  int rc = dgp_create(out, device, max_n, max_m, (void*)st);
+  if (rc != 0) { cudaStreamDestroy((cudaStream_t)st); cudaStreamDestroy((cudaStream_t)st_hi); return rc; }
+  dgp_handle h = *out;
+  cudaStreamDestroy(h->stream_hi);
+  h->stream_hi = (cudaStream_t)st_hi;
+  h->own_stream = true;
+  h->sms = S.chain_sms;   // the half-tile thresholds of the chain launches refer to the chain partition
+  return 0;
+}
+
 int dgp_create_partitioned(dgp_handle* out, int device, int max_n, int max_m, int part) {
   if (device < 0 || device >= 64) DGP_FAIL((dgp_handle) nullptr, -1, "dgp_create_partitioned: bad device");
   SmPartitions& P = g_partitions[device];
@@ -351,6 +430,8 @@ int dgp_destroy(dgp_handle h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stream_hi) { cudaStreamSynchronize(h->stream_hi); cudaStreamDestroy(h->stream_hi); }
+  if (h->stream_lo) { cudaStreamSynchronize(h->stream_lo); cudaStreamDestroy(h->stream_lo); }
+  for (int i = 0; i < 2; i++) if (h->ev_lo[i]) cudaEventDestroy(h->ev_lo[i]);
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   for (auto& gs : h->graphs) if (gs.exec) cudaGraphExecDestroy(gs.exec);
   double* bufs[] = {h->bufA, h->bufL, h->bufU, h->DI, h->X, h->y, h->noise, h->Xw, h->r, h->z, h->alpha, h->theta,
@@ -719,12 +800,24 @@ static int evaluate_enqueue(dgp_handle h, double jitter, int level) {
   if ((rc = run_potrf(h, jitter, level == 0))) return rc;  // level >= 1: z = U'r after the inverse instead
   if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
   if (level >= 1) {
-    if ((rc = run_trtri(h, level == 2))) return rc;
-    if (h->timing) CK(h, cudaEventRecord(h->ev[2], h->stream));
-    if (level == 1) {
-      if ((rc = run_lauum_grad(h))) return rc;
+    // the O(n^3) phases after the factorisation go to the low-priority stream (when the handle has one)
+    cudaStream_t main_stream = h->stream;
+    const bool lo = h->stream_lo != nullptr && !h->use_graphs;
+    if (lo) {
+      CK(h, cudaEventRecord(h->ev_lo[0], main_stream));
+      CK(h, cudaStreamWaitEvent(h->stream_lo, h->ev_lo[0], 0));
+      h->stream = h->stream_lo;
     }
-    if (h->timing) CK(h, cudaEventRecord(h->ev[3], h->stream));
+    rc = run_trtri(h, level == 2);
+    if (!rc && h->timing) { cudaEventRecord(h->ev[2], h->stream); }
+    if (!rc && level == 1) rc = run_lauum_grad(h);
+    if (!rc && h->timing) { cudaEventRecord(h->ev[3], h->stream); }
+    if (lo) {
+      cudaEventRecord(h->ev_lo[1], h->stream_lo);
+      h->stream = main_stream;
+      CK(h, cudaStreamWaitEvent(main_stream, h->ev_lo[1], 0));
+    }
+    if (rc) return rc;
   }
   if ((rc = run_finish(h, level == 1))) return rc;
   return 0;

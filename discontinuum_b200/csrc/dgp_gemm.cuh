@@ -25,6 +25,10 @@ constexpr int B_BYTES = BN * BK * 8;   //  8 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_THREADS = 160;      // 4 consumer warps + 1 producer warp
 constexpr int WS = BN + 1;             // padded row stride of the W tile in the grad epilogue
+#ifndef DGP_COV_V
+#define DGP_COV_V 8
+#endif
+constexpr int COV_V = DGP_COV_V;       // covariance entries a thread evaluates side by side when it generates a tile
 
 enum { M_TRSM = 0, M_TRAIL = 1, M_TRAIL_COL = 2, M_INV_M = 3, M_LAUUM = 4, M_PREDVAR = 5, M_GENERIC = 6, M_INV_U = 7, M_ZL = 8 };
 enum { INIT_ZERO = 0, INIT_LOAD = 1, INIT_COV = 2 };
@@ -273,11 +277,11 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
       const int gr = job.crow + t;
       const double dn = (gr < g.n) ? (g.latent ? g.jitter : g.noise[gr] + cc->extra_noise) : 0.0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 8) {
-        double val[8];
-        cov_vals<8>(cc, xaT, BM, t, xb + c0 * DGP_XS, val);
+      for (int c0 = 0; c0 < BN; c0 += COV_V) {
+        double val[COV_V];
+        cov_vals<COV_V>(cc, xaT, BM, t, xb + c0 * DGP_XS, val);
 #pragma unroll
-        for (int v = 0; v < 8; v++) {
+        for (int v = 0; v < COV_V; v++) {
           const int gc = job.ccol + c0 + v;
           double x = val[v];
           if (gr < g.n && gc < g.n) { if (gr == gc) x += dn; }
