@@ -64,8 +64,6 @@ _SIGNATURES = [
     ("dgp_nlml_grad_ready", C.c_int, [_P]),
     ("dgp_partition_device", C.c_int, [C.c_int, C.c_int, _P]),
     ("dgp_create_partitioned", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
-    ("dgp_chain_split_device", C.c_int, [C.c_int, C.c_int, _P]),
-    ("dgp_create_chain_split", C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     ("dgp_factorize", C.c_int, [_P, _P, C.c_double, _P]),
     ("dgp_predict", C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     ("dgp_mean_functional_grad", C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
@@ -155,29 +153,15 @@ def partition_device(device: int, parts: int) -> Tuple[int, int]:
     return rc, sms.value
 
 
-def chain_split_device(device: int, chain_sms: int) -> Tuple[int, int]:
-    """Set `chain_sms` SMs of `device` aside for the panel chains of every engine created with partition="chain".
-    Returns (chain SMs, work SMs)."""
-    lib = load_library()
-    work = C.c_int(0)
-    rc = lib.dgp_chain_split_device(int(device), int(chain_sms), C.byref(work))
-    if rc < 8:
-        msg = lib.dgp_last_error(None)
-        raise DgpError(f"dgp_chain_split_device failed ({rc}): {msg.decode() if msg else ''}")
-    return rc, work.value
-
-
 class Engine:
     """One libdgp handle: the resident training set of one site and its factorisation workspace."""
 
-    def __init__(self, max_n: int, max_m: int = 2048, device: int = 0, stream: int = 0, partition=None):
+    def __init__(self, max_n: int, max_m: int = 2048, device: int = 0, stream: int = 0, partition: Optional[int] = None):
         """partition: index of an SM partition made by `partition_device` (the engine's kernels then only run on
         that slice of the GPU: concurrent sites do not queue behind each other's long tiles)."""
         self.lib = load_library()
         self._h = _P()
-        if partition == "chain":
-            rc = self.lib.dgp_create_chain_split(C.byref(self._h), int(device), int(max_n), int(max_m))
-        elif partition is not None:
+        if partition is not None:
             rc = self.lib.dgp_create_partitioned(C.byref(self._h), int(device), int(max_n), int(max_m), int(partition))
         else:
             rc = self.lib.dgp_create(C.byref(self._h), int(device), int(max_n), int(max_m), _P(stream) if stream else None)

@@ -61,8 +61,6 @@ struct SmPartitions {
   std::vector<CUgreenCtx> ctx;
 };
 SmPartitions g_partitions[64];
-struct ChainSplit { bool made = false; CUgreenCtx chain = nullptr, work = nullptr; int chain_sms = 0, work_sms = 0; };
-ChainSplit g_chain_split[64];
 
 }  // namespace
 
@@ -337,68 +335,6 @@ int dgp_partition_device(int device, int parts, int* sms_out) {
   P.sms = (int)groups[0].sm.smCount;
   if (sms_out) *sms_out = P.sms;
   return P.parts;
-}
-
-int dgp_chain_split_device(int device, int chain_sms, int* work_sms_out) {
-  if (device < 0 || device >= 64 || chain_sms < 8) DGP_FAIL((dgp_handle) nullptr, -1, "dgp_chain_split_device: bad arguments");
-  ChainSplit& S = g_chain_split[device];
-  if (S.made) { if (work_sms_out) *work_sms_out = S.work_sms; return S.chain_sms; }
-  if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess)
-    DGP_FAIL((dgp_handle) nullptr, -2, "dgp_chain_split_device: no CUDA device %d", device);
-  typedef CUresult (*PFN_devres)(CUdevice, CUdevResource*, CUdevResourceType);
-  typedef CUresult (*PFN_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
-  typedef CUresult (*PFN_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
-  typedef CUresult (*PFN_gcreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
-  typedef CUresult (*PFN_devget)(CUdevice*, int);
-  PFN_devres f_res = driver_fn<PFN_devres>("cuDeviceGetDevResource");
-  PFN_split f_split = driver_fn<PFN_split>("cuDevSmResourceSplitByCount");
-  PFN_desc f_desc = driver_fn<PFN_desc>("cuDevResourceGenerateDesc");
-  PFN_gcreate f_create = driver_fn<PFN_gcreate>("cuGreenCtxCreate");
-  PFN_devget f_dev = driver_fn<PFN_devget>("cuDeviceGet");
-  if (!f_res || !f_split || !f_desc || !f_create || !f_dev)
-    DGP_FAIL((dgp_handle) nullptr, -3, "dgp_chain_split_device: green-context entry points not available in this driver");
-  CUdevice dev;
-  CUresult r = f_dev(&dev, device);
-  CUdevResource all, first, rest;
-  if (r == CUDA_SUCCESS) r = f_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM);
-  unsigned int nb = 1;
-  if (r == CUDA_SUCCESS) r = f_split(&first, &nb, &all, &rest, 0, (unsigned int)(chain_sms / 8 * 8));
-  if (r != CUDA_SUCCESS || nb != 1 || rest.sm.smCount < 8) DGP_FAIL((dgp_handle) nullptr, -3, "SM split failed (%d)", (int)r);
-  CUdevResourceDesc d0, d1;
-  r = f_desc(&d0, &first, 1);
-  if (r == CUDA_SUCCESS) r = f_desc(&d1, &rest, 1);
-  if (r == CUDA_SUCCESS) r = f_create(&S.chain, d0, dev, CU_GREEN_CTX_DEFAULT_STREAM);
-  if (r == CUDA_SUCCESS) r = f_create(&S.work, d1, dev, CU_GREEN_CTX_DEFAULT_STREAM);
-  if (r != CUDA_SUCCESS) DGP_FAIL((dgp_handle) nullptr, -3, "cuGreenCtxCreate failed (%d)", (int)r);
-  S.made = true;
-  S.chain_sms = (int)first.sm.smCount;
-  S.work_sms = (int)rest.sm.smCount;
-  if (work_sms_out) *work_sms_out = S.work_sms;
-  return S.chain_sms;
-}
-
-int dgp_create_chain_split(dgp_handle* out, int device, int max_n, int max_m) {
-  if (device < 0 || device >= 64 || !g_chain_split[device].made)
-    DGP_FAIL((dgp_handle) nullptr, -1, "dgp_create_chain_split: call dgp_chain_split_device first");
-  ChainSplit& S = g_chain_split[device];
-  typedef CUresult (*PFN_gstream)(CUstream*, CUgreenCtx, unsigned int, int);
-  PFN_gstream f_stream = driver_fn<PFN_gstream>("cuGreenCtxStreamCreate");
-  if (!f_stream) DGP_FAIL((dgp_handle) nullptr, -3, "cuGreenCtxStreamCreate not available");
-  if (cudaSetDevice(device) != cudaSuccess) DGP_FAIL((dgp_handle) nullptr, -2, "no CUDA device %d", device);
-  int lo = 0, hi = 0;
-  cudaDeviceGetStreamPriorityRange(&lo, &hi);
-  CUstream st = nullptr, st_hi = nullptr;
-  CUresult r = f_stream(&st, S.work, CU_STREAM_NON_BLOCKING, lo);
-  if (r == CUDA_SUCCESS) r = f_stream(&st_hi, S.chain, CU_STREAM_NON_BLOCKING, hi);
-  if (r != CUDA_SUCCESS) DGP_FAIL((dgp_handle) nullptr, -3, "cuGreenCtxStreamCreate failed (%d)", (int)r);
-  int rc = dgp_create(out, device, max_n, max_m, (void*)st);
-  if (rc != 0) { cudaStreamDestroy((cudaStream_t)st); cudaStreamDestroy((cudaStream_t)st_hi); return rc; }
-  dgp_handle h = *out;
-  cudaStreamDestroy(h->stream_hi);
-  h->stream_hi = (cudaStream_t)st_hi;
-  h->own_stream = true;
-  h->sms = S.chain_sms;   // the half-tile thresholds of the chain launches refer to the chain partition
-  return 0;
 }
 
 int dgp_create_partitioned(dgp_handle* out, int device, int max_n, int max_m, int part) {

@@ -95,9 +95,6 @@ def _finish_step(s: _SiteState):
         s.sched.step(s.history[-1])
 
 
-_ENGINE_PARTITION = None  # "chain" after chain_split_device (see fit_sites_local, chain_sms)
-
-
 def _open_site(idx, tup, device, lr, scheduler, patience, pool: Optional[List[capi.Engine]] = None,
                free_parts: Optional[List[int]] = None) -> _SiteState:
     X, y = np.ascontiguousarray(tup[0], dtype=np.float64), np.ascontiguousarray(tup[1], dtype=np.float64)
@@ -118,7 +115,7 @@ def _open_site(idx, tup, device, lr, scheduler, patience, pool: Optional[List[ca
             eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device, partition=part)
             eng.partition = part
         else:
-            eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device, partition=_ENGINE_PARTITION)
+            eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device)
     eng.set_train(module.spec.to_c(), X, y, noise)
     opt = torch.optim.Adam(module.raw_list(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
     sch = None
@@ -155,7 +152,7 @@ def _close_site(s: _SiteState, predict, pool: Optional[List[capi.Engine]] = None
 
 def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int = 0, concurrency: int = 4,
                     predict: Optional[Dict[int, np.ndarray]] = None, lr: float = 0.05, scheduler: bool = True,
-                    patience: int = 60, partitions: Optional[int] = None, chain_sms: Optional[int] = None) -> Dict[int, dict]:
+                    patience: int = 60, partitions: Optional[int] = None) -> Dict[int, dict]:
     """Fit the loadest-gp model on every site of this rank.  sites: {index: (X, y[, noise])} in model space.
     Returns {index: {"theta", "objective", "history", "mu", "var"}}.
 
@@ -174,11 +171,6 @@ def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int 
     active: List[_SiteState] = []
     pool: List[capi.Engine] = []
     free_parts: Optional[List[int]] = None
-    global _ENGINE_PARTITION
-    _ENGINE_PARTITION = None
-    if chain_sms:
-        capi.chain_split_device(device, chain_sms)
-        _ENGINE_PARTITION = "chain"
     if partitions and partitions > 1:
         nparts, _ = capi.partition_device(device, partitions)
         concurrency = nparts

@@ -108,11 +108,7 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream);
  * sms_out (optional): SMs per partition. */
 int dgp_partition_device(int device, int parts, int* sms_out);
 int dgp_create_partitioned(dgp_handle* out, int device, int max_n, int max_m, int part);
-/* A different split for sites that share one GPU: `chain_sms` SMs (multiple of 8) are set aside for the panel chains
- * of ALL engines created with dgp_create_chain_split (their high-priority streams live there), the other SMs run the
- * throughput kernels of all of them.  A chain kernel then never waits for a slot behind another site's long tiles. */
-int dgp_chain_split_device(int device, int chain_sms, int* work_sms_out);
-int dgp_create_chain_split(dgp_handle* out, int device, int max_n, int max_m);
+
 int dgp_destroy(dgp_handle h);
 const char* dgp_last_error(dgp_handle h); /* h may be NULL: error of a failed dgp_create */
 int dgp_abi_version(void);

@@ -1,3 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/gputests_r01d.log 2>&1; tail -3 gpurun_out/gputests_r01d.log
-python bench.py > gpurun_out/bench_r01d.json 2> gpurun_out/bench_r01d.err; tail -c 1500 gpurun_out/bench_r01d.json
-bash tools/prof.sh r01d > gpurun_out/prof_r01d.log 2>&1; tail -12 gpurun_out/prof_r01d.log
+TIERS=3 python tools/sites_probe.py 16 100 3 2>&1 | grep "sites="
+TIERS=2 python tools/sites_probe.py 16 100 2 2>&1 | grep "sites="
+TIERS=3 PHASES=1 python tools/sites_probe.py 16 100 3 2>&1 | grep -v "final obj"
