@@ -586,7 +586,10 @@ k_wgrad(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta,
 // learned-noise slot), wgt = 2 below the diagonal, 1 on it.  Same tiling as the LAUUM launch that wrote Kinv
 // (128 x 64 lower tiles, tile -> (i, c) triangular), one thread per row, 4 columns side by side.  Unlike the fused
 // epilogue this runs with every warp of the SM on FP64 ALU work, so the pipe is not shared with DMMA issue.
-__global__ void __launch_bounds__(128, 4)
+#ifndef DGP_GC_BLOCKS
+#define DGP_GC_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, DGP_GC_BLOCKS)
 k_grad_contract(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta, const double* __restrict__ Xw,
                 const double* __restrict__ alpha, const double* __restrict__ Kinv, long long ld, int n,
                 double* __restrict__ part) {

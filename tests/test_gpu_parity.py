@@ -366,6 +366,61 @@ def test_async_launch_wait_two_sites(cuda_device):
         e.close()
 
 
+def test_ready_poll_then_wait(cuda_device):
+    import time
+    X, y, noise = synthetic.loadest_site(1100, 77)
+    eng = _engine(models.loadest_spec(2), X, y, noise)
+    th = H.loadest_theta1()
+    want = eng.nlml_grad(th)
+    eng.nlml_grad_launch(th)
+    t0 = time.time()
+    while not eng.nlml_grad_ready():
+        assert time.time() - t0 < 30.0
+    got = eng.nlml_grad_wait()
+    assert got[2] == 0 and got[0] == want[0] and np.array_equal(got[1], want[1])
+    with pytest.raises(capi.DgpError):
+        eng.nlml_grad_ready()  # nothing in flight any more
+    eng.close()
+
+
+def test_engine_on_sm_partition_matches_whole_gpu(cuda_device):
+    """An engine whose streams live in a green-context SM partition computes exactly what the default engine does
+    (same kernels, same launch geometry, fewer SMs)."""
+    parts, sms = capi.partition_device(0, 4)
+    assert parts >= 2 and sms >= 8 and sms % 8 == 0
+    X, y, noise = synthetic.loadest_site(1500, 78)
+    th = H.loadest_theta1()
+    ref = _engine(models.loadest_spec(2), X, y, noise)
+    want = ref.nlml_grad(th)
+    ref.close()
+    for part in (0, parts - 1):
+        eng = capi.Engine(max_n=X.shape[0], max_m=256, partition=part)
+        eng.set_train(models.loadest_spec(2).to_c(), X, y, noise)
+        got = eng.nlml_grad(th)
+        assert got[2] == 0
+        assert abs(got[0] - want[0]) <= 1e-12 * abs(want[0])
+        _grad_close(got[1], want[1], 1e-10)
+        eng.close()
+    with pytest.raises(capi.DgpError):
+        capi.Engine(max_n=64, partition=parts)
+
+
+def test_diagonal_block_kernel_edge_sizes(cuda_device):
+    """n around multiples of 32 and 128: ragged last diagonal block (identity padding) through the 32x32 sub-block kernel."""
+    th = H.loadest_theta1()
+    for n in (31, 33, 95, 161, 257, 383):
+        X, y, noise = synthetic.loadest_site(n, 300 + n)
+        eng = _engine(models.loadest_spec(2), X, y, noise)
+        val, grad, info = eng.nlml_grad(th)
+        v, g, a, L, _ = _oracle("loadest", th, X, y, noise)
+        assert info == 0
+        assert abs(val - v) <= RTOL * abs(v)
+        _grad_close(grad, g)
+        Lg = eng.chol()
+        assert np.max(np.abs(np.tril(Lg) - L)) <= 1e-9 * np.max(np.abs(L))
+        eng.close()
+
+
 def _loadest_arrays(n, seed):
     rng = np.random.default_rng(seed)
     days = np.sort(rng.uniform(0, 3650, n))
