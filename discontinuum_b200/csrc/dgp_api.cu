@@ -1,14 +1,18 @@
 // libdgp.so -- C ABI (include/dgp.h) and host-side schedule of the B200 exact-GP engine.
 //
-// Per evaluation the schedule is a chain of launches on one stream:
+// Per evaluation, on three streams of decreasing priority (P: panel chain, T: trailing updates,
+// W: everything after the factorisation):
 //   features/residual -> [block-column 0 covariance panel] ->
-//   for s: potf2(s) -> TRSM(s) -> forward-substitution(s) -> trailing update(s)     (n^3/3, DMMA)
-//   for s: TRI_FINAL(s) -> TRI_UPDATE(s)                                            (U = L^-T, n^3/3, DMMA)
-//   alpha = U z ;  LAUUM fused with the W (.) dK/dtheta contraction                 (n^3/3, DMMA)
+//   two-level right-looking Cholesky, panels of 4 block columns:
+//     P: for s in panel: k_potf2_v2(s) -> panel solve(s) (GEMM against T_ss) -> rank-128 update of the panel's columns
+//        (programmatic dependent launches; 64-row half tiles while a launch is smaller than the GPU)
+//     T: rank-512 update right of the panel: next panel's first column | its other columns | the rest   (n^3/3, DMMA)
+//   W: U = L^-T by recursive doubling (two long-K products and a transpose per level)                   (n^3/3, DMMA)
+//      z = U'r, alpha = U z, LAUUM -> Ky^-1 (lower tiles), gradient contraction W (.) dK/dtheta          (n^3/3, DMMA)
 //   deterministic reductions -> {nlml, info, grad} -> pinned host buffer.
-// Three padded n x n panels: bufA (work matrix, later the partial sums of U, later T = L^-1),
-// bufL (L, lower), bufU (U = L^-T, upper).  The covariance matrix itself is never stored: tiles are
-// generated in registers as accumulator initial values at their first trailing update.
+// Three padded n x n panels: bufA (work matrix, then T = L^-1 and scratch, then Ky^-1), bufL (L, lower), bufU (U = L^-T,
+// upper).  The covariance matrix itself is never stored: tiles are generated in registers as accumulator initial values
+// at their first trailing update.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
