@@ -63,9 +63,11 @@ __device__ __forceinline__ double* p2_blk(double* sm, int i, int j) { return sm 
 // acc (16 x 32: rows g8 and 8 + g8, columns 8 ni + 2q, +1) += sum over nks k4-steps of A[row][4 ks + q] * Bop
 //   NN = false: Bop = Bm[8 ni + g8][4 ks + q]   (A Bm^T);   NN = true: Bop = Bm[4 ks + q][8 ni + g8]   (A Bm)
 //   SCALE: A[row][k] is multiplied by wk[k] on the way in;  NEG: the product is subtracted
-template <bool NN, bool NEG, bool SCALE, int NKS>
+//   LOWB: Bm (NN) is lower triangular, B[k][c] = 0 for k < c: column group ni only sees k >= 8 ni
+//   nmax: column groups ni >= nmax are not needed (upper half of a diagonal tile)
+template <bool NN, bool NEG, bool SCALE, int NKS, bool LOWB = false>
 __device__ __forceinline__ void p2_strip2(double (&acc)[2][4][2], const double* A, const double* Bm,
-                                          const double* wk, int g8, int q) {
+                                          const double* wk, int g8, int q, int nmax = 4) {
   const double* ap = A + g8 * P2_LD + q;
   const double* bp = NN ? Bm + q * P2_LD + g8 : Bm + g8 * P2_LD + q;
 #pragma unroll
@@ -75,9 +77,12 @@ __device__ __forceinline__ void p2_strip2(double (&acc)[2][4][2], const double* 
     if (NEG) { a0 = -a0; a1 = -a1; }
 #pragma unroll
     for (int ni = 0; ni < 4; ni++) {
-      const double b = NN ? bp[4 * ks * P2_LD + 8 * ni] : bp[8 * ni * P2_LD + 4 * ks];
-      dmma(acc[0][ni], a0, b);
-      dmma(acc[1][ni], a1, b);
+      if (LOWB && ks < 2 * ni) continue;
+      if (ni < nmax) {
+        const double b = NN ? bp[4 * ks * P2_LD + 8 * ni] : bp[8 * ni * P2_LD + 4 * ks];
+        dmma(acc[0][ni], a0, b);
+        dmma(acc[1][ni], a1, b);
+      }
     }
   }
 }
@@ -144,7 +149,7 @@ __device__ __forceinline__ void p2_inv_first(double* sm, int R, int hx, int nh, 
     double acc[2][4][2];
     double* C = p2_blk(sm, i, R) + 16 * mh * P2_LD;
     p2_zero(acc);
-    p2_strip2<true, false, true, 8>(acc, C, p2_blk(sm, R, R), sm + P2_OFF_W + 32 * R, g8, q);
+    p2_strip2<true, false, true, 8, true>(acc, C, p2_blk(sm, R, R), sm + P2_OFF_W + 32 * R, g8, q);
     __syncwarp();
     p2_store2(C, acc, g8, q);
   }
@@ -312,7 +317,7 @@ k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double*
       }
     } else if (warp == 4) {
       // scalings of this sub-block, log-determinant, and L_kk = Lu_kk sqrt(D_k) -> global, once the last pivot is out
-      while (p2_ld_prog(prog) < 32 * k + 32) { }
+      while (p2_ld_prog(prog) < 32 * k + 32) __nanosleep(200);  // (shares a scheduler with the pivot warp: poll rarely)
       const double d = dvs[32 * k + lane];
       const double rs = rsqrt(d), sq = d * rs;
       rsv[32 * k + lane] = rs;
@@ -401,7 +406,8 @@ k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double*
             const double2 v = *reinterpret_cast<const double2*>(Cst + (8 * h + g8) * P2_LD + 8 * ni + 2 * q);
             acc[h][ni][0] = v.x; acc[h][ni][1] = v.y;
           }
-        p2_strip2<false, true, true, 8>(acc, p2_blk(sm, i, k) + 16 * mh * P2_LD, p2_blk(sm, j, k), wv + 32 * k, g8, q);
+        p2_strip2<false, true, true, 8>(acc, p2_blk(sm, i, k) + 16 * mh * P2_LD, p2_blk(sm, j, k), wv + 32 * k, g8, q,
+                                        (i == j && mh == 0) ? 2 : 4);  // a diagonal tile is only used below its diagonal
         p2_store2(Cst, acc, g8, q);
       }
       __syncthreads();
