@@ -62,35 +62,36 @@ class _SiteState:
     engine: capi.Engine
     opt: torch.optim.Optimizer
     sched: Optional[torch.optim.lr_scheduler.ReduceLROnPlateau]
-    nat: Optional[torch.Tensor] = None
+    chain: Optional[tuple] = None  # GPModule.host_chain() of the evaluation in flight
     history: List[float] = field(default_factory=list)
     failed: Optional[str] = None
 
 
 def _finish_step(s: _SiteState):
-    """Host side of one optimiser step (discontinuum/engines/gpytorch.py:353-420) once the GPU results are back."""
+    """Host side of one optimiser step (discontinuum/engines/gpytorch.py:353-420) once the GPU results are back: the
+    constraint / prior chain rule in closed form (GPModule.host_chain, no autograd graph), clipping, Adam, scheduler."""
     val, grad, info = s.engine.nlml_grad_wait()
+    nat, dnat, lp, dlp = s.chain
     if info != 0 or not np.isfinite(val):
-        th = s.nat.detach().numpy().astype(np.float64)
         for jit in JITTERS[1:]:
-            val, grad, info = s.engine.nlml_grad(th, jit)
+            val, grad, info = s.engine.nlml_grad(nat, jit)
             if info == 0 and np.isfinite(val):
                 break
         else:
             s.failed = f"not positive definite (info={info})"
             return
     n = s.X.shape[0]
-    g = torch.from_numpy(grad.copy())
-    nll = val + ((s.nat - s.nat.detach()) * g).sum()  # value = NLML, d/dnat = analytic gradient from the GPU
-    obj = (nll - s.module.log_prior(s.nat)) / n
-    obj.backward()
-    params = s.module.raw_list()
-    torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
-    for p in params:
-        if p.grad is not None and torch.isnan(p.grad).any():
-            p.grad = torch.nan_to_num(p.grad, nan=0.0, posinf=0.0, neginf=0.0)
+    obj = (val - lp) / n
+    graw = (grad - dlp) * dnat / n
+    coef = 1.0 / (float(np.sqrt(np.sum(graw * graw))) + 1e-6)   # clip_grad_norm_(max_norm=1.0)
+    if not coef >= 1.0:
+        graw = graw * coef
+    if np.isnan(graw).any():
+        graw = np.nan_to_num(graw, nan=0.0, posinf=0.0, neginf=0.0)
+    for p, gv in zip(s.module.raw_list(), graw):
+        p.grad = torch.tensor([gv], dtype=torch.float64)
     s.opt.step()
-    s.history.append(float(obj.detach()))
+    s.history.append(float(obj))
     if s.sched is not None:
         s.sched.step(s.history[-1])
 
@@ -117,7 +118,7 @@ def _open_site(idx, tup, device, lr, scheduler, patience, pool: Optional[List[ca
         else:
             eng = capi.Engine(max_n=X.shape[0], max_m=2048, device=device)
     eng.set_train(module.spec.to_c(), X, y, noise)
-    opt = torch.optim.Adam(module.raw_list(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    opt = torch.optim.Adam(module.raw_list(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, fused=True)
     sch = None
     if scheduler:
         sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.7, patience=max(20, patience // 2),
@@ -127,8 +128,8 @@ def _open_site(idx, tup, device, lr, scheduler, patience, pool: Optional[List[ca
 
 def _launch_step(s: _SiteState):
     s.opt.zero_grad(set_to_none=True)
-    s.nat = s.module.natural()
-    s.engine.nlml_grad_launch(s.nat.detach().numpy().astype(np.float64))
+    s.chain = s.module.host_chain()
+    s.engine.nlml_grad_launch(np.ascontiguousarray(s.chain[0]))
 
 
 def _close_site(s: _SiteState, predict, pool: Optional[List[capi.Engine]] = None) -> dict:

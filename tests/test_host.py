@@ -131,6 +131,48 @@ def test_host_objective_and_chain_rule_rating():
     assert np.max(np.abs(got - ref)) <= 1e-9 * np.max(np.abs(ref))
 
 
+@pytest.mark.parametrize("model", ["loadest", "rating"])
+def test_closed_form_host_path_matches_autograd(model):
+    """GPModule.host_chain / MarginalB200._objective_closed_form against the autograd path: same objective, same
+    gradient w.r.t. every raw parameter, at the initial values and after moving the raw parameters around."""
+    from discontinuum_b200 import synthetic
+
+    if model == "loadest":
+        X, y, noise = synthetic.loadest_site(50, 9)
+        m = models.LoadestGP()
+        m.X, m.y = X, y
+        m.model = m.build_model(X, y)
+    else:
+        X, y, noise = synthetic.rating_gauge(40, 4)
+        b_lo, b_hi = models.stage_quantile_bounds(X[:, 1])
+        m = models.RatingGP()
+        m.X, m.y = X, y
+        m.fixed_noise = noise
+        m.model = spec.GPModule(models.rating_spec(b_lo, b_hi))
+    m._engine = _FakeEngine(model, X, y, noise)
+    rng = np.random.default_rng(1)
+    for rep in range(3):
+        if rep:
+            with torch.no_grad():
+                for p in m.model.raw_list():
+                    p.add_(float(rng.normal(0.0, 0.4)))
+        for p in m.model.raw_list():
+            p.grad = None
+        obj, _ = m._objective()
+        obj.backward()
+        want = np.concatenate([p.grad.numpy() for p in m.model.raw_list()])
+        val, graw = m._objective_closed_form()
+        assert abs(val - float(obj)) <= 1e-13 * abs(float(obj))
+        assert np.max(np.abs(graw - want)) <= 1e-12 * np.max(np.abs(want))
+    # softplus threshold and interval constraint at the extremes
+    with torch.no_grad():
+        m.model.raw_list()[1].fill_(25.0)
+        m.model.raw_list()[2].fill_(-30.0)
+    nat, dnat, lp, dlp = m.model.host_chain()
+    ref = m.model.natural().detach().numpy()
+    assert np.allclose(nat, ref, rtol=1e-15, atol=1e-300) and dnat[1] == 1.0 and np.isfinite(lp)
+
+
 def test_rating_projection():
     m = models.RatingGP()
     X = np.stack([np.linspace(-1, 1, 30), np.linspace(1.0, 2.0, 30)], 1)
