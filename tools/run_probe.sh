@@ -1,1 +1,2 @@
-CPU=1 python tools/configs_probe.py 2>&1 | tail -3
+REPS=6 python tools/perf_probe.py 512 1024 2048 2>&1 | grep -v "nlml only" | cut -c1-170
+echo GRAPHS; DGP_GRAPHS=1 REPS=6 python tools/perf_probe.py 512 1024 2048 2>&1 | grep -v "nlml only" | cut -c1-170
