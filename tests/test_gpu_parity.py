@@ -509,6 +509,32 @@ def test_engine_fit_trajectory_matches_reference_loop_rating(cuda_device):
     assert np.max(np.abs(np.array(histp) - np.array(hist[:8]))) > 0  # the penalty was active on this data
 
 
+def test_engine_surface_with_xarray_stand_in(cuda_device, monkeypatch):
+    """predict / predict_grid / sample return the reference's container types when xarray objects come in
+    (engines/gpytorch.py:496-499,541-549,583-591); xarray itself is not installable here: tests/fake_xarray.py."""
+    import fake_xarray as fx
+    from discontinuum_b200 import data as dmod
+
+    monkeypatch.setattr(dmod, "_xr", fx)
+    cov, conc = _loadest_arrays(160, 3)
+    ds = fx.Dataset({"flow": ("time", cov["flow"])}, coords={"time": cov["time"]})
+    tgt = fx.DataArray(conc, coords={"time": cov["time"]}, dims=("time",), attrs={"units": "mg/L"}, name="conc")
+    m = models.LoadestGP()
+    m.fit(ds, tgt, iterations=5)
+    ref = models.LoadestGP()
+    ref.fit(cov, conc, iterations=5)
+    target, se = m.predict(ds)
+    t_ref, se_ref = ref.predict(cov)
+    assert isinstance(target, fx.DataArray) and isinstance(se, fx.DataArray) and target.attrs == {"units": "mg/L"}
+    assert np.allclose(target.values, t_ref, rtol=1e-12) and np.allclose(se.values, se_ref, rtol=1e-12)
+    assert np.array_equal(target.coords["time"].values, cov["time"])
+    grid = m.predict_grid("flow")
+    assert isinstance(grid, fx.DataArray) and grid.dims == ("time", "flow") and grid.shape[1] == 18
+    sub = fx.Dataset({"flow": ("time", cov["flow"][:30])}, coords={"time": cov["time"][:30]})
+    sim = m.sample(sub, n=8, seed=2)
+    assert isinstance(sim, fx.DataArray) and sim.dims == ("draw", "time") and sim.shape == (8, 30) and np.all(sim.values > 0)
+
+
 def test_graft_smoke(cuda_device):
     import __graft_entry__ as ge
 

@@ -210,3 +210,32 @@ def test_data_manager_model_space():
         models.LoadestGP(engine.ModelConfig(transform="bogus"))
     with pytest.raises(RuntimeError, match="hasn't been fitted"):
         models.LoadestGP().predict({"time": time, "flow": flow})
+
+
+def test_xarray_adapter_branches_with_stand_in(monkeypatch):
+    """The optional xarray adapter (data.py) against tests/fake_xarray.py: same model-space arrays as the numpy / dict
+    route, DataArray out with the training target's attributes and name, coordinates first in the column order."""
+    import fake_xarray as fx
+
+    monkeypatch.setattr(data, "_xr", fx)
+    rng = np.random.default_rng(2)
+    n = 40
+    time = (np.datetime64("2001-01-01") + (np.sort(rng.uniform(0, 2000, n)) * 86400e9).astype("timedelta64[ns]"))
+    flow = rng.lognormal(3, 1, n)
+    conc = rng.lognormal(0, 0.5, n)
+    ds = fx.Dataset({"flow": ("time", flow)}, coords={"time": time})
+    tgt = fx.DataArray(conc, coords={"time": time}, dims=("time",), attrs={"units": "mg/L"}, name="concentration")
+    a, b = models.LoadestGP(), models.LoadestGP()
+    a.dm.fit(target=tgt, covariates=ds)
+    b.dm.fit(target=conc, covariates={"time": time, "flow": flow})
+    assert np.array_equal(a.dm.X, b.dm.X) and np.array_equal(a.dm.y, b.dm.y)
+    assert a.dm.get_dim("time") == 0 and a.dm.get_dim("flow") == 1
+    back = a.dm.y_t(a.dm.y)
+    assert isinstance(back, fx.DataArray) and back.attrs == {"units": "mg/L"} and back.name == "concentration"
+    assert back.dims == ("time",) and np.allclose(back.values, conc)
+    se = a.dm.se_t(np.full(n, 0.04))
+    assert isinstance(se, fx.DataArray) and np.allclose(se.values, np.asarray(b.dm.se_t(np.full(n, 0.04))))
+    placed = engine._assign_coords(back, ds)
+    assert list(placed.coords) == ["time"] and np.array_equal(placed.coords["time"].values, time)
+    assert isinstance(b.dm.y_t(b.dm.y), np.ndarray)  # numpy in, numpy out
+
