@@ -96,6 +96,9 @@ def _finish_step(s: _SiteState):
         s.sched.step(s.history[-1])
 
 
+_COMPLETION_ORDER = True  # serve sites as their evaluations finish (False: fixed round, blocking on each in turn)
+
+
 def _open_site(idx, tup, device, lr, scheduler, patience, pool: Optional[List[capi.Engine]] = None,
                free_parts: Optional[List[int]] = None) -> _SiteState:
     X, y = np.ascontiguousarray(tup[0], dtype=np.float64), np.ascontiguousarray(tup[1], dtype=np.float64)
@@ -188,7 +191,7 @@ def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int 
     while active:
         served = False
         for s in list(active):
-            if iterations > 0 and not s.engine.nlml_grad_ready():
+            if iterations > 0 and _COMPLETION_ORDER and not s.engine.nlml_grad_ready():
                 continue
             served = True
             if iterations > 0:
