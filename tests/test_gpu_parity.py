@@ -509,6 +509,46 @@ def test_engine_fit_trajectory_matches_reference_loop_rating(cuda_device):
     assert np.max(np.abs(np.array(histp) - np.array(hist[:8]))) > 0  # the penalty was active on this data
 
 
+def test_engine_fit_adamw_matches_reference_loop(cuda_device):
+    """optimizer="adamw" (gpytorch.py:271-288: AdamW, weight decay 1e-2) through the closed-form host path and fused AdamW."""
+    cov, conc = _loadest_arrays(180, 11)
+    m = models.LoadestGP()
+    m.fit(cov, conc, iterations=10, optimizer="adamw")
+    raw = orc.loadest_init_raw()
+    _, hist = orc.fit_adam("loadest", raw, torch.tensor(m.X), torch.tensor(m.y), torch.tensor(m.fixed_noise), iterations=10,
+                           optimizer="adamw")
+    assert np.max(np.abs(np.array(m.history) - np.array(hist)) / np.abs(hist)) <= RTOL
+
+
+def test_schedule_switches_agree(cuda_device):
+    """The fall-back switches of the schedule (first-generation diagonal-block kernel, no programmatic dependent launch,
+    no half tiles, single stream) give the same NLML and gradient as the default path: run in a fresh process each,
+    because the switches are read once per process."""
+    import subprocess
+    import sys
+
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from discontinuum_b200 import capi, models, synthetic\n"
+            "X, y, noise = synthetic.loadest_site(1300, 21)\n"
+            "eng = capi.Engine(max_n=1300, max_m=256); eng.set_train(models.loadest_spec(2).to_c(), X, y, noise)\n"
+            "th = np.array([0.05, 0.7, 1.0, 1.0, 2.0, 1.3, 0.5, 0.2, 0.3, 0.4])\n"
+            "v, g, info = eng.nlml_grad(th); v0, _ = eng.nlml(th)\n"
+            "print(json.dumps({'v': v, 'v0': v0, 'g': g.tolist(), 'info': info}))\n") % (
+                os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for name, env in {"default": {}, "potf2_v1": {"DGP_POTF2_V1": "1"}, "plain": {"DGP_PDL": "0", "DGP_CHAIN_HALF": "0", "DGP_PRIO3": "0"},
+                      "one_stream": {"DGP_LOOKAHEAD": "0"}}.items():
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    ref = out["default"]
+    assert ref["info"] == 0 and abs(ref["v"] - ref["v0"]) <= 1e-10 * abs(ref["v"])
+    for name, o in out.items():
+        assert o["info"] == 0, name
+        assert abs(o["v"] - ref["v"]) <= 1e-11 * abs(ref["v"]), name
+        _grad_close(np.array(o["g"]), np.array(ref["g"]), 1e-9)
+
+
 def test_engine_surface_with_xarray_stand_in(cuda_device, monkeypatch):
     """predict / predict_grid / sample return the reference's container types when xarray objects come in
     (engines/gpytorch.py:496-499,541-549,583-591); xarray itself is not installable here: tests/fake_xarray.py."""
