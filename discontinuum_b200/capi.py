@@ -13,7 +13,8 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 MAX_TERMS, MAX_FACTORS, MAX_FDIMS, MAX_COLS, MAX_THETA = 8, 3, 4, 8, 48
-ABI_VERSION = 1
+ABI_VERSION = 2
+BATCH_MAX_SITES = 32
 
 RBF, MATERN32, MATERN52, PERIODIC = 0, 1, 2, 3
 GATE_NONE, GATE_SIGMOID, GATE_INV_SIGMOID = 0, 1, 2
@@ -84,6 +85,19 @@ _SIGNATURES = [
     ("dgp_set_debug_kinv", C.c_int, [_P, C.c_int]),
     ("dgp_get_kinv", C.c_int, [_P, _P, C.c_int]),
     ("dgp_gemm_nt", C.c_int, [_P, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("dgp_batch_create", C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, _P]),
+    ("dgp_batch_destroy", C.c_int, [_P]),
+    ("dgp_batch_last_error", C.c_char_p, [_P]),
+    ("dgp_batch_workspace_bytes", C.c_size_t, [C.c_int, C.c_int]),
+    ("dgp_batch_set_train", C.c_int, [_P, C.POINTER(DgpSpec), C.c_int, _P, _P, _P, _P]),
+    ("dgp_batch_nlml_grad", C.c_int, [_P, _P, _P, _P, _P, _P]),
+    ("dgp_batch_nlml_grad_launch", C.c_int, [_P, _P, _P]),
+    ("dgp_batch_nlml_grad_ready", C.c_int, [_P]),
+    ("dgp_batch_nlml_grad_wait", C.c_int, [_P, _P, _P, _P]),
+    ("dgp_batch_get_alpha", C.c_int, [_P, C.c_int, _P]),
+    ("dgp_batch_launch_count", C.c_longlong, [_P]),
+    ("dgp_batch_set_timing", C.c_int, [_P, C.c_int]),
+    ("dgp_batch_last_timing", C.c_int, [_P, _P]),
     ("dgp_launch_count", C.c_longlong, [_P]),
     ("dgp_last_timing", C.c_int, [_P, _P]),
     ("dgp_set_timing", C.c_int, [_P, C.c_int]),
@@ -151,6 +165,106 @@ def partition_device(device: int, parts: int) -> Tuple[int, int]:
         msg = lib.dgp_last_error(None)
         raise DgpError(f"dgp_partition_device failed ({rc}): {msg.decode() if msg else ''}")
     return rc, sms.value
+
+
+class BatchEngine:
+    """One libdgp batch handle (dgp_batch_*): up to `max_sites` independent sites sharing one covariance spec, evaluated
+    by ONE launch sequence per call (NLML + gradient of every site).  Host arrays in, host arrays out."""
+
+    def __init__(self, max_sites: int, max_n: int, device: int = 0, stream: int = 0):
+        self.lib = load_library()
+        self._h = _P()
+        rc = self.lib.dgp_batch_create(C.byref(self._h), int(device), int(max_sites), int(max_n), _P(stream) if stream else None)
+        if rc != 0:
+            msg = self.lib.dgp_batch_last_error(None)
+            self._h = _P()
+            raise DgpError(f"dgp_batch_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.max_sites, self.max_n, self.device = int(max_sites), int(max_n), int(device)
+        self.nsites = 0
+        self.ntheta = 0
+        self.ns: Sequence[int] = ()
+
+    def _check(self, rc: int, what: str) -> int:
+        if rc < 0:
+            msg = self.lib.dgp_batch_last_error(self._h)
+            raise DgpError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.dgp_batch_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def set_train(self, spec: DgpSpec, sites):
+        """sites: sequence of (X[n, ndim], y[n], noise[n]) host arrays, one per site."""
+        data = [(_f64(X), _f64(y), _f64(nz)) for X, y, nz in sites]
+        G = len(data)
+        for X, y, nz in data:
+            if X.ndim != 2 or X.shape[1] != spec.ndim or y.shape[0] != X.shape[0] or nz.shape[0] != X.shape[0]:
+                raise ValueError("BatchEngine.set_train: X[n, ndim], y[n], noise[n] expected for every site")
+        ns = (C.c_int * G)(*[int(d[0].shape[0]) for d in data])
+        px = (_P * G)(*[d[0].ctypes.data for d in data])
+        py = (_P * G)(*[d[1].ctypes.data for d in data])
+        pn = (_P * G)(*[d[2].ctypes.data for d in data])
+        self._check(self.lib.dgp_batch_set_train(self._h, C.byref(spec), G, ns, px, py, pn), "dgp_batch_set_train")
+        self.nsites, self.ntheta = G, int(spec.ntheta)
+        self.ns = [int(v) for v in ns]
+        self._keep = spec
+
+    def _args(self, theta, jitter):
+        th = _f64(theta)
+        if th.shape != (self.nsites, self.ntheta):
+            raise ValueError(f"theta must be [{self.nsites}, {self.ntheta}], got {th.shape}")
+        jit = None
+        if jitter is not None:
+            jit = _f64(jitter).reshape(-1)
+            if jit.shape[0] != self.nsites:
+                raise ValueError("jitter must have one entry per site")
+        return th, jit
+
+    def nlml_grad(self, theta, jitter=None):
+        """(nlml[G], grad[G, P], info[G]) of every site at theta[G, P] (natural parameters)."""
+        self.nlml_grad_launch(theta, jitter)
+        return self.nlml_grad_wait()
+
+    def nlml_grad_launch(self, theta, jitter=None):
+        th, jit = self._args(theta, jitter)
+        self._check(self.lib.dgp_batch_nlml_grad_launch(self._h, th.ctypes.data, jit.ctypes.data if jit is not None else None),
+                    "dgp_batch_nlml_grad_launch")
+
+    def nlml_grad_ready(self) -> bool:
+        return self._check(self.lib.dgp_batch_nlml_grad_ready(self._h), "dgp_batch_nlml_grad_ready") == 1
+
+    def nlml_grad_wait(self):
+        val = np.zeros(self.nsites)
+        grad = np.zeros((self.nsites, self.ntheta))
+        info = np.zeros(self.nsites, dtype=np.int32)
+        self._check(self.lib.dgp_batch_nlml_grad_wait(self._h, val.ctypes.data, grad.ctypes.data, info.ctypes.data),
+                    "dgp_batch_nlml_grad_wait")
+        return val, grad, info
+
+    def alpha(self, site: int) -> np.ndarray:
+        a = np.empty(self.ns[site])
+        self._check(self.lib.dgp_batch_get_alpha(self._h, int(site), a.ctypes.data), "dgp_batch_get_alpha")
+        return a
+
+    def set_timing(self, on: bool):
+        self._check(self.lib.dgp_batch_set_timing(self._h, 1 if on else 0), "dgp_batch_set_timing")
+
+    def last_timing(self) -> Sequence[float]:
+        ms = (C.c_double * 4)()
+        self.lib.dgp_batch_last_timing(self._h, ms)
+        return list(ms)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.dgp_batch_launch_count(self._h))
 
 
 class Engine:

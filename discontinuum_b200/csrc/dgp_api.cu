@@ -89,6 +89,7 @@ struct dgp_handle_s {
   int n = 0, npad = 0, nb = 0, sms = 148;
   bool have_train = false, factorized = false, have_T = false, debug_kinv = false, timing = false;
   bool lu_zeroed = false;  // bufL / bufU cleared for the current leading dimension (see k_potf2_v2, zero_lu)
+  int zeroed_npad = 0;     // ... which is this one
   dgp_spec spec;       // internal copy: the caller's spec + derived sin/cos feature columns of periodic factors
   dgp_spec user_spec;  // as passed to dgp_set_train
   // device buffers
@@ -184,11 +185,15 @@ static cudaError_t launch_ex(void (*kern)(KArgs...), int grid, int block, size_t
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
-template <int INIT, int EPI, int MT = 8>
-static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g,
-                       cudaStream_t st = nullptr, bool pdl = false) {
+static const BatchTab g_no_batch = {};   // count == 0: single-site launch
+static const P2Batch g_no_p2batch = {};
+
+template <int INIT, int EPI, int MT = 8, typename HT>
+static int launch_gemm(HT h, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g,
+                       cudaStream_t st = nullptr, bool pdl = false, const BatchTab* bt = nullptr) {
   if (g.ntiles <= 0) return 0;
   if (st == nullptr) st = h->stream;
+  if (bt == nullptr) bt = &g_no_batch;
   static bool attr_set[64] = {false};  // per device: function attributes belong to the device's context
   static int smem_bytes = SM_TOTAL;
   const int dev = (h->device >= 0 && h->device < 64) ? h->device : 0;
@@ -198,7 +203,7 @@ static int launch_gemm(dgp_handle h, const CUtensorMap& a, const CUtensorMap& b,
     CK(h, cudaFuncSetAttribute(k_gemm<INIT, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set[dev] = true;
   }
-  CK(h, launch_ex(k_gemm<INIT, EPI, MT>, g.ntiles * (MT == 8 ? 1 : 2), GEMM_THREADS, (size_t)smem_bytes, st, pdl, a, b, h->spec, g));
+  CK(h, launch_ex(k_gemm<INIT, EPI, MT>, g.ntiles * (MT == 8 ? 1 : 2), GEMM_THREADS, (size_t)smem_bytes, st, pdl, a, b, h->spec, g, *bt));
   h->launches++;
   return 0;
 }
@@ -386,7 +391,9 @@ int dgp_destroy(dgp_handle h) {
   return 0;
 }
 
-static int check_spec(dgp_handle h, const dgp_spec* sp) {
+extern "C++" {
+template <typename HT>
+static int check_spec(HT h, const dgp_spec* sp) {
   if (sp->abi != DGP_ABI_VERSION) DGP_FAIL(h, -1, "spec abi %d != %d", sp->abi, DGP_ABI_VERSION);
   if (sp->ndim < 1 || sp->ndim > DGP_MAX_COLS || sp->ncols < 1 || sp->ncols > DGP_MAX_COLS)
     DGP_FAIL(h, -1, "spec: ndim/ncols out of range");
@@ -423,6 +430,7 @@ static int check_spec(dgp_handle h, const dgp_spec* sp) {
         DGP_FAIL(h, -1, "spec: power-law mean");
   return 0;
 }
+}  // extern "C++"
 
 // Append sinpi / cospi feature columns for periodic factors while the feature table has room (see dgp_cov.cuh).
 static void augment_spec(dgp_spec* sp) {
@@ -468,9 +476,14 @@ int dgp_set_train(dgp_handle h, const dgp_spec* spec, const double* X, const dou
   h->factorized = false;
   h->have_T = false;
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  CK(h, cudaMemsetAsync(h->bufL, 0, (size_t)h->npad * h->npad * 8, h->stream));
-  CK(h, cudaMemsetAsync(h->bufU, 0, (size_t)h->npad * h->npad * 8, h->stream));
-  h->lu_zeroed = true;
+  // The zero sub-blocks of bufL / bufU (above / below the diagonal) are only ever written by the diagonal-block kernel, and
+  // only with zeros: with an unchanged leading dimension they are still clear from the previous training set.
+  if (!h->lu_zeroed || h->zeroed_npad != h->npad) {
+    CK(h, cudaMemsetAsync(h->bufL, 0, (size_t)h->npad * h->npad * 8, h->stream));
+    CK(h, cudaMemsetAsync(h->bufU, 0, (size_t)h->npad * h->npad * 8, h->stream));
+    h->lu_zeroed = true;
+    h->zeroed_npad = h->npad;
+  }
   CK(h, cudaMemsetAsync(h->noise, 0, (size_t)h->npad * 8, h->stream));
   CK(h, cudaMemcpyAsync(h->X, X, (size_t)n * spec->ndim * 8, kind, h->stream));
   CK(h, cudaMemcpyAsync(h->y, y, (size_t)n * 8, kind, h->stream));
@@ -576,7 +589,7 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
     else  // dependent launch behind the in-panel update of the previous block column (same stream, nothing in between)
       CK(h, launch_ex(k_potf2_v2, 1, P2_THREADS, (size_t)P2_SMEM, P, pdl && s > pb && !inplace && !fwd, (const double*)(b.A + off), b.L + off,
                       b.U ? b.U + off : (double*)nullptr, ld, t_in_a ? (double*)nullptr : b.DI + (size_t)s * 128 * 128, b.scal, s * 128,
-                      inplace ? (double*)nullptr : b.A + off, lu_clean ? 0 : 1));
+                      inplace ? (double*)nullptr : b.A + off, lu_clean ? 0 : 1, g_no_p2batch));
     h->launches++;
     CK(h, cudaGetLastError());
     trace_mark(h, P, "potf2>", s);
@@ -1417,3 +1430,5 @@ int dgp_last_timing(dgp_handle h, double* ms4) {
 }
 
 }  // extern "C"
+
+#include "dgp_batch.cuh"

@@ -18,6 +18,8 @@
 
 namespace dgp {
 
+constexpr int DGP_BATCH_MAX = 32;  // sites per batched launch (dgp_batch_*)
+
 struct FactorC {
   int kind, ndims;
   int col[DGP_MAX_FDIMS];

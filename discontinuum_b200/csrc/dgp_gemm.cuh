@@ -49,6 +49,22 @@ struct GemmArgs {
   int latent;                   // INIT_COV: add only `jitter` on the diagonal (latent posterior covariance)
 };
 
+// Batched launches (dgp_batch_*: several independent sites per launch).  A launch covers the tiles of up to
+// DGP_BATCH_MAX sites: entry e owns tile indices [e.tile0, next.tile0) and carries the per-site values of the mode
+// dependent GemmArgs fields.  Every per-site array lives in a slab indexed by the site: matrices [site][ld][ld] behind 3-D
+// tensor maps (the site is the third TMA coordinate), per-point vectors [site][ld], theta [site][DGP_MAX_THETA].
+// count == 0: a plain single-site launch (GemmArgs as given, 2-D tensor maps).
+struct BatchEnt { int tile0, site, step, nb, n, aux0, aux1, aux2; };
+struct BatchTab {
+  int count, pad_;
+  long long ld;                 // leading dimension of every slab matrix = rows of a per-point vector slab
+  const double* jitv;           // [sites] diagonal jitter of each site
+  BatchEnt e[DGP_BATCH_MAX];
+};
+
+// the fields of GemmArgs that decode_job reads (per site in a batched launch)
+struct JobCtx { int mode, step, nb, aux0, aux1, aux2; };
+
 struct Job {
   int rowA, kA, rowB, kB, nk;   // operand panel origins (elements) and number of 16-wide k steps
   int crow, ccol;               // output tile origin
@@ -63,7 +79,7 @@ __device__ __forceinline__ int isqrt_floor(int x) {
   return r;
 }
 
-__device__ __forceinline__ Job decode_job(const GemmArgs& g, int tile, int init_default) {
+__device__ __forceinline__ Job decode_job(const JobCtx& g, int tile, int init_default) {
   Job j;
   j.init = init_default;
   j.valid = 1;
@@ -188,6 +204,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -213,7 +234,7 @@ static_assert(SMG_END <= STAGES * STAGE_BYTES, "grad epilogue does not fit the s
 template <int INIT, int EPI, int MT = 8>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-       const __grid_constant__ dgp_spec spec, const GemmArgs g) {
+       const __grid_constant__ dgp_spec spec, const GemmArgs g, const __grid_constant__ BatchTab bt) {
   static_assert(MT == 8 || (MT == 4 && INIT != INIT_COV && EPI == EPI_STORE), "half tiles: plain load/store tiles only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -222,7 +243,23 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   CovC* cc = (CovC*)(smem + SM_COVC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Job job = decode_job(g, MT == 8 ? blockIdx.x : (blockIdx.x >> 1), INIT);
+  int tile = MT == 8 ? blockIdx.x : (blockIdx.x >> 1);
+  JobCtx jc{g.mode, g.step, g.nb, g.aux0, g.aux1, g.aux2};
+  int site = -1, npts = g.n;   // site >= 0: batched launch
+  double jitter = g.jitter;
+  if (bt.count > 0) {
+    int k = 0;
+#pragma unroll 1
+    for (int i = 1; i < bt.count; i++) if (tile >= bt.e[i].tile0) k = i;
+    const BatchEnt& e = bt.e[k];
+    tile -= e.tile0; site = e.site; npts = e.n;
+    jc.step = e.step; jc.nb = e.nb; jc.aux0 = e.aux0; jc.aux1 = e.aux1; jc.aux2 = e.aux2;
+    jitter = bt.jitv[site];
+  }
+  // slab offsets of this site (0 for a single-site launch)
+  const size_t soff_m = site >= 0 ? (size_t)site * (size_t)bt.ld * (size_t)bt.ld : 0;  // matrices
+  const size_t soff_v = site >= 0 ? (size_t)site * (size_t)bt.ld : 0;                   // per-point vectors
+  Job job = decode_job(jc, tile, INIT);
   if (!job.valid) return;
   if (MT == 4) { job.rowA += 64 * (blockIdx.x & 1); job.crow += 64 * (blockIdx.x & 1); }
 
@@ -244,9 +281,15 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
         if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
         uint8_t* st = smem + SM_STAGES + s * STAGE_BYTES;
         mbar_expect_tx(&full[s], MT == 8 ? STAGE_BYTES : STAGE_BYTES - 64 * BK * 8);
-        tma_load_2d(st, &tmA, &full[s], job.kA + it * BK, job.rowA);
-        if (MT == 8) tma_load_2d(st + 64 * BK * 8, &tmA, &full[s], job.kA + it * BK, job.rowA + 64);
-        tma_load_2d(st + A_BYTES, &tmB, &full[s], job.kB + it * BK, job.rowB);
+        if (site < 0) {
+          tma_load_2d(st, &tmA, &full[s], job.kA + it * BK, job.rowA);
+          if (MT == 8) tma_load_2d(st + 64 * BK * 8, &tmA, &full[s], job.kA + it * BK, job.rowA + 64);
+          tma_load_2d(st + A_BYTES, &tmB, &full[s], job.kB + it * BK, job.rowB);
+        } else {
+          tma_load_3d(st, &tmA, &full[s], job.kA + it * BK, job.rowA, site);
+          if (MT == 8) tma_load_3d(st + 64 * BK * 8, &tmA, &full[s], job.kA + it * BK, job.rowA + 64, site);
+          tma_load_3d(st + A_BYTES, &tmB, &full[s], job.kB + it * BK, job.rowB, site);
+        }
       }
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -269,13 +312,15 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
     double* xb = xaT + DGP_XS * BM;                 // [64][DGP_XS]  column-point features
     double* W = (double*)(smem + SM_STAGES);
     const int t = threadIdx.x;  // 0..127
-    cov_compile(cc, spec, g.theta, g.jitter, t, 128);
-    for (int e = t; e < BM * DGP_XS; e += 128) xaT[(e % DGP_XS) * BM + e / DGP_XS] = g.Xw[(size_t)job.crow * DGP_XS + e];
-    for (int e = t; e < BN * DGP_XS; e += 128) xb[e] = g.Xw[(size_t)job.ccol * DGP_XS + e];
+    const double* Xw_s = g.Xw + soff_v * DGP_XS;
+    const double* noise_s = g.noise + soff_v;
+    cov_compile(cc, spec, g.theta + (site >= 0 ? site * DGP_MAX_THETA : 0), jitter, t, 128);
+    for (int e = t; e < BM * DGP_XS; e += 128) xaT[(e % DGP_XS) * BM + e / DGP_XS] = Xw_s[(size_t)job.crow * DGP_XS + e];
+    for (int e = t; e < BN * DGP_XS; e += 128) xb[e] = Xw_s[(size_t)job.ccol * DGP_XS + e];
     consumer_bar();
     {
       const int gr = job.crow + t;
-      const double dn = (gr < g.n) ? (g.latent ? g.jitter : g.noise[gr] + cc->extra_noise) : 0.0;
+      const double dn = (gr < npts) ? (g.latent ? jitter : noise_s[gr] + cc->extra_noise) : 0.0;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += COV_V) {
         double val[COV_V];
@@ -284,7 +329,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
         for (int v = 0; v < COV_V; v++) {
           const int gc = job.ccol + c0 + v;
           double x = val[v];
-          if (gr < g.n && gc < g.n) { if (gr == gc) x += dn; }
+          if (gr < npts && gc < npts) { if (gr == gc) x += dn; }
           else x = (gr == gc) ? 1.0 : 0.0;
           W[t * WS + c0 + v] = g.sign * x;
         }
@@ -305,7 +350,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   } else if ((INIT == INIT_LOAD || INIT == INIT_COV) && job.init == INIT_LOAD) {
 #pragma unroll
     for (int mi = 0; mi < MT; mi++) {
-      const double* crow = g.C + (size_t)(job.crow + WROWS * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
+      const double* crow = g.C + soff_m + (size_t)(job.crow + WROWS * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
 #pragma unroll
       for (int ni = 0; ni < 4; ni++) {
         const double2 v = *reinterpret_cast<const double2*>(crow + 8 * ni);
@@ -362,7 +407,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   if constexpr (EPI == EPI_STORE) {
 #pragma unroll
     for (int mi = 0; mi < MT; mi++) {
-      double* crow = g.C + (size_t)(job.crow + WROWS * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
+      double* crow = g.C + soff_m + (size_t)(job.crow + WROWS * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
 #pragma unroll
       for (int ni = 0; ni < 4; ni++) {
         double2 v;

@@ -15,11 +15,10 @@ constexpr int SC_SIZE = SC_GRAD + DGP_MAX_THETA;
 // Xw[i] = feature row of point i (copy / log-warp / gate columns, src/rating_gp/models/kernels.py:307-382),
 // mean[i] = m(x_i) (ConstantMean, or PowerLawTransform src/rating_gp/models/gpytorch.py:28-40),
 // r[i] = y[i] - mean[i] when y != nullptr.  Rows >= n are zero.
-__global__ void k_features(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta,
-                           const double* __restrict__ X, const double* __restrict__ y, double* __restrict__ Xw,
-                           double* __restrict__ r, double* __restrict__ mean_out, int n, int npad,
-                           double* __restrict__ scal) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void features_body(const dgp_spec& spec, const double* __restrict__ theta,
+                                              const double* __restrict__ X, const double* __restrict__ y, double* __restrict__ Xw,
+                                              double* __restrict__ r, double* __restrict__ mean_out, int n, int npad,
+                                              double* __restrict__ scal, int i) {
   if (scal != nullptr && i < SC_SIZE) scal[i] = 0.0;
   if (i >= npad) return;
   double row[DGP_XS];
@@ -47,22 +46,49 @@ __global__ void k_features(const __grid_constant__ dgp_spec spec, const double* 
   if (r != nullptr) r[i] = (i < n && y != nullptr) ? y[i] - m : 0.0;
 }
 
+__global__ void k_features(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta,
+                           const double* __restrict__ X, const double* __restrict__ y, double* __restrict__ Xw,
+                           double* __restrict__ r, double* __restrict__ mean_out, int n, int npad,
+                           double* __restrict__ scal) {
+  features_body(spec, theta, X, y, Xw, r, mean_out, n, npad, scal, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// ------------------------------------------------------------------ batched companions (dgp_batch_*)
+// Per-site sizes of a batch.  Per-site arrays are slabs indexed by the site: matrices [site][ld][ld], per-point vectors
+// [site][ld], feature tables [site][ld][DGP_XS], inputs [site][ld][DGP_MAX_COLS], theta [site][DGP_MAX_THETA],
+// scalar blocks [site][SC_SIZE].  The kernels below are the single-site bodies with the site taken from the grid.
+struct SiteDims {
+  int count, nbmax;
+  long long ld;
+  int n[DGP_BATCH_MAX], nb[DGP_BATCH_MAX];
+  int tile0[DGP_BATCH_MAX + 1];   // prefix of nb (nb + 1) lower 128 x 64 tiles per site (gradient contraction)
+};
+
+// grid = (ceil(ld / 256), sites)
+__global__ void k_features_b(const __grid_constant__ dgp_spec spec, const __grid_constant__ SiteDims sd,
+                             const double* __restrict__ theta, const double* __restrict__ X, const double* __restrict__ y,
+                             double* __restrict__ Xw, double* __restrict__ r, double* __restrict__ scal) {
+  const int st = blockIdx.y;
+  const size_t v = (size_t)st * sd.ld;
+  features_body(spec, theta + st * DGP_MAX_THETA, X + v * DGP_MAX_COLS, y + v, Xw + v * DGP_XS, r + v, nullptr, sd.n[st],
+                sd.nb[st] * 128, scal + (size_t)st * SC_SIZE, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 // ------------------------------------------------------------------ covariance rectangle
 // out[i, j] = k(xa_i, xb_j) (+ noise on the global diagonal when `diag_noise`), i < ra_pad, j in this
 // CTA's 128-column block.  Entries outside (na, nb_) are identity padding when `ident_pad`, else 0.
 // Optionally accumulates dot[cblock][i] = sum_j out[i, j] * vec[j] (posterior mean partials).
 // grid = (ra_pad / 32, ncol_blocks), block = 256 threads, each thread 16 entries.
-__global__ void __launch_bounds__(256)
-k_cov_rect(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta,
+__device__ __forceinline__ void cov_rect_body(const dgp_spec& spec, const double* __restrict__ theta,
            const double* __restrict__ XwA, const double* __restrict__ XwB, const double* __restrict__ noise,
            double jitter, double* __restrict__ out, long long ld, int na, int nb_, int diag_noise, int ident_pad,
-           const double* __restrict__ vec, double* __restrict__ dot, int dot_ld) {
+           const double* __restrict__ vec, double* __restrict__ dot, int dot_ld, int bx, int by) {
   __shared__ CovC cc;
   __shared__ double xa[32 * DGP_XS];    // row points, row-major (broadcast side)
   __shared__ double xbT[DGP_XS * 128];  // column points, column-major (per-thread side)
   __shared__ double red[32][9];
   const int t = threadIdx.x;
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+  const int r0 = bx * 32, c0 = by * 128;
   cov_compile(&cc, spec, theta, jitter, t, 256);
   for (int e = t; e < 32 * DGP_XS; e += 256) xa[e] = XwA[(size_t)r0 * DGP_XS + e];
   for (int e = t; e < 128 * DGP_XS; e += 256) xbT[(e % DGP_XS) * 128 + e / DGP_XS] = XwB[(size_t)c0 * DGP_XS + e];
@@ -94,8 +120,29 @@ k_cov_rect(const __grid_constant__ dgp_spec spec, const double* __restrict__ the
   }
   if (dot != nullptr) {
     __syncthreads();
-    if (t < 32) dot[(size_t)blockIdx.y * dot_ld + r0 + t] = (red[t][0] + red[t][1]) + (red[t][2] + red[t][3]);
+    if (t < 32) dot[(size_t)by * dot_ld + r0 + t] = (red[t][0] + red[t][1]) + (red[t][2] + red[t][3]);
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_cov_rect(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta,
+           const double* __restrict__ XwA, const double* __restrict__ XwB, const double* __restrict__ noise,
+           double jitter, double* __restrict__ out, long long ld, int na, int nb_, int diag_noise, int ident_pad,
+           const double* __restrict__ vec, double* __restrict__ dot, int dot_ld) {
+  cov_rect_body(spec, theta, XwA, XwB, noise, jitter, out, ld, na, nb_, diag_noise, ident_pad, vec, dot, dot_ld, blockIdx.x,
+                blockIdx.y);
+}
+
+// block column 0 of every site's work matrix (noise on the diagonal, identity padding): grid = (4 nbmax, 1, sites)
+__global__ void __launch_bounds__(256)
+k_cov_col0_b(const __grid_constant__ dgp_spec spec, const __grid_constant__ SiteDims sd, const double* __restrict__ theta,
+             const double* __restrict__ Xw, const double* __restrict__ noise, const double* __restrict__ jitv,
+             double* __restrict__ A) {
+  const int st = blockIdx.z;
+  if ((int)blockIdx.x >= 4 * sd.nb[st]) return;
+  const size_t v = (size_t)st * sd.ld;
+  cov_rect_body(spec, theta + st * DGP_MAX_THETA, Xw + v * DGP_XS, Xw + v * DGP_XS, noise + v, jitv[st], A + v * sd.ld, sd.ld,
+                sd.n[st], sd.n[st], 1, 1, nullptr, nullptr, 0, blockIdx.x, 0);
 }
 
 // ------------------------------------------------------------------ diagonal block: L, L^-1, L^-T
@@ -293,9 +340,9 @@ k_fwd_step(const double* __restrict__ L, long long ld, const double* __restrict_
 
 // ------------------------------------------------------------------ alpha = U z  (U = L^-T upper triangular)
 // one warp per row, grid = npad / 8, block = 256
-__global__ void __launch_bounds__(256)
-k_upper_gemv(const double* __restrict__ U, long long ld, const double* __restrict__ z, double* __restrict__ out, int npad) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+__device__ __forceinline__ void upper_gemv_body(const double* __restrict__ U, long long ld, const double* __restrict__ z,
+                                                double* __restrict__ out, int npad, int bx) {
+  const int row = bx * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= npad) return;
   const double* up = U + (size_t)row * ld;
   double a0 = 0.0, a1 = 0.0;
@@ -310,14 +357,24 @@ k_upper_gemv(const double* __restrict__ U, long long ld, const double* __restric
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) out[row] = acc;
 }
+__global__ void __launch_bounds__(256)
+k_upper_gemv(const double* __restrict__ U, long long ld, const double* __restrict__ z, double* __restrict__ out, int npad) {
+  upper_gemv_body(U, ld, z, out, npad, blockIdx.x);
+}
+// grid = (ld / 8, sites)
+__global__ void __launch_bounds__(256)
+k_upper_gemv_b(const __grid_constant__ SiteDims sd, const double* __restrict__ U, const double* __restrict__ z,
+               double* __restrict__ out) {
+  const int st = blockIdx.y;
+  const size_t v = (size_t)st * sd.ld;
+  upper_gemv_body(U + v * sd.ld, sd.ld, z + v, out + v, sd.nb[st] * 128, blockIdx.x);
+}
 
 // ------------------------------------------------------------------ z = U^T r  (U upper triangular), two stages
 // stage 1: grid = (nb, nb); CTA (cb, rb) with rb <= cb sums rows of row block rb for the 128 columns of block cb
 // into part[rb][col]; stage 2 adds the row-block partials in a fixed order.
-__global__ void __launch_bounds__(256)
-k_upperT_gemv_part(const double* __restrict__ U, long long ld, const double* __restrict__ r, double* __restrict__ part,
-                   long long ldp) {
-  const int cb = blockIdx.x, rb = blockIdx.y;
+__device__ __forceinline__ void upperT_gemv_part_body(const double* __restrict__ U, long long ld, const double* __restrict__ r,
+                                                      double* __restrict__ part, long long ldp, int cb, int rb) {
   if (rb > cb) return;
   __shared__ double rs[128];
   __shared__ double hs[128];
@@ -338,23 +395,47 @@ k_upperT_gemv_part(const double* __restrict__ U, long long ld, const double* __r
   __syncthreads();
   if (half == 0) part[(size_t)rb * ldp + cb * 128 + col] = acc + hs[col];
 }
-
 __global__ void __launch_bounds__(256)
-k_upperT_gemv_sum(const double* __restrict__ part, long long ldp, double* __restrict__ z, int npad) {
-  const int j = blockIdx.x * 256 + threadIdx.x;
+k_upperT_gemv_part(const double* __restrict__ U, long long ld, const double* __restrict__ r, double* __restrict__ part,
+                   long long ldp) {
+  upperT_gemv_part_body(U, ld, r, part, ldp, blockIdx.x, blockIdx.y);
+}
+// grid = (nbmax, nbmax, sites); part: [site][nbmax][ld]
+__global__ void __launch_bounds__(256)
+k_upperT_gemv_part_b(const __grid_constant__ SiteDims sd, const double* __restrict__ U, const double* __restrict__ r,
+                     double* __restrict__ part) {
+  const int st = blockIdx.z;
+  if ((int)blockIdx.x >= sd.nb[st]) return;
+  const size_t v = (size_t)st * sd.ld;
+  upperT_gemv_part_body(U + v * sd.ld, sd.ld, r + v, part + v * sd.nbmax, sd.ld, blockIdx.x, blockIdx.y);
+}
+
+__device__ __forceinline__ void upperT_gemv_sum_body(const double* __restrict__ part, long long ldp, double* __restrict__ z,
+                                                     int npad, int j) {
   if (j >= npad) return;
   double s = 0.0;
   for (int rb = 0; rb <= (j >> 7); rb++) s += part[(size_t)rb * ldp + j];
   z[j] = s;
 }
+__global__ void __launch_bounds__(256)
+k_upperT_gemv_sum(const double* __restrict__ part, long long ldp, double* __restrict__ z, int npad) {
+  upperT_gemv_sum_body(part, ldp, z, npad, blockIdx.x * 256 + threadIdx.x);
+}
+// grid = (ceil(ld / 256), sites)
+__global__ void __launch_bounds__(256)
+k_upperT_gemv_sum_b(const __grid_constant__ SiteDims sd, const double* __restrict__ part, double* __restrict__ z) {
+  const int st = blockIdx.y;
+  const size_t v = (size_t)st * sd.ld;
+  upperT_gemv_sum_body(part + v * sd.nbmax, sd.ld, z + v, sd.nb[st] * 128, blockIdx.x * 256 + threadIdx.x);
+}
 
 // ------------------------------------------------------------------ T21 = U12^T for every pair of one merge level
 // Pair p merges block ranges [o, o+h) and [o+h, o+2h), o = 2 h p.  grid.x = pairs * (4h)^2 tiles of 32x32.
-__global__ void __launch_bounds__(256)
-k_transpose_pairs(const double* __restrict__ U, double* __restrict__ T, long long ld, int hb, int npad) {
+__device__ __forceinline__ void transpose_pairs_body(const double* __restrict__ U, double* __restrict__ T, long long ld, int hb,
+                                                     int npad, int bx) {
   __shared__ double tile[32][33];
   const int per = 16 * hb * hb;
-  const int pr = blockIdx.x / per, rem = blockIdx.x % per;
+  const int pr = bx / per, rem = bx % per;
   const int ty32 = rem / (4 * hb), tx32 = rem % (4 * hb);
   const int r0 = pr * 2 * hb * 128 + ty32 * 32, c0 = (pr * 2 * hb + hb) * 128 + tx32 * 32;
   if (c0 >= npad) return;
@@ -363,16 +444,29 @@ k_transpose_pairs(const double* __restrict__ U, double* __restrict__ T, long lon
   __syncthreads();
   for (int r = ty; r < 32; r += 8) T[(size_t)(c0 + r) * ld + r0 + tx] = tile[tx][r];
 }
+__global__ void __launch_bounds__(256)
+k_transpose_pairs(const double* __restrict__ U, double* __restrict__ T, long long ld, int hb, int npad) {
+  transpose_pairs_body(U, T, ld, hb, npad, blockIdx.x);
+}
+// grid = (max over sites of pairs * 16 hb^2, sites); a site takes part while the next merge level needs its T21 (2 hb < nb)
+__global__ void __launch_bounds__(256)
+k_transpose_pairs_b(const __grid_constant__ SiteDims sd, const double* __restrict__ U, double* __restrict__ T, int hb) {
+  const int st = blockIdx.y, nb = sd.nb[st];
+  if (2 * hb >= nb) return;
+  const int npairs = (nb - hb + 2 * hb - 1) / (2 * hb);
+  if ((int)blockIdx.x >= npairs * 16 * hb * hb) return;
+  const size_t m = (size_t)st * sd.ld * sd.ld;
+  transpose_pairs_body(U + m, T + m, sd.ld, hb, nb * 128, blockIdx.x);
+}
 
 // ------------------------------------------------------------------ final reductions (deterministic order)
 // block b < ntheta: grad[b] = sum_tiles part[tile][b] (+ mean-parameter terms -J' alpha)
 // block ntheta:     quad = z'z ; nlml = 1/2 quad + logdet + n/2 log 2 pi
-__global__ void __launch_bounds__(256)
-k_finish(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta, const double* __restrict__ part,
+__device__ __forceinline__ void finish_body(const dgp_spec& spec, const double* __restrict__ theta, const double* __restrict__ part,
          int ntiles, const double* __restrict__ z, const double* __restrict__ alpha, const double* __restrict__ X,
-         int n, int npad, double* __restrict__ scal, int want_grad) {
+         int n, int npad, double* __restrict__ scal, int want_grad, int b) {
   __shared__ double red[256];
-  const int tid = threadIdx.x, b = blockIdx.x;
+  const int tid = threadIdx.x;
   double s = 0.0;
   if (b == spec.ntheta) {
     for (int i = tid; i < npad; i += 256) s = fma(z[i], z[i], s);
@@ -409,6 +503,22 @@ k_finish(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta
       scal[SC_GRAD + b] = want_grad ? red[0] : 0.0;
     }
   }
+}
+__global__ void __launch_bounds__(256)
+k_finish(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta, const double* __restrict__ part,
+         int ntiles, const double* __restrict__ z, const double* __restrict__ alpha, const double* __restrict__ X,
+         int n, int npad, double* __restrict__ scal, int want_grad) {
+  finish_body(spec, theta, part, ntiles, z, alpha, X, n, npad, scal, want_grad, blockIdx.x);
+}
+// grid = (ntheta + 1, sites); part: [site][nbmax (nbmax + 1)][DGP_MAX_THETA]
+__global__ void __launch_bounds__(256)
+k_finish_b(const __grid_constant__ dgp_spec spec, const __grid_constant__ SiteDims sd, const double* __restrict__ theta,
+           const double* __restrict__ part, const double* __restrict__ z, const double* __restrict__ alpha,
+           const double* __restrict__ X, double* __restrict__ scal) {
+  const int st = blockIdx.y, nb = sd.nb[st];
+  const size_t v = (size_t)st * sd.ld;
+  finish_body(spec, theta + st * DGP_MAX_THETA, part + (size_t)st * sd.nbmax * (sd.nbmax + 1) * DGP_MAX_THETA, nb * (nb + 1),
+              z + v, alpha + v, X + v * DGP_MAX_COLS, sd.n[st], nb * 128, scal + (size_t)st * SC_SIZE, 1, blockIdx.x);
 }
 
 // ------------------------------------------------------------------ prediction reductions
@@ -589,17 +699,15 @@ k_wgrad(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta,
 #ifndef DGP_GC_BLOCKS
 #define DGP_GC_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(128, DGP_GC_BLOCKS)
-k_grad_contract(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta, const double* __restrict__ Xw,
+__device__ __forceinline__ void grad_contract_body(const dgp_spec& spec, const double* __restrict__ theta, const double* __restrict__ Xw,
                 const double* __restrict__ alpha, const double* __restrict__ Kinv, long long ld, int n,
-                double* __restrict__ part) {
+                double* __restrict__ part, int tile) {
   __shared__ CovC cc;
   __shared__ double xaT[DGP_XS * 128];
   __shared__ double xb[64 * DGP_XS];
   __shared__ double al[64];
   __shared__ double red[4 * DGP_MAX_TERMS * NSLOT + 4];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int tile = blockIdx.x;
   int ib = (int)sqrt((double)(4 * tile + 1));
   while (ib * ib > 4 * tile + 1) --ib;
   while ((ib + 1) * (ib + 1) <= 4 * tile + 1) ++ib;
@@ -658,6 +766,24 @@ k_grad_contract(const __grid_constant__ dgp_spec spec, const double* __restrict_
       for (int w4 = 0; w4 < 4; w4++) s += red[4 * DGP_MAX_TERMS * NSLOT + w4];
     part[(size_t)tile * DGP_MAX_THETA + t] = -0.5 * s;
   }
+}
+__global__ void __launch_bounds__(128, DGP_GC_BLOCKS)
+k_grad_contract(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta, const double* __restrict__ Xw,
+                const double* __restrict__ alpha, const double* __restrict__ Kinv, long long ld, int n,
+                double* __restrict__ part) {
+  grad_contract_body(spec, theta, Xw, alpha, Kinv, ld, n, part, blockIdx.x);
+}
+// grid = sd.tile0[sites] tiles of all sites (prefix lookup); part: [site][nbmax (nbmax + 1)][DGP_MAX_THETA]
+__global__ void __launch_bounds__(128, DGP_GC_BLOCKS)
+k_grad_contract_b(const __grid_constant__ dgp_spec spec, const __grid_constant__ SiteDims sd, const double* __restrict__ theta,
+                  const double* __restrict__ Xw, const double* __restrict__ alpha, const double* __restrict__ Kinv,
+                  double* __restrict__ part) {
+  int st = 0;
+#pragma unroll 1
+  for (int i = 1; i < sd.count; i++) if ((int)blockIdx.x >= sd.tile0[i]) st = i;
+  const size_t v = (size_t)st * sd.ld;
+  grad_contract_body(spec, theta + st * DGP_MAX_THETA, Xw + v * DGP_XS, alpha + v, Kinv + v * sd.ld, sd.ld, sd.n[st],
+                     part + (size_t)st * sd.nbmax * (sd.nbmax + 1) * DGP_MAX_THETA, (int)blockIdx.x - sd.tile0[st]);
 }
 
 // v[j] = sum_p c[p] Kx[p, j]   (p < mpad), grid = npad / 256

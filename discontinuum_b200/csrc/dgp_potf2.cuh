@@ -208,10 +208,28 @@ __device__ __forceinline__ void p2_st_prog(int* prog, int v) {
 // Warp roles in phase A of step k: warp 0 pivots; warps 1..3-k follow with the rows of the sub-blocks below and warp 5
 // with the rows of the identity (one pivot behind, through the published columns of Lu); warp 4 waits for the last pivot
 // and takes the scalings; the helpers (warps 6, 7; at k = 3 warps 1, 2, 3, 6, 7) finish the previous row of the inverse.
+//
+// Batched launch (pb.count > 0, one CTA per site): Ablk / Lblk / Ublk / Tblk are then the bases of the [site][ld][ld]
+// slabs and scal the base of [site][SC_SIZE]; CTA b factors the diagonal block pb.step[b] of site pb.site[b].
+struct P2Batch {
+  int count, pad_;
+  long long slab;               // elements between the matrices of consecutive sites
+  short site[DGP_BATCH_MAX], step[DGP_BATCH_MAX];
+};
+
 __global__ void __maxnreg__(144)
 k_potf2_v2(const double* Ablk, double* Lblk, double* Ublk, long long ld, double* DIblk, double* __restrict__ scal, int base,
-           double* Tblk, int zero_lu) {
+           double* Tblk, int zero_lu, const __grid_constant__ P2Batch pb) {
   extern __shared__ __align__(16) double p2_smem[];
+  if (pb.count > 0) {
+    const int st = pb.site[blockIdx.x], s = pb.step[blockIdx.x];
+    const size_t off = (size_t)st * (size_t)pb.slab + (size_t)s * 128 * (size_t)ld + (size_t)s * 128;
+    Ablk += off; Lblk += off;
+    if (Ublk != nullptr) Ublk += off;
+    if (Tblk != nullptr) Tblk += off;
+    scal += (size_t)st * SC_SIZE;
+    base = s * 128;
+  }
   double* sm = p2_smem;
   double* ex = sm + P2_OFF_EX;
   double* wv = sm + P2_OFF_W;

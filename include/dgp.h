@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DGP_ABI_VERSION 1
+#define DGP_ABI_VERSION 2
 
 #define DGP_MAX_TERMS 8    /* additive terms of the covariance                        */
 #define DGP_MAX_FACTORS 3  /* stationary factors multiplied inside one term           */
@@ -221,6 +221,42 @@ int dgp_get_kinv(dgp_handle h, double* Kinv_out, int out_on_device);
  * M % 128 == 0, N % 64 == 0, K % 16 == 0; row-major with leading dimensions lda/ldb/ldc. */
 int dgp_gemm_nt(dgp_handle h, const double* A, long long lda, const double* B, long long ldb, double* C,
                 long long ldc, int M, int N, int K, int mode);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batched, variable-size multi-site evaluation: up to DGP_BATCH_MAX_SITES independent sites that share one covariance
+ * spec (an NWQN-style batch of loadest-gp sites, a set of rating-gp gauges) evaluated by ONE launch sequence.  Replaces
+ * the reference's one-worker-per-site map, examples/nwqn-loadest-example/nwqn-loadest-example.py:156-157 (fexec.map over
+ * sites, each running MarginalGPyTorch.fit, discontinuum/engines/gpytorch.py:346-444) and the per-gauge loop of
+ * docs/source/notebooks/rating-gp-demo.ipynb.  Every kernel launch of the single-site schedule covers all sites (tile
+ * index -> (site, tile) through a per-launch prefix table), so the latency-bound panel chain is paid once per block step
+ * for the whole batch.  Sites of different n are end-aligned; per site the arithmetic is that of dgp_nlml_grad,
+ * bit for bit.  Workspace (3 max_sites x max_n^2 float64 + O(max_sites max_n)) is allocated at create; later calls
+ * allocate nothing.  Host pointers throughout. */
+#define DGP_BATCH_MAX_SITES 32
+typedef struct dgp_batch_s* dgp_batch;
+int dgp_batch_create(dgp_batch* out, int device, int max_sites, int max_n, void* stream);
+int dgp_batch_destroy(dgp_batch b);
+const char* dgp_batch_last_error(dgp_batch b); /* b may be NULL: error of a failed dgp_batch_create */
+size_t dgp_batch_workspace_bytes(int max_sites, int max_n);
+/* Training sets of nsites sites: n[s] points each, X[s][n[s], ndim], y[s][n[s]], noise[s][n[s]] (host arrays of host pointers). */
+int dgp_batch_set_train(dgp_batch b, const dgp_spec* spec, int nsites, const int* n, const double* const* X,
+                        const double* const* y, const double* const* noise);
+/* NLML and gradient of every site.  theta[nsites][ntheta] natural parameters, jitter[nsites] (NULL: 0);
+ * nlml_out[nsites], grad_out[nsites][ntheta], info_out[nsites] (LAPACK-style, 0 = ok) may each be NULL.
+ * Returns the number of sites with info != 0, or < 0 (bad argument / CUDA error). */
+int dgp_batch_nlml_grad(dgp_batch b, const double* theta, const double* jitter, double* nlml_out, double* grad_out,
+                        int* info_out);
+/* Asynchronous form: launch enqueues the evaluation and the device-to-host copy of the results; ready polls (1 / 0 / < 0);
+ * wait blocks and returns like dgp_batch_nlml_grad. */
+int dgp_batch_nlml_grad_launch(dgp_batch b, const double* theta, const double* jitter);
+int dgp_batch_nlml_grad_ready(dgp_batch b);
+int dgp_batch_nlml_grad_wait(dgp_batch b, double* nlml_out, double* grad_out, int* info_out);
+/* Parity accessor: alpha of one site after an evaluation. */
+int dgp_batch_get_alpha(dgp_batch b, int site, double* alpha_out);
+long long dgp_batch_launch_count(dgp_batch b);
+/* Device time (ms) of the last evaluation: factorisation / inverse / LAUUM + gradient / rest. */
+int dgp_batch_set_timing(dgp_batch b, int enable);
+int dgp_batch_last_timing(dgp_batch b, double* ms4);
 
 /* Counters for bench.py: kernels launched by this handle since creation. */
 long long dgp_launch_count(dgp_handle h);

@@ -43,7 +43,7 @@ int main() {
       cudaEventRecord(e0);
       for (int it = 0; it < iters; it++) {
         if (v == 0) k_potf2<<<1, PF_THREADS, PF_SMEM>>>(dA, dL[v], dU[v], ld, dDI[v], scal, 0, dT[v]);
-        else k_potf2_v2<<<1, P2_THREADS, P2_SMEM>>>(dA, dL[v], dU[v], ld, getenv("P2_FULL") ? dDI[v] : nullptr, scal, 0, dT[v], getenv("P2_FULL") ? 1 : 0);
+        else k_potf2_v2<<<1, P2_THREADS, P2_SMEM>>>(dA, dL[v], dU[v], ld, getenv("P2_FULL") ? dDI[v] : nullptr, scal, 0, dT[v], getenv("P2_FULL") ? 1 : 0, P2Batch{});
       }
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1);
