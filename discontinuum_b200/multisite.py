@@ -2,9 +2,10 @@
 (examples/nwqn-loadest-example/nwqn-loadest-example.py:38-128,156-159).
 
 Sites are independent GPs: nothing is exchanged while fitting.  One process per GPU (torchrun); sites are
-assigned to ranks by longest-processing-time-first on the cost iterations * n^3; inside a rank several sites are
-in flight at once, each on its own libdgp handle/stream (dgp_nlml_grad_launch / _wait), so that the latency-bound
-panel steps of one site overlap the trailing updates of the others.  The only collective is the final gather.
+assigned to ranks by longest-processing-time-first on the cost iterations * n^3; inside a rank the sites are fitted in
+groups on one batch handle (dgp_batch_*): every optimiser iteration of a group is ONE launch sequence that evaluates
+NLML + gradient of all its sites, so the latency-bound panel chain is paid once per block step for the whole group.
+The only collective is the final gather.
 """
 from __future__ import annotations
 
@@ -52,6 +53,301 @@ def gather_results(local: Dict[int, dict], dist=None) -> Optional[Dict[int, dict
     return merged
 
 
+# ---------------------------------------------------------------- model kinds of a site batch
+class LoadestKind:
+    """loadest-gp sites (src/loadest_gp/models/gpytorch.py:48-128): fixed noise 0.1**2, nothing projected."""
+    name = "loadest"
+
+    def module(self, X, y, noise) -> GPModule:
+        return GPModule(loadest_spec(X.shape[1]))
+
+    def default_noise(self, n):
+        return np.full(n, LOADEST_FIXED_NOISE)
+
+    def project(self, module: GPModule, X: np.ndarray):
+        pass
+
+    def project_raw(self, raw: np.ndarray, modules, Xs):
+        pass
+
+
+class RatingKind:
+    """rating-gp gauges (src/rating_gp/models/gpytorch.py:64-79,205-372): per-point noise from the measurement
+    uncertainties plus a learned homoskedastic term, the power-law mean's random initial draws (in the reference's order:
+    a, b, c, then the gate switch point) and its in-place projection on every forward (gpytorch.py:39,259)."""
+    name = "rating"
+
+    def module(self, X, y, noise) -> GPModule:
+        from .models import rating_spec, stage_quantile_bounds
+
+        b_lo, b_hi = stage_quantile_bounds(X[:, 1])
+        a = float(torch.randn(1)); b = float(torch.randn(1) + 1.3); c = float(torch.rand(1))
+        gb = b_lo + float(torch.rand(1)) * (b_hi - b_lo)
+        gb = min(max(gb, b_lo + 1e-9 * (b_hi - b_lo)), b_hi - 1e-9 * (b_hi - b_lo))
+        return GPModule(rating_spec(b_lo, b_hi, gate_b_init=gb, pl_a=a, pl_b=b, pl_c=c))
+
+    def default_noise(self, n):
+        from .models import RATING_DEFAULT_NOISE
+
+        return np.full(n, RATING_DEFAULT_NOISE)
+
+    def project(self, module: GPModule, X: np.ndarray):
+        with torch.no_grad():
+            module.raw["powerlaw__b"].clamp_(1.2, 2.5)
+            module.raw["powerlaw__c"].clamp_(max=float(X[:, 1].min()) - 1e-6)
+
+    def project_raw(self, raw: np.ndarray, modules, Xs):
+        """The same projection on the [G, P] raw-parameter array of a group (Xs: the sites' training inputs)."""
+        ib, ic = modules[0].spec.index("powerlaw.b"), modules[0].spec.index("powerlaw.c")
+        raw[:, ib] = np.clip(raw[:, ib], 1.2, 2.5)
+        raw[:, ic] = np.minimum(raw[:, ic], np.array([float(X[:, 1].min()) - 1e-6 for X in Xs]))
+
+
+KINDS = {"loadest": LoadestKind, "rating": RatingKind}
+
+
+def _kind(model):
+    return KINDS[model]() if isinstance(model, str) else model
+
+
+def observed_variance(spec, theta: np.ndarray, var_latent: np.ndarray, fixed_noise: np.ndarray, m: int) -> np.ndarray:
+    """Variance of `likelihood(model(x))` in eval mode, as MarginalB200._model_space_predict returns it:
+    latent variance + learned noise, + the fixed training noise only when m == n_train, clamped at MIN_VARIANCE."""
+    var = np.asarray(var_latent, dtype=np.float64)
+    if spec.noise_theta >= 0:
+        var = var + theta[spec.noise_theta]
+    if m == fixed_noise.shape[0]:
+        var = var + fixed_noise
+    return np.maximum(var, MIN_VARIANCE)
+
+
+# ---------------------------------------------------------------- vectorised host step of a group of sites
+class GroupOptimizer:
+    """The reference's per-site optimiser step (discontinuum/engines/gpytorch.py:266-315,353-420) for G sites at once:
+    raw parameters, constraint / prior chain rule (GPModule.host_chain semantics), global-norm clipping at 1.0, Adam
+    (lr, betas 0.9 / 0.999, eps 1e-8, weight_decay 1e-4 added to the gradient, torch.optim.Adam's arithmetic) on [G, P]
+    numpy arrays, and one torch ReduceLROnPlateau per site (its own state machine, driven by a one-element dummy
+    optimiser whose learning rate is read back).  tests/test_multisite.py checks it against torch.optim.Adam."""
+
+    def __init__(self, modules: Sequence[GPModule], lr: float = 0.05, scheduler: bool = True, patience: int = 60,
+                 weight_decay: float = 1e-4):
+        self.modules = list(modules)
+        G, P = len(self.modules), len(self.modules[0].spec.params)
+        tabs = [m._tables() for m in self.modules]
+        self.kind, self.lb, self.lo, self.hi, self.pk, self.pa, self.pb, self.pc = (np.stack([t[k] for t in tabs]) for k in range(8))
+        self.raw = np.array([[float(r.detach()) for r in m.raw_list()] for m in self.modules], dtype=np.float64)
+        self.m = np.zeros((G, P))
+        self.v = np.zeros((G, P))
+        self.steps = np.zeros(G, dtype=np.int64)
+        self.lr = np.full(G, float(lr))
+        self.wd = float(weight_decay)
+        self.sched = None
+        if scheduler:
+            self.sched = []
+            for _ in range(G):
+                dummy = torch.optim.SGD([torch.zeros(1, requires_grad=True)], lr=float(lr))
+                self.sched.append(torch.optim.lr_scheduler.ReduceLROnPlateau(
+                    dummy, mode="min", factor=0.7, patience=max(20, patience // 2), threshold=1e-4, threshold_mode="rel",
+                    min_lr=1e-6, cooldown=10))
+
+    def pull(self, g: Optional[int] = None):
+        """raw parameters of the torch modules -> the arrays (after a projection changed them)."""
+        for k in ([g] if g is not None else range(len(self.modules))):
+            self.raw[k] = [float(r.detach()) for r in self.modules[k].raw_list()]
+
+    def push(self):
+        with torch.no_grad():
+            for k, mod in enumerate(self.modules):
+                for p, v in zip(mod.raw_list(), self.raw[k]):
+                    p.fill_(float(v))
+
+    def chain(self):
+        """(natural[G, P], d natural / d raw, sum log prior [G], d sum log prior / d natural) -- GPModule.host_chain."""
+        raw, kind = self.raw, self.kind
+        sig = 1.0 / (1.0 + np.exp(-raw))
+        sp = np.where(raw > 20.0, raw, np.log1p(np.exp(np.minimum(raw, 20.0))))
+        nat = np.where(kind == 1, sp + self.lb, np.where(kind == 2, self.lo + (self.hi - self.lo) * sig, raw))
+        dnat = np.where(kind == 1, np.where(raw > 20.0, 1.0, sig), np.where(kind == 2, (self.hi - self.lo) * sig * (1.0 - sig), 1.0))
+        pk, pa, pb, pc = self.pk, self.pa, self.pb, self.pc
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lp = np.where(pk == 1, pc - nat * nat / (2.0 * pb * pb),
+                          np.where(pk == 2, pc - (nat - pa) ** 2 / (2.0 * pb * pb),
+                                   np.where(pk == 3, pc + (pa - 1.0) * np.log(nat) - pb * nat, 0.0)))
+            dlp = np.where(pk == 1, -nat / (pb * pb),
+                           np.where(pk == 2, -(nat - pa) / (pb * pb),
+                                    np.where(pk == 3, (pa - 1.0) / nat - pb, 0.0)))
+        return nat, dnat, lp.sum(axis=1), dlp
+
+    def step(self, graw: np.ndarray, objective: np.ndarray, active: np.ndarray):
+        """clip_grad_norm_(1.0) + NaN guard + Adam + scheduler for the sites in `active` (bool [G])."""
+        g = np.array(graw, dtype=np.float64)
+        coef = 1.0 / (np.sqrt(np.sum(g * g, axis=1)) + 1e-6)
+        scale = np.where(coef >= 1.0, 1.0, coef)      # (a NaN norm scales the row to NaN, as torch's clamp does)
+        g = g * scale[:, None]
+        g = np.where(np.isnan(g).any(axis=1)[:, None], np.nan_to_num(g, nan=0.0, posinf=0.0, neginf=0.0), g)
+        a = np.asarray(active, dtype=bool)
+        b1, b2, eps = 0.9, 0.999, 1e-8
+        self.steps[a] += 1
+        g = g + self.wd * self.raw
+        m = self.m + (g - self.m) * (1.0 - b1)
+        v = self.v * b2 + (1.0 - b2) * g * g
+        t = np.maximum(self.steps, 1).astype(np.float64)
+        bc1, bc2 = 1.0 - b1 ** t, 1.0 - b2 ** t
+        denom = np.sqrt(v) / np.sqrt(bc2)[:, None] + eps
+        new = self.raw - (self.lr / bc1)[:, None] * (m / denom)
+        am = a[:, None]
+        self.m, self.v, self.raw = np.where(am, m, self.m), np.where(am, v, self.v), np.where(am, new, self.raw)
+        if self.sched is not None:
+            for k in np.nonzero(a)[0]:
+                self.sched[k].step(float(objective[k]))
+                self.lr[k] = self.sched[k].optimizer.param_groups[0]["lr"]
+
+
+@dataclass
+class _Site:
+    idx: int
+    X: np.ndarray
+    y: np.ndarray
+    noise: np.ndarray
+    module: GPModule
+    history: List[float] = field(default_factory=list)
+    failed: Optional[str] = None
+    bad_streak: int = 0
+
+
+def _groups(order: List[int], group: int) -> List[List[int]]:
+    return [order[i:i + group] for i in range(0, len(order), group)]
+
+
+def _predict_site(eng: capi.Engine, s: _Site, theta: np.ndarray, Xs: np.ndarray, res: dict):
+    """Factorise at the fitted theta (psd_safe_cholesky's jitter ladder) and predict the site's grid."""
+    eng.set_train(s.module.spec.to_c(), s.X, s.y, s.noise)
+    for jit in JITTERS:
+        _, info = eng.factorize(theta, jit)
+        if info == 0:
+            break
+    else:
+        res["failed"] = f"prediction: not positive definite after jitter {JITTERS[-1]:g} (info={info})"
+        return
+    mu, var = eng.predict(Xs)
+    res["mu"], res["var_latent"] = mu, var
+    res["var"] = observed_variance(s.module.spec, theta, var, s.noise, Xs.shape[0])
+
+
+def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int = 0, group: int = 16,
+                    predict: Optional[Dict[int, np.ndarray]] = None, lr: float = 0.05, scheduler: bool = True,
+                    patience: int = 60, model="loadest", stats: Optional[dict] = None, concurrency: Optional[int] = None,
+                    partitions: Optional[int] = None) -> Dict[int, dict]:
+    """Fit one GP per site on this rank.  sites: {index: (X, y[, noise])} in model space; model: "loadest", "rating" or a
+    kind object (see LoadestKind).  Returns {index: {"theta", "objective", "history", "failed", "n", "mu", "var",
+    "var_latent"}} ("var" follows `likelihood(model(x))` like MarginalB200.predict).
+
+    Sites are sorted by size and fitted in groups of up to `group` on ONE batch handle (capi.BatchEngine): every
+    iteration is a single launch sequence that evaluates NLML + gradient of the whole group (dgp_batch_nlml_grad), one
+    device-to-host copy of the G results, and one vectorised host step (GroupOptimizer).  The latency-bound panel chain,
+    which dominated when every site ran its own launch sequence, is paid once per block step for the group.  Evaluations
+    that fail (info != 0 or a non-finite value) climb psd_safe_cholesky's jitter ladder per site; a site whose objective
+    stays bad for more than 10 consecutive iterations is marked failed, as MarginalB200.fit gives up.
+    `concurrency` / `partitions` select the round-1 per-handle pipelines instead (fit_sites_local_per_handle)."""
+    if concurrency is not None or partitions is not None:
+        return fit_sites_local_per_handle(sites, iterations=iterations, device=device, concurrency=concurrency or 4,
+                                          predict=predict, lr=lr, scheduler=scheduler, patience=patience, partitions=partitions)
+    kind = _kind(model)
+    t_start = time.perf_counter()
+    st = {"groups": 0, "evals": 0, "gpu_eval_ms": 0.0, "predict_s": 0.0, "host_step_s": 0.0, "retries": 0}
+    results: Dict[int, dict] = {}
+    if not sites:
+        if stats is not None:
+            stats.update(st, wall_s=0.0)
+        return results
+    state: Dict[int, _Site] = {}
+    for idx in sorted(sites):   # modules are built in index order: the rating kind draws from torch's global generator
+        tup = sites[idx]
+        X, y = np.ascontiguousarray(tup[0], dtype=np.float64), np.ascontiguousarray(tup[1], dtype=np.float64)
+        noise = np.ascontiguousarray(tup[2], dtype=np.float64) if len(tup) > 2 and tup[2] is not None else kind.default_noise(y.shape[0])
+        state[idx] = _Site(idx, X, y, noise, kind.module(X, y, noise))
+    order = sorted(state, key=lambda i: (-state[i].X.shape[0], i))
+    group = max(1, min(int(group), capi.BATCH_MAX_SITES))
+    n_max = state[order[0]].X.shape[0]
+    batch = capi.BatchEngine(max_sites=min(group, len(order)), max_n=n_max, device=device) if iterations > 0 else None
+    single: Optional[capi.Engine] = None
+    try:
+        for members in _groups(order, group):
+            grp = [state[i] for i in members]
+            G = len(grp)
+            st["groups"] += 1
+            if iterations > 0:
+                batch.set_train(grp[0].module.spec.to_c(), [(s.X, s.y, s.noise) for s in grp])
+                batch.set_timing(stats is not None)
+                opt = GroupOptimizer([s.module for s in grp], lr=lr, scheduler=scheduler, patience=patience)
+                ns = np.array([s.X.shape[0] for s in grp], dtype=np.float64)
+                for _ in range(iterations):
+                    alive = np.array([s.failed is None for s in grp])
+                    if not alive.any():
+                        break
+                    kind.project_raw(opt.raw, opt.modules, [s.X for s in grp])
+                    nat, dnat, lp, dlp = opt.chain()
+                    theta = np.ascontiguousarray(nat)
+                    val, grad, info = batch.nlml_grad(theta)
+                    st["evals"] += 1
+                    if stats is not None:
+                        st["gpu_eval_ms"] += sum(batch.last_timing())
+                    bad = alive & ((info != 0) | ~np.isfinite(val))
+                    if bad.any():   # jitter ladder, per site; the others are re-evaluated unchanged and keep their numbers
+                        jit = np.zeros(G)
+                        for j in JITTERS[1:]:
+                            jit[bad] = j
+                            v2, g2, i2 = batch.nlml_grad(theta, jit)
+                            st["retries"] += 1
+                            fixed = bad & (i2 == 0) & np.isfinite(v2)
+                            val[fixed], grad[fixed], info[fixed] = v2[fixed], g2[fixed], 0
+                            bad &= ~fixed
+                            if not bad.any():
+                                break
+                    t0 = time.perf_counter()
+                    obj = (val - lp) / ns
+                    graw = (grad - dlp) * dnat / ns[:, None]
+                    ok = alive & ~bad & np.isfinite(obj)
+                    for k, s in enumerate(grp):
+                        if not alive[k]:
+                            continue
+                        if ok[k]:
+                            s.bad_streak = 0
+                            s.history.append(float(obj[k]))
+                        else:
+                            s.bad_streak += 1
+                            if s.bad_streak > 10:
+                                s.failed = f"more than 10 consecutive bad objectives (info={int(info[k])})"
+                    opt.step(np.where(ok[:, None], graw, 0.0), obj, ok)
+                    st["host_step_s"] += time.perf_counter() - t0
+                opt.push()
+            t0 = time.perf_counter()
+            for s in grp:
+                with torch.no_grad():
+                    theta = s.module.natural().numpy().astype(np.float64)
+                res = {"theta": theta, "history": s.history, "objective": s.history[-1] if s.history else None,
+                       "failed": s.failed, "n": int(s.X.shape[0])}
+                if predict is not None and s.idx in predict and s.failed is None:
+                    if single is None:
+                        single = capi.Engine(max_n=n_max, max_m=2048, device=device)
+                    kind.project(s.module, np.concatenate([s.X, predict[s.idx]], axis=0))
+                    with torch.no_grad():
+                        theta = s.module.natural().numpy().astype(np.float64)
+                    res["theta"] = theta
+                    _predict_site(single, s, theta, np.ascontiguousarray(predict[s.idx], dtype=np.float64), res)
+                results[s.idx] = res
+            st["predict_s"] += time.perf_counter() - t0
+    finally:
+        if batch is not None:
+            batch.close()
+        if single is not None:
+            single.close()
+    if stats is not None:
+        stats.update(st, wall_s=time.perf_counter() - t_start)
+    return results
+
+
+# ---------------------------------------------------------------- round-1 path: one handle and launch sequence per site
 @dataclass
 class _SiteState:
     idx: int
@@ -145,8 +441,12 @@ def _close_site(s: _SiteState, predict, pool: Optional[List[capi.Engine]] = None
             _, info = s.engine.factorize(theta, jit)
             if info == 0:
                 break
-        mu, var = s.engine.predict(predict[s.idx])
-        res["mu"], res["var"] = mu, np.maximum(var, MIN_VARIANCE)
+        else:
+            res["failed"] = f"prediction: not positive definite after jitter {JITTERS[-1]:g} (info={info})"
+        if res["failed"] is None:
+            mu, var = s.engine.predict(predict[s.idx])
+            res["mu"], res["var_latent"] = mu, var
+            res["var"] = observed_variance(s.module.spec, theta, var, s.noise, predict[s.idx].shape[0])
     if pool is not None:
         pool.append(s.engine)
     else:
@@ -154,22 +454,12 @@ def _close_site(s: _SiteState, predict, pool: Optional[List[capi.Engine]] = None
     return res
 
 
-def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int = 0, concurrency: int = 4,
-                    predict: Optional[Dict[int, np.ndarray]] = None, lr: float = 0.05, scheduler: bool = True,
-                    patience: int = 60, partitions: Optional[int] = None) -> Dict[int, dict]:
-    """Fit the loadest-gp model on every site of this rank.  sites: {index: (X, y[, noise])} in model space.
-    Returns {index: {"theta", "objective", "history", "mu", "var"}}.
-
-    `concurrency` sites are in flight at any time, each a pipeline of its own: as soon as a site's evaluation is
-    back the host does its optimiser step and enqueues its next evaluation, while the GPU works on the others; a
-    finished site is predicted, closed and replaced by the next largest one (no group barrier).  Sites are served in
-    completion order (`dgp_nlml_grad_ready`), not in a fixed round: their costs differ by up to (n_max / n_min)^3, and
-    a round would make every site advance at the pace of the largest one in flight.
-
-    partitions: split the GPU's SMs into that many disjoint partitions (`capi.partition_device`) and run one site per
-    partition (concurrency = partitions).  Sites sharing all SMs slow each other down 3-4x (the short dependent kernels
-    of one site's panel chain wait behind the long tiles of another's inverse); on its own slice a site of this size is
-    work-bound and nobody waits."""
+def fit_sites_local_per_handle(sites: Dict[int, tuple], iterations: int = 100, device: int = 0, concurrency: int = 4,
+                               predict: Optional[Dict[int, np.ndarray]] = None, lr: float = 0.05, scheduler: bool = True,
+                               patience: int = 60, partitions: Optional[int] = None) -> Dict[int, dict]:
+    """Round-1 driver, kept for comparison and as the reference of the bit-identity tests: `concurrency` loadest sites in
+    flight, each a pipeline of its own on its own libdgp handle and streams (dgp_nlml_grad_launch / _ready / _wait), served
+    in completion order; optional SM partitions (`capi.partition_device`, one site per partition)."""
     results: Dict[int, dict] = {}
     queue = sorted(sites, key=lambda i: -sites[i][0].shape[0])  # largest first: later sites fit the pooled workspaces
     active: List[_SiteState] = []
@@ -210,7 +500,8 @@ def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int 
 
 
 def fit_sites(sites: Dict[int, tuple], iterations: int = 100, predict: Optional[Dict[int, np.ndarray]] = None,
-              concurrency: int = 4, dist=None, device: int = 0) -> Optional[Dict[int, dict]]:
+              group: int = 16, dist=None, device: int = 0, model="loadest", stats: Optional[dict] = None,
+              concurrency: Optional[int] = None) -> Optional[Dict[int, dict]]:
     """Shard `sites` (every rank holds the same dict, or at least the same keys and sizes) over the ranks of
     `dist`, fit this rank's share, gather everything on rank 0."""
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
@@ -218,8 +509,9 @@ def fit_sites(sites: Dict[int, tuple], iterations: int = 100, predict: Optional[
     keys = sorted(sites)
     costs = [site_cost(sites[k][0].shape[0], iterations, predict[k].shape[0] if predict and k in predict else 0) for k in keys]
     mine = [keys[i] for i in assign_sites(costs, world)[rank]]
-    local = fit_sites_local({k: sites[k] for k in mine}, iterations=iterations, device=device, concurrency=concurrency,
-                            predict={k: predict[k] for k in mine} if predict else None)
+    local = fit_sites_local({k: sites[k] for k in mine}, iterations=iterations, device=device, group=group,
+                            predict={k: predict[k] for k in mine} if predict else None, model=model, stats=stats,
+                            concurrency=concurrency)
     return gather_results(local, dist)
 
 
@@ -264,7 +556,8 @@ def panel_owner(p: int, world: int) -> int:
     return p % world
 
 
-def sample_sharded(engine, Xs: np.ndarray, S: int, dist=None, seed: int = 0, jitter: float = 0.0, Z: Optional[np.ndarray] = None):
+def sample_sharded(engine, Xs: np.ndarray, S: int, dist=None, seed: int = 0, jitter: float = 0.0, Z: Optional[np.ndarray] = None,
+                   stats: Optional[dict] = None):
     """Exact joint posterior draws [S, m] with the m x m posterior-covariance Cholesky distributed over the ranks of
     `dist` (torch.distributed, NCCL).  Every rank holds the same training factorisation (`engine.factorize` at the same
     theta) and calls this with the same arguments; every rank returns (draws, info).
@@ -300,6 +593,11 @@ def sample_sharded(engine, Xs: np.ndarray, S: int, dist=None, seed: int = 0, jit
     def rows_below(p):
         return (mb - min((p + 1) * pw_blocks, mb)) * 128
 
+    if stats is not None:   # bytes each collective moves (payload of the buffer it is called on), for the bench line
+        stats.update(world=world, npanels=npanels, all_gather_VT_bytes=int(VT.numel()) * 8 if world > 1 else 0,
+                     all_reduce_mu_bytes=int(mu.numel()) * 8 if world > 1 else 0,
+                     broadcast_panel_bytes=sum(rows_below(p) for p in range(npanels)) * dims["panel_cols"] * 8 if world > 1 else 0,
+                     all_reduce_draws_bytes=int(Od.numel()) * 8 if world > 1 else 0)
     tok = engine.dist_begin(Xs, S, Z, seed, jitter, rank, world, VT, Od, mu)
     try:
         engine.dist_call("vt_rows", tok, rank * rpr, min((rank + 1) * rpr, dims["mpad"]))

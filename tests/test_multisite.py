@@ -56,6 +56,63 @@ def test_gather_results_world2_gloo(tmp_path):
     assert (tmp_path / "ok").exists()
 
 
+def test_group_optimizer_matches_torch_adam_clip_and_plateau():
+    """GroupOptimizer (vectorised host step of a site group) against the per-site torch objects the reference loop uses:
+    clip_grad_norm_(1.0), Adam(lr .05, wd 1e-4) and ReduceLROnPlateau, over enough steps for the scheduler to act."""
+    from discontinuum_b200.models import loadest_spec
+    from discontinuum_b200.spec import GPModule
+
+    rng = np.random.default_rng(0)
+    G, steps = 3, 130
+    mods = [GPModule(loadest_spec(2)) for _ in range(G)]
+    refs = [GPModule(loadest_spec(2)) for _ in range(G)]
+    P = len(mods[0].spec.params)
+    opt = multisite.GroupOptimizer(mods, lr=0.05, scheduler=True, patience=60)
+    topt = [torch.optim.Adam(m.raw_list(), lr=0.05, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, fused=True) for m in refs]
+    tsch = [torch.optim.lr_scheduler.ReduceLROnPlateau(o, mode="min", factor=0.7, patience=30, threshold=1e-4,
+                                                       threshold_mode="rel", min_lr=1e-6, cooldown=10) for o in topt]
+    for t in range(steps):
+        g = rng.standard_normal((G, P)) * np.array([0.01, 1.0, 30.0])[:, None]   # below / around / far above the clip norm
+        obj = np.array([1.0 / (1 + t), 1.0, 1.0 + 0.5 * np.sin(t)])               # improving / flat (plateau) / noisy
+        active = np.array([True, True, t % 7 != 3])                              # site 2 skips some iterations
+        nat, dnat, lp, dlp = opt.chain()
+        for k in range(G):
+            n2, d2, l2, dl2 = refs[k].host_chain()
+            assert np.max(np.abs(nat[k] - n2)) <= 1e-13 and np.max(np.abs(dnat[k] - d2)) <= 1e-13
+            assert abs(lp[k] - l2) <= 1e-12 * max(1.0, abs(l2)) and np.max(np.abs(dlp[k] - dl2)) <= 1e-12 * max(1.0, np.max(np.abs(dl2)))
+        opt.step(g, obj, active)
+        for k in range(G):
+            if not active[k]:
+                continue
+            gk = g[k].copy()
+            coef = 1.0 / (float(np.sqrt(np.sum(gk * gk))) + 1e-6)
+            if not coef >= 1.0:
+                gk = gk * coef
+            for p, gv in zip(refs[k].raw_list(), gk):
+                p.grad = torch.tensor([gv], dtype=torch.float64)
+            topt[k].step()
+            tsch[k].step(float(obj[k]))
+        want = np.array([[float(r.detach()) for r in m.raw_list()] for m in refs])
+        assert np.max(np.abs(opt.raw - want)) <= 1e-12, (t, np.max(np.abs(opt.raw - want)))
+        assert np.allclose(opt.lr, [o.param_groups[0]["lr"] for o in topt], rtol=0, atol=0)
+    assert opt.lr[1] < 0.05 and opt.lr[0] == 0.05  # the flat objective did trigger the plateau scheduler
+    opt.push()
+    assert all(float(a.detach()) == float(b_) for a, b_ in zip(mods[1].raw_list(), opt.raw[1]))
+
+
+def test_observed_variance_rule():
+    """likelihood(model(x)) in eval mode: + learned noise always, + fixed noise only when m == n, clamp."""
+    from discontinuum_b200.models import loadest_spec, rating_spec
+
+    lat = np.array([1e-12, 0.5, 0.2])
+    fixed = np.full(3, 0.01)
+    th = np.arange(20) * 0.01
+    assert np.array_equal(multisite.observed_variance(loadest_spec(2), th, lat, fixed, 3), np.maximum(lat + fixed, 1e-10))
+    assert np.array_equal(multisite.observed_variance(loadest_spec(2), th, lat[:2], fixed, 2), np.maximum(lat[:2], 1e-10))
+    rs = rating_spec(1.0, 2.0)
+    assert np.allclose(multisite.observed_variance(rs, th, lat[:2], fixed, 2), lat[:2] + th[rs.noise_theta])
+
+
 class _FakeEngine:
     """Stands in for capi.Engine on the CPU: 'predicts' a known function of the inputs."""
 
@@ -94,14 +151,50 @@ def test_concurrent_sites_match_single_site_fits(cuda_device):
 
     sites = {i: synthetic.loadest_site(n, 1000 + i)[:2] for i, n in enumerate((300, 450, 700))}
     grid = {i: synthetic.daily_grid(sites[i][0], 200) for i in sites}
-    res = multisite.fit_sites(sites, iterations=8, predict=grid, concurrency=3)
-    assert sorted(res) == [0, 1, 2]
+    res = multisite.fit_sites(sites, iterations=8, predict=grid, concurrency=3)   # per-handle pipelines (round 1)
+    stats = {}
+    resb = multisite.fit_sites(sites, iterations=8, predict=grid, group=2, stats=stats)  # batched groups: (700, 450), (300)
+    assert sorted(res) == [0, 1, 2] and sorted(resb) == [0, 1, 2]
+    assert stats["groups"] == 2 and stats["evals"] == 16 and stats["gpu_eval_ms"] > 0
     for i, (X, y) in sites.items():
         raw = orc.loadest_init_raw()
         _, hist = orc.fit_adam("loadest", raw, torch.tensor(X), torch.tensor(y), orc.loadest_noise(X.shape[0]), iterations=8)
+        for r in (res, resb):
+            assert r[i]["failed"] is None
+            assert np.max(np.abs(np.array(r[i]["history"]) - np.array(hist)) / np.abs(hist)) <= 1e-6
+            assert r[i]["mu"].shape == (200,) and np.all(r[i]["var"] > 0)
+        # the batched groups reproduce the per-handle fits (same evaluations bit for bit, host step equal to rounding)
+        assert np.max(np.abs(np.array(resb[i]["history"]) - np.array(res[i]["history"]))) <= 1e-12
+        assert np.max(np.abs(resb[i]["theta"] - res[i]["theta"])) <= 1e-11
+        assert np.max(np.abs(resb[i]["mu"] - res[i]["mu"])) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_rating_gauges_through_the_batch_driver(cuda_device):
+    """Four rating-gp gauges (the per-gauge loop of docs/source/notebooks/rating-gp-demo.ipynb cell 18; model
+    rating_gp/models/gpytorch.py:64-79) fitted as one group: objective trajectories equal the oracle's restatement of
+    the reference loop with the same random initial draws, per-point noise and per-iteration projection."""
+    from discontinuum_b200 import models, synthetic
+    from helpers import orc
+
+    ns = (150, 260, 200, 330)
+    sites = {i: synthetic.rating_gauge(n, 20 + i) for i, n in enumerate(ns)}
+    grids = {i: synthetic.daily_grid(sites[i][0], 120) for i in sites}
+    torch.manual_seed(0)
+    res = multisite.fit_sites(sites, iterations=8, predict=grids, model="rating", group=4)
+    torch.manual_seed(0)
+    for i in sorted(sites):
+        X, y, noise = sites[i]
+        a = float(torch.randn(1)); b = float(torch.randn(1) + 1.3); c = float(torch.rand(1)); u = float(torch.rand(1))
+        b_lo, b_hi = models.stage_quantile_bounds(X[:, 1])
+        raw = orc.rating_init_raw(b_lo, b_hi, gate_b=b_lo + u * (b_hi - b_lo), pl_a=a, pl_b=b, pl_c=c)
+        _, hist = orc.fit_adam("rating", raw, torch.tensor(X), torch.tensor(y), torch.tensor(noise), iterations=8,
+                               b_lo=b_lo, b_hi=b_hi, h_min=float(X[:, 1].min()))
         assert res[i]["failed"] is None
         assert np.max(np.abs(np.array(res[i]["history"]) - np.array(hist)) / np.abs(hist)) <= 1e-6
-        assert res[i]["mu"].shape == (200,) and np.all(res[i]["var"] > 0)
+        spec = models.rating_spec(b_lo, b_hi)
+        assert np.all(res[i]["var"] >= res[i]["var_latent"] + res[i]["theta"][spec.noise_theta] - 1e-15)
+        assert res[i]["mu"].shape == (120,) and np.all(np.isfinite(res[i]["mu"]))
 
 
 @pytest.mark.gpu
@@ -109,8 +202,8 @@ def test_sites_on_sm_partitions_match_shared_gpu(cuda_device):
     from discontinuum_b200 import synthetic
 
     sites = {i: synthetic.loadest_site(n, 1100 + i)[:2] for i, n in enumerate((500, 260, 380, 640))}
-    shared = multisite.fit_sites_local(sites, iterations=6, concurrency=2)
-    split = multisite.fit_sites_local(sites, iterations=6, partitions=2)
+    shared = multisite.fit_sites_local_per_handle(sites, iterations=6, concurrency=2)
+    split = multisite.fit_sites_local_per_handle(sites, iterations=6, partitions=2)
     for i in sites:
         assert split[i]["failed"] is None
         assert np.max(np.abs(np.array(split[i]["history"]) - np.array(shared[i]["history"]))) <= 1e-9
