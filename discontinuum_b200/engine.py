@@ -8,15 +8,17 @@ ReduceLROnPlateau, clipping, NaN guards, early stopping: gpytorch.py:266-444), c
 """
 from __future__ import annotations
 
+import dataclasses
 import functools
 import math
+import warnings
 from dataclasses import dataclass
 from typing import Callable, Optional
 
 import numpy as np
 import torch
 
-from . import capi
+from . import capi, checkpoint
 from .data import DataManager, LogErrorPipeline, LogStandardPipeline, StandardErrorPipeline, StandardPipeline
 from .spec import CovSpec, GPModule
 
@@ -118,7 +120,7 @@ class MarginalB200:
     # ------------------------------------------------------------------ engine plumbing
     def _bind_engine(self):
         n = self.X.shape[0]
-        if self._engine is None or self._engine.max_n < n:
+        if self._engine is None or self._engine.max_n < n or self._engine.max_m < self.max_predict_chunk:
             if self._engine is not None:
                 self._engine.close()
             self._engine = capi.Engine(max_n=n, max_m=self.max_predict_chunk, device=self.device_index)
@@ -136,7 +138,12 @@ class MarginalB200:
                 penalty_val = penalty_callback()
                 if not torch.is_tensor(penalty_val):
                     penalty_val = None
-            except Exception:  # noqa: BLE001
+            except capi.DgpError:
+                raise  # bad argument / CUDA error: not a numerical failure of this iteration
+            except Exception as exc:  # noqa: BLE001
+                if not getattr(self, "_penalty_warned", False):
+                    warnings.warn(f"penalty callback failed ({exc!r}); training continues without the penalty term", stacklevel=2)
+                    self._penalty_warned = True
                 penalty_val = None
         objective = nll if penalty_val is None else nll + float(penalty_weight) * penalty_val
         return objective, penalty_val
@@ -172,8 +179,9 @@ class MarginalB200:
             scheduler = getattr(self, "_last_scheduler", None)
         if not hasattr(self, "model"):
             raise RuntimeError("No model to save. Call fit() first.")
-        sd = self.model.state_dict()
-        lik = {k: v for k, v in sd.items() if "likelihood" in k}
+        # model_state_dict / likelihood_state_dict carry the reference's gpytorch key names and shapes (checkpoint.py)
+        sd, lik = checkpoint.to_reference_state(self.model)
+        cfg = getattr(self, "model_config", None)
         ckpt = {
             "model_class": f"{self.__class__.__module__}.{self.__class__.__name__}",
             "model_state_dict": sd,
@@ -184,15 +192,16 @@ class MarginalB200:
             "scheduler_state_dict": scheduler.state_dict() if scheduler is not None else None,
             "scheduler_name": scheduler.__class__.__name__ if scheduler is not None else None,
             "current_iteration": getattr(self, "_current_iteration", 0),
-            "model_config": getattr(self, "model_config", None),
+            "model_config": dataclasses.asdict(cfg) if dataclasses.is_dataclass(cfg) else cfg,  # plain dict: loads under weights_only
             "extra": extra or {},
         }
         torch.save(ckpt, f)
 
     @classmethod
     def load(cls, f, covariates, target, target_unc=None):
-        ckpt = torch.load(f, map_location="cpu", weights_only=False)
-        model = cls()
+        ckpt = torch.load(f, map_location="cpu", weights_only=True)  # tensors, numbers, strings and dicts only: no pickled code
+        cfg = ckpt.get("model_config")
+        model = cls(ModelConfig(**cfg)) if isinstance(cfg, dict) and cfg else cls()
         model.dm.fit(target=target, covariates=covariates, target_unc=target_unc)
         model.X, model.y = model.dm.X, model.dm.y
         if target_unc is None:
@@ -200,7 +209,8 @@ class MarginalB200:
         else:
             model.y_unc = model.dm.y_unc
             model.model = model.build_model(model.X, model.y, model.y_unc)
-        model.model.load_state_dict(ckpt["model_state_dict"])
+        # reference-named state dicts (from MarginalB200.save or from the reference's MarginalGPyTorch.save) or round-1 native ones
+        checkpoint.load_state(model.model, ckpt["model_state_dict"], ckpt.get("likelihood_state_dict"))
         model._resume_info = {k: ckpt.get(k) for k in ("optimizer_state_dict", "optimizer_name", "optimizer_lr",
                                                        "scheduler_state_dict", "scheduler_name")}
         model._resume_info["current_iteration"] = ckpt.get("current_iteration", 0)
@@ -282,6 +292,8 @@ class MarginalB200:
                     else:
                         objective, penalty_val = self._objective(penalty_callback, penalty_weight)
                         obj_value = float(objective.item())
+                except capi.DgpError:
+                    raise  # rc < 0 from libdgp (bad argument / CUDA error, possibly sticky): never a "NaN iteration"
                 except Exception:
                     nan_loss_counter += 1
                     if nan_loss_counter > 10:

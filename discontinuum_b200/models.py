@@ -205,6 +205,8 @@ class RatingGPMarginalB200(RatingDataMixin, MarginalB200):
             return super().fit(covariates=covariates, target=target, target_unc=target_unc, iterations=iterations,
                                optimizer=optimizer, learning_rate=learning_rate, early_stopping=early_stopping,
                                patience=patience, scheduler=scheduler, resume=resume, **kw)
+        # dgp_mean_functional_grad takes the 2 x grid_size penalty points in one prediction chunk
+        self.max_predict_chunk = max(self.max_predict_chunk, -(-2 * int(grid_size) // 128) * 128)
         step = {"i": 0}
 
         def penalty_callback():

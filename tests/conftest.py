@@ -14,9 +14,12 @@ def pytest_configure(config):
 
 
 @pytest.fixture(scope="session")
-def cuda_device():
+def cuda_device(request):
     import torch
 
     if not torch.cuda.is_available():
-        pytest.fail("GPU test selected but no CUDA device is visible")
+        expr = request.config.getoption("markexpr", default="") or ""
+        if "gpu" in expr and "not gpu" not in expr:   # `-m gpu` was asked for explicitly: a missing device is a failure
+            pytest.fail("GPU tests selected (-m gpu) but no CUDA device is visible")
+        pytest.skip("needs a CUDA device (run with -m gpu on the GPU box)")
     return 0

@@ -239,3 +239,67 @@ def test_xarray_adapter_branches_with_stand_in(monkeypatch):
     assert list(placed.coords) == ["time"] and np.array_equal(placed.coords["time"].values, time)
     assert isinstance(b.dm.y_t(b.dm.y), np.ndarray)  # numpy in, numpy out
 
+
+
+def test_checkpoint_keys_follow_the_reference_module_tree():
+    """engine.save writes the gpytorch key names / shapes of the reference's modules (loadest_gp/models/gpytorch.py:61-128,
+    rating_gp/models/gpytorch.py:205-372; engines/gpytorch.py:147-160) and load reads a reference-format state dict."""
+    from discontinuum_b200 import checkpoint
+
+    m = spec.GPModule(models.loadest_spec(3))
+    with torch.no_grad():
+        for k, p in enumerate(m.raw_list()):
+            p.fill_(0.1 * (k + 1))
+    sd, lik = checkpoint.to_reference_state(m)
+    assert lik == {}
+    assert set(sd) == {"mean_module.raw_constant", "covar_module.kernels.0.raw_outputscale",
+                       "covar_module.kernels.0.base_kernel.kernels.0.raw_lengthscale",
+                       "covar_module.kernels.0.base_kernel.kernels.0.raw_period_length",
+                       "covar_module.kernels.0.base_kernel.kernels.1.raw_lengthscale", "covar_module.kernels.1.raw_outputscale",
+                       "covar_module.kernels.1.base_kernel.raw_lengthscale", "covar_module.kernels.2.raw_outputscale",
+                       "covar_module.kernels.2.base_kernel.raw_lengthscale"}
+    assert sd["covar_module.kernels.1.base_kernel.raw_lengthscale"].shape == (1, 2)   # ARD over the two covariates
+    assert sd["covar_module.kernels.2.base_kernel.raw_lengthscale"].shape == (1, 3)
+    assert sd["covar_module.kernels.0.raw_outputscale"].shape == () and sd["mean_module.raw_constant"].shape == ()
+    # a reference-written checkpoint also holds constraint / prior buffers and may use the nested (A + B) + C layout
+    ref = dict(sd)
+    ref["covar_module.kernels.0.raw_outputscale_constraint.lower_bound"] = torch.tensor(0.0)
+    ref["covar_module.kernels.0.outputscale_prior.scale"] = torch.tensor(1.0)
+    m2 = spec.GPModule(models.loadest_spec(3))
+    checkpoint.load_state(m2, ref, {})
+    assert all(float(a.detach()) == float(b.detach()) for a, b in zip(m.raw_list(), m2.raw_list()))
+    nested = {}
+    for k, v in sd.items():
+        for flat, nest in (("covar_module.kernels.0.", "covar_module.kernels.0.kernels.0."),
+                           ("covar_module.kernels.1.", "covar_module.kernels.0.kernels.1."),
+                           ("covar_module.kernels.2.", "covar_module.kernels.1.")):
+            if k.startswith(flat):
+                k = nest + k[len(flat):]
+                break
+        nested[k] = v
+    m3 = spec.GPModule(models.loadest_spec(3))
+    checkpoint.load_state(m3, nested)
+    assert all(float(a.detach()) == float(b.detach()) for a, b in zip(m.raw_list(), m3.raw_list()))
+    # round-1 native layout still loads; a foreign state dict fails with the missing key named
+    m4 = spec.GPModule(models.loadest_spec(3))
+    checkpoint.load_state(m4, m.state_dict())
+    assert all(float(a.detach()) == float(b.detach()) for a, b in zip(m.raw_list(), m4.raw_list()))
+    with pytest.raises(KeyError, match="raw_period_length"):
+        checkpoint.load_state(m4, {k: v for k, v in sd.items() if "period" not in k})
+
+    r = spec.GPModule(models.rating_spec(1.1, 1.8))
+    with torch.no_grad():
+        for k, p in enumerate(r.raw_list()):
+            p.fill_(-0.3 + 0.07 * k)
+    rsd, rlik = checkpoint.to_reference_state(r)
+    assert set(rlik) == {"second_noise_covar.raw_noise"} and rlik["second_noise_covar.raw_noise"].shape == (1,)
+    assert {"powerlaw.a", "powerlaw.b", "powerlaw.c", "likelihood.second_noise_covar.raw_noise",
+            "covar_module.kernels.0.kernels.0.raw_b", "covar_module.kernels.1.kernels.0.sigmoid_kernel.raw_b",
+            "covar_module.kernels.0.kernels.1.base_kernel.kernels.1.base_kernel.kernels.1.raw_lengthscale",
+            "covar_module.kernels.1.kernels.1.base_kernel.raw_outputscale",
+            "covar_module.kernels.2.base_kernel.kernels.1.base_kernel.kernels.0.raw_period_length"} <= set(rsd)
+    assert len(rsd) == 20 + 2   # 20 parameters + the two extra registrations of the shared gate switch point
+    r2 = spec.GPModule(models.rating_spec(1.1, 1.8))
+    model_only = {k: v for k, v in rsd.items() if not k.startswith("likelihood.")}
+    checkpoint.load_state(r2, model_only, rlik)   # learned noise taken from the likelihood state dict
+    assert all(float(a.detach()) == float(b.detach()) for a, b in zip(r.raw_list(), r2.raw_list()))
