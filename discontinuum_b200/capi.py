@@ -70,6 +70,7 @@ _SIGNATURES = [
     ("dgp_mean_functional_grad", C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     ("dgp_sample", C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_double, _P, C.c_int]),
     ("dgp_sample_ex", C.c_int, [_P, _P, C.c_int, _P, C.c_ulonglong, C.c_int, C.c_double, C.POINTER(DgpFluxReduce), _P, C.c_int]),
+    ("dgp_reserve", C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     ("dgp_dist_dims", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     ("dgp_dist_begin", C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_ulonglong, C.c_double, C.c_int, C.c_int, _P, _P, _P, C.POINTER(_P)]),
     ("dgp_dist_vt_rows", C.c_int, [_P, C.c_int, C.c_int]),
@@ -428,6 +429,10 @@ class Engine:
         info = self._check(self.lib.dgp_sample_ex(self._h, Xs.ctypes.data, m, zp, int(seed), int(S), float(jitter),
                                                   C.byref(red) if red is not None else None, out.ctypes.data, 0), "dgp_sample_ex")
         return out, info
+
+    def reserve(self, max_m_sample: int, max_S: int = 1, max_groups: int = 0):
+        """Size the sampling workspace ahead of time (sample / sample_ex / dist_* then allocate nothing); 0 releases it."""
+        self._check(self.lib.dgp_reserve(self._h, int(max_m_sample), int(max_S), int(max_groups)), "dgp_reserve")
 
     # -- distributed sampling primitives (multisite.sample_sharded drives them)
     def dist_dims(self, m: int, S: int, world: int) -> dict:

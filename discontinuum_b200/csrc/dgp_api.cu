@@ -100,6 +100,10 @@ struct dgp_handle_s {
   double *cvec = nullptr, *vvec = nullptr, *gam = nullptr, *tmpz = nullptr, *mfg_out = nullptr, *wpart = nullptr;
   double* h_mfg = nullptr;
   size_t wpart_count = 0;
+  // m-sized workspace of dgp_sample_ex / dgp_dist_begin: one grow-only arena (dgp_reserve sizes it ahead of time, so that the
+  // calls themselves allocate nothing; a call that needs more than was reserved grows it once and keeps it)
+  double* arena = nullptr;
+  size_t arena_count = 0;
   // prediction chunk
   double *Kx = nullptr, *Xs = nullptr, *Xws = nullptr, *means = nullptr, *dot = nullptr, *vpart = nullptr;
   double *mu = nullptr, *var = nullptr;
@@ -283,6 +287,8 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
   acc(A(&h->theta, DGP_MAX_THETA)); acc(A(&h->scal, SC_SIZE)); acc(A(&h->gpart, nbm * (nbm + 1) * DGP_MAX_THETA));
   acc(A(&h->zpart, nbm * np));
   acc(A(&h->cvec, mc)); acc(A(&h->vvec, np)); acc(A(&h->gam, np)); acc(A(&h->tmpz, np)); acc(A(&h->mfg_out, 1 + DGP_MAX_THETA));
+  h->wpart_count = (mc / 128 + nbm) * (np / 64) * DGP_MAX_THETA;  // dgp_mean_functional_grad partials at the largest m, n
+  acc(A(&h->wpart, h->wpart_count));
   acc(cudaMallocHost((void**)&h->h_mfg, (1 + DGP_MAX_THETA) * sizeof(double)));
   acc(A(&h->Kx, mc * np)); acc(A(&h->Xs, mc * DGP_MAX_COLS)); acc(A(&h->Xws, mc * DGP_XS)); acc(A(&h->means, mc));
   acc(A(&h->dot, nbm * mc)); acc(A(&h->vpart, 2 * nbm * mc)); acc(A(&h->mu, mc)); acc(A(&h->var, mc));
@@ -382,6 +388,7 @@ int dgp_destroy(dgp_handle h) {
   double* bufs[] = {h->bufA, h->bufL, h->bufU, h->DI, h->X, h->y, h->noise, h->Xw, h->r, h->z, h->alpha, h->theta,
                     h->scal, h->gpart, h->zpart, h->cvec, h->vvec, h->gam, h->tmpz, h->mfg_out, h->wpart, h->Kx, h->Xs, h->Xws, h->means, h->dot, h->vpart, h->mu, h->var};
   for (double* p : bufs) if (p) cudaFree(p);
+  if (h->arena) cudaFree(h->arena);
   if (h->h_theta) cudaFreeHost(h->h_theta);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->h_mfg) cudaFreeHost(h->h_mfg);
@@ -981,12 +988,7 @@ int dgp_mean_functional_grad(dgp_handle h, const double* Xs, int m, const double
   int rc;
   const int mpad = round_up(m, 128), npad = h->npad, nb = h->nb;
   const size_t nparts = (size_t)(mpad / 128 + nb) * (npad / 64);
-  if (h->wpart_count < nparts * DGP_MAX_THETA) {
-    if (h->wpart) cudaFree(h->wpart);
-    h->wpart = nullptr; h->wpart_count = 0;
-    CK(h, cudaMalloc((void**)&h->wpart, nparts * DGP_MAX_THETA * sizeof(double)));
-    h->wpart_count = nparts * DGP_MAX_THETA;
-  }
+  if (h->wpart_count < nparts * DGP_MAX_THETA) DGP_FAIL(h, -1, "dgp_mean_functional_grad: partials workspace too small (internal)");
   cudaStream_t st = h->stream;
   if ((rc = stage_xs(h, Xs, 0, m, 0))) return rc;
   CK(h, cudaMemsetAsync(h->cvec, 0, (size_t)mpad * 8, st));
@@ -1022,6 +1024,53 @@ int dgp_mean_functional_grad(dgp_handle h, const double* Xs, int m, const double
 //   Sigma* lower tiles = cov tile(x*_i, x*_j) - V'[i, :] V'[j, :]'   (covariance tile generated as accumulator init)
 //   Lpost by the same blocked Cholesky as the training factorisation
 //   out [S, m] = Z [S, m] Lpost'     (triangular k range) + mu
+// bump allocation out of the handle's arena (256-byte granules)
+struct ArenaCarver {
+  double* base; size_t used = 0;
+  explicit ArenaCarver(double* b) : base(b) {}
+  double* take(size_t count) { double* p = base ? base + used : nullptr; used += (count + 31) / 32 * 32; return p; }
+};
+// doubles dgp_sample_ex(m, S, ngroups) / dgp_dist_begin(m, S) carve for a training set padded to npad (nb blocks)
+static size_t sample_arena_count(size_t mpad, size_t Spad, size_t npad, size_t nb, size_t S, size_t ngroups, bool dist) {
+  ArenaCarver c(nullptr);
+  c.take(mpad * DGP_MAX_COLS); c.take(mpad * DGP_XS); c.take(mpad); c.take(nb * mpad);
+  if (!dist) { c.take(mpad); c.take(mpad * npad); }
+  c.take(mpad * mpad); c.take(mpad * 128); c.take(mpad * 128); c.take(Spad * mpad);
+  if (!dist) c.take(Spad * mpad);
+  c.take(mpad); c.take(SC_SIZE);
+  if (ngroups) { c.take(mpad); c.take(S * ngroups); c.take((ngroups + 2) / 2 + 1); }
+  return c.used;
+}
+static int ensure_arena(dgp_handle h, size_t count) {
+  if (h->arena_count >= count) return 0;
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (h->arena) cudaFree(h->arena);
+  h->arena = nullptr; h->arena_count = 0;
+  cudaError_t e = cudaMalloc((void**)&h->arena, count * sizeof(double));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    DGP_FAIL(h, -2, "workspace allocation of %.1f GB failed: %s", (double)count * 8e-9, cudaGetErrorString(e));
+  }
+  h->arena_count = count;
+  return 0;
+}
+
+int dgp_reserve(dgp_handle h, int max_m_sample, int max_S, int max_groups) {
+  if (!h) return -1;
+  if (max_m_sample < 0 || max_S < 0 || max_groups < 0) DGP_FAIL(h, -1, "dgp_reserve: bad arguments");
+  CK(h, cudaSetDevice(h->device));
+  if (max_m_sample == 0) {  // release
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->arena) cudaFree(h->arena);
+    h->arena = nullptr; h->arena_count = 0;
+    return 0;
+  }
+  const size_t mpad = round_up(max_m_sample, 128), Spad = round_up(max_S > 0 ? max_S : 1, 128), npad = h->max_pad, nb = npad / 128;
+  const size_t a = sample_arena_count(mpad, Spad, npad, nb, (size_t)(max_S > 0 ? max_S : 1), (size_t)max_groups, false);
+  const size_t b = sample_arena_count(mpad, Spad, npad, nb, 0, 0, true);
+  return ensure_arena(h, a > b ? a : b);
+}
+
 int dgp_sample(dgp_handle h, const double* Xs, int m, const double* Z, int S, double jitter, double* out, int on_device) {
   if (!h) return -1;
   if (!Z) DGP_FAIL(h, -1, "dgp_sample: Z is NULL (use dgp_sample_ex for device-generated normals)");
@@ -1043,33 +1092,22 @@ int dgp_sample_ex(dgp_handle h, const double* Xs, int m, const double* Z, unsign
   const int mpad = round_up(m, 128), Spad = round_up(S, 128), npad = h->npad, mb = mpad / 128;
   const cudaMemcpyKind ikind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const cudaMemcpyKind okind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  // m-sized work buffers, allocated per call: V' (m x n), Sigma* (m x m, factorised in place), the panel staging
-  // buffer and block inverses of that factorisation, Z and the draws.  The cross covariance goes through the
-  // handle's prediction chunk, so the footprint is 8 (m n + m^2) B + O(m): 106 GB at m = 100k, n = 32k.
-  double *Xsd = nullptr, *Xws = nullptr, *means = nullptr, *dot = nullptr, *mu = nullptr, *VT = nullptr;
-  double *Sig = nullptr, *Pb = nullptr, *DI2 = nullptr, *Zd = nullptr, *Od = nullptr, *zero = nullptr, *scal2 = nullptr;
+  // m-sized work buffers, carved out of the handle's arena (dgp_reserve sizes it ahead of time; otherwise it grows here,
+  // once, and stays): V' (m x n), Sigma* (m x m, factorised in place), the panel staging buffer and block inverses of that
+  // factorisation, Z and the draws.  The cross covariance goes through the handle's prediction chunk, so the footprint is
+  // 8 (m n + m^2) B + O(m): 106 GB at m = 100k, n = 32k.
+  {
+    int rca = ensure_arena(h, sample_arena_count(mpad, Spad, npad, h->nb, S, red ? red->ngroups : 0, false));
+    if (rca) return rca;
+  }
+  ArenaCarver ar(h->arena);
+  double* Xsd = ar.take((size_t)mpad * DGP_MAX_COLS); double* Xws = ar.take((size_t)mpad * DGP_XS); double* means = ar.take(mpad);
+  double* dot = ar.take((size_t)h->nb * mpad); double* mu = ar.take(mpad); double* VT = ar.take((size_t)mpad * npad);
+  double* Sig = ar.take((size_t)mpad * mpad); double* Pb = ar.take((size_t)mpad * 128); double* DI2 = ar.take((size_t)mpad * 128);
+  double* Zd = ar.take((size_t)Spad * mpad); double* Od = ar.take((size_t)Spad * mpad); double* zero = ar.take(mpad);
+  double* scal2 = ar.take(SC_SIZE);
   double *wd = nullptr, *gout = nullptr, *gstart = nullptr;
-  struct Freer {
-    double** p[18]; int k = 0;
-    ~Freer() { for (int i = 0; i < k; i++) if (*p[i]) cudaFree(*p[i]); }
-  } fr;
-  auto A = [&](double** p, size_t count) {
-    fr.p[fr.k++] = p;
-    return cudaMalloc((void**)p, count * sizeof(double));
-  };
-  cudaError_t r = cudaSuccess;
-  auto acc = [&](cudaError_t x) { if (r == cudaSuccess) r = x; };
-  acc(A(&Xsd, (size_t)mpad * DGP_MAX_COLS)); acc(A(&Xws, (size_t)mpad * DGP_XS)); acc(A(&means, mpad));
-  acc(A(&dot, (size_t)h->nb * mpad)); acc(A(&mu, mpad)); acc(A(&VT, (size_t)mpad * npad));
-  acc(A(&Sig, (size_t)mpad * mpad)); acc(A(&Pb, (size_t)mpad * 128)); acc(A(&DI2, (size_t)mpad * 128));
-  acc(A(&Zd, (size_t)Spad * mpad)); acc(A(&Od, (size_t)Spad * mpad)); acc(A(&zero, mpad)); acc(A(&scal2, SC_SIZE));
-  if (red) {
-    acc(A(&wd, mpad)); acc(A(&gout, (size_t)S * red->ngroups)); acc(A(&gstart, (size_t)(red->ngroups + 2) / 2 + 1));
-  }
-  if (r != cudaSuccess) {
-    cudaGetLastError();
-    DGP_FAIL(h, -2, "dgp_sample: workspace allocation failed for m=%d, S=%d: %s", m, S, cudaGetErrorString(r));
-  }
+  if (red) { wd = ar.take(mpad); gout = ar.take((size_t)S * red->ngroups); gstart = ar.take((size_t)(red->ngroups + 2) / 2 + 1); }
   int rc;
   CK(h, cudaMemsetAsync(zero, 0, (size_t)mpad * 8, h->stream));
   CK(h, cudaMemsetAsync(scal2, 0, SC_SIZE * 8, h->stream));
@@ -1187,16 +1225,14 @@ int dgp_dist_begin(dgp_handle h, const double* Xs, int m, int S, const double* Z
   d->pw = h->panel_blocks; d->npanels = (d->mb + d->pw - 1) / d->pw; d->rank = rank; d->world = world; d->jitter = jitter;
   d->VT = VT; d->Od = Od; d->mu = mu;
   const size_t mpad = d->mpad;
-  cudaError_t r = cudaSuccess;
-  auto A = [&](double** p, size_t count) { if (r == cudaSuccess) r = cudaMalloc((void**)p, count * sizeof(double)); };
-  A(&d->Xsd, mpad * DGP_MAX_COLS); A(&d->Xws, mpad * DGP_XS); A(&d->means, mpad); A(&d->dot, (size_t)h->nb * mpad);
-  A(&d->Sig, mpad * mpad); A(&d->Pb, mpad * 128); A(&d->DI2, mpad * 128); A(&d->Zd, (size_t)d->Spad * mpad);
-  A(&d->zero, mpad); A(&d->scal2, SC_SIZE);
-  if (r != cudaSuccess) {
-    cudaGetLastError();
-    dgp_dist_end(d);
-    DGP_FAIL(h, -2, "dgp_dist_begin: workspace allocation failed for m=%d: %s", m, cudaGetErrorString(r));
+  {
+    int rca = ensure_arena(h, sample_arena_count(mpad, d->Spad, h->npad, h->nb, 0, 0, true));
+    if (rca) { delete d; return rca; }
   }
+  ArenaCarver ar(h->arena);
+  d->Xsd = ar.take(mpad * DGP_MAX_COLS); d->Xws = ar.take(mpad * DGP_XS); d->means = ar.take(mpad); d->dot = ar.take((size_t)h->nb * mpad);
+  d->Sig = ar.take(mpad * mpad); d->Pb = ar.take(mpad * 128); d->DI2 = ar.take(mpad * 128); d->Zd = ar.take((size_t)d->Spad * mpad);
+  d->zero = ar.take(mpad); d->scal2 = ar.take(SC_SIZE);
   cudaStream_t st = h->stream;
   int rc;
   CK(h, cudaMemsetAsync(d->zero, 0, mpad * 8, st));
@@ -1224,9 +1260,7 @@ int dgp_dist_begin(dgp_handle h, const double* Xs, int m, int S, const double* Z
 int dgp_dist_end(dgp_dist d) {
   if (!d) return 0;
   if (d->h) { cudaSetDevice(d->h->device); cudaStreamSynchronize(d->h->stream); }
-  double* bufs[] = {d->Xsd, d->Xws, d->means, d->dot, d->Sig, d->Pb, d->DI2, d->Zd, d->zero, d->scal2};
-  for (double* p : bufs) if (p) cudaFree(p);
-  delete d;
+  delete d;  // its buffers live in the handle's arena
   return 0;
 }
 

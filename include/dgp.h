@@ -181,6 +181,11 @@ typedef struct {
 int dgp_sample_ex(dgp_handle h, const double* Xs, int m, const double* Z, unsigned long long seed, int S,
                   double jitter, const dgp_flux_reduce* red, double* out, int on_device);
 
+/* Workspace of dgp_sample / dgp_sample_ex / dgp_dist_*: sized ahead of time for grids of up to max_m_sample points, max_S
+ * draws and max_groups flux groups, so that those calls allocate nothing (8 (m n + m^2) B + O(m)).  Without it the first
+ * call that needs more grows the workspace once and keeps it.  max_m_sample = 0 releases it. */
+int dgp_reserve(dgp_handle h, int max_m_sample, int max_S, int max_groups);
+
 /* Distributed joint posterior sampling: the per-rank half of a panel-cyclic Cholesky of the m x m posterior covariance
  * (the exchange step of SURVEY 8e).  Panel p (panel_cols / 128 block columns) belongs to rank p mod world.  The caller
  * owns the collectives and the exchanged DEVICE buffers (row-major float64):
