@@ -189,6 +189,12 @@ static cudaError_t launch_ex(void (*kern)(KArgs...), int grid, int block, size_t
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// L2-aware tile order of the LAUUM / inverse launches (DGP_RASTER=0: the round-1 row-by-row order)
+static int raster_on() {
+  static const int v = getenv("DGP_RASTER") ? atoi(getenv("DGP_RASTER")) != 0 : 1;
+  return v;
+}
+
 static const BatchTab g_no_batch = {};   // count == 0: single-site launch
 static const P2Batch g_no_p2batch = {};
 
@@ -703,11 +709,13 @@ static int run_trtri(dgp_handle h, bool want_T) {
     const int npairs = (nb - hb + 2 * hb - 1) / (2 * hb);  // pairs whose second range is non-empty
     {
       GemmArgs g = base_args(h, M_INV_M, 0);
+      g.raster = raster_on();
       g.aux0 = hb; g.aux1 = npairs; g.C = h->bufA; g.ntiles = npairs * hb * 2 * hb;
       if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmU, h->tmL, g))) return rc;
     }
     {
       GemmArgs g = base_args(h, M_INV_U, 0);
+      g.raster = raster_on();
       g.aux0 = hb; g.aux1 = npairs; g.C = h->bufU; g.ntiles = npairs * hb * 2 * hb; g.sign = -1.0;
       if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmA, h->tmA, g))) return rc;
     }
@@ -728,17 +736,21 @@ static int run_trtri(dgp_handle h, bool want_T) {
 
 static int run_lauum_grad(dgp_handle h) {
   GemmArgs g = base_args(h, M_LAUUM, 0);
-  g.C = h->bufA; g.ntiles = h->nb * (h->nb + 1);
+  g.raster = raster_on();
+  g.C = h->bufA; g.ntiles = lauum_slots(h->nb, g.raster);
   g.Kinv = h->debug_kinv ? h->bufA : nullptr;
   // Default: LAUUM stores the lower tiles of Ky^-1 (8 n^2 / 2 B, over T, which is dead by now) and a separate
   // high-occupancy pass contracts W = alpha alpha' - Ky^-1 with the regenerated dK/dtheta tiles.  DGP_FUSED_GRAD=1
   // selects the contraction fused into the LAUUM epilogue instead (no Ky^-1 round trip; measured 3-4 ms slower at
   // n = 16384 because the epilogue's dependent FP64 chains wait behind the co-resident CTA's DMMA issue).
   static const bool fused = getenv("DGP_FUSED_GRAD") != nullptr && atoi(getenv("DGP_FUSED_GRAD")) != 0;
-  if (fused) return launch_gemm<INIT_ZERO, EPI_GRAD>(h, h->tmU, h->tmU, g);
+  if (fused) {  // per-tile partials are indexed by the CTA: row-by-row order, one CTA per tile
+    g.raster = 0; g.ntiles = h->nb * (h->nb + 1);
+    return launch_gemm<INIT_ZERO, EPI_GRAD>(h, h->tmU, h->tmU, g);
+  }
   int rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmU, h->tmU, g);
   if (rc) return rc;
-  k_grad_contract<<<g.ntiles, 128, 0, h->stream>>>(h->spec, h->theta, h->Xw, h->alpha, h->bufA, h->npad, h->n, h->gpart);
+  k_grad_contract<<<h->nb * (h->nb + 1), 128, 0, h->stream>>>(h->spec, h->theta, h->Xw, h->alpha, h->bufA, h->npad, h->n, h->gpart);
   h->launches++;
   CK(h, cudaGetLastError());
   return 0;

@@ -79,6 +79,7 @@ GemmArgs b_args(dgp_batch_t b, int mode, double* C, double sign, int ntiles) {
   g.mode = mode; g.nb = b->NB; g.n = 0;
   g.ntiles = ntiles; g.C = C; g.ldc = b->ld; g.sign = sign;
   g.Xw = b->Xw; g.noise = b->noise; g.theta = b->theta; g.alpha = b->alpha; g.part = b->gpart;
+  g.raster = raster_on();
   return g;
 }
 
@@ -225,7 +226,7 @@ int b_lauum_grad(dgp_batch_t b, cudaStream_t W) {
   TabBuilder tb(b);
   for (int k = 0; k < b->G; k++) {
     const int i = b->order[k];
-    tb.add(i, 0, b->nb[i], b->n[i], 0, 0, 0, b->nb[i] * (b->nb[i] + 1));
+    tb.add(i, 0, b->nb[i], b->n[i], 0, 0, 0, lauum_slots(b->nb[i], raster_on()));
   }
   GemmArgs g = b_args(b, M_LAUUM, b->A, 1.0, tb.total);
   int rc = launch_gemm<INIT_ZERO, EPI_STORE>(b, b->tmU, b->tmU, g, W, false, &tb.t);

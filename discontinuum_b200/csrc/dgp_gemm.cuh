@@ -47,6 +47,7 @@ struct GemmArgs {
   double* Kinv;                 // optional dense Ky^-1 output (EPI_GRAD, debug), ld = ldc
   double jitter;
   int latent;                   // INIT_COV: add only `jitter` on the diagonal (latent posterior covariance)
+  int raster;                   // M_LAUUM / M_INV_M / M_INV_U: tiles enumerated in 8 x 16 super-tiles (see decode_job)
 };
 
 // Batched launches (dgp_batch_*: several independent sites per launch).  A launch covers the tiles of up to
@@ -62,8 +63,14 @@ struct BatchTab {
   BatchEnt e[DGP_BATCH_MAX];
 };
 
+// tile slots of an M_LAUUM launch over nb block rows (raster order: 8-row bands of 8 x 16 cells, see decode_job)
+__host__ __device__ inline int lauum_slots(int nb, int raster) {
+  const int B = (nb + 7) / 8;
+  return raster ? 64 * B * (B + 1) : nb * (nb + 1);
+}
+
 // the fields of GemmArgs that decode_job reads (per site in a batched launch)
-struct JobCtx { int mode, step, nb, aux0, aux1, aux2; };
+struct JobCtx { int mode, step, nb, aux0, aux1, aux2, raster; };
 
 struct Job {
   int rowA, kA, rowB, kB, nk;   // operand panel origins (elements) and number of 16-wide k steps
@@ -123,7 +130,14 @@ __device__ __forceinline__ Job decode_job(const JobCtx& g, int tile, int init_de
       const int pr = tile % np_, w = tile / np_;
       const int o = pr * 2 * hb;
       int jb, ic;
-      if (g.mode == M_INV_M) { jb = w / (2 * hb); ic = w % (2 * hb); }
+      if (g.raster) {
+        // L2-aware order: the hb x 2hb tiles of a pair in cells of R x 2R tiles (R = min(8, hb)), so that the CTAs resident
+        // together share R row panels and 2R column panels instead of one row panel and ~150 column panels
+        const int R = hb < 8 ? hb : 8, C2 = 2 * R, per = R * C2, cpr = hb / R;
+        const int cell = w / per, within = w % per;
+        if (g.mode == M_INV_M) { jb = (cell / cpr) * R + within / C2; ic = (cell % cpr) * C2 + within % C2; }
+        else { jb = (cell % cpr) * R + within % R; ic = 2 * hb - 1 - ((cell / cpr) * C2 + within / R); }
+      } else if (g.mode == M_INV_M) { jb = w / (2 * hb); ic = w % (2 * hb); }
       else { ic = 2 * hb - 1 - w / hb; jb = w % hb; }
       const int cb64 = 2 * (o + hb) + ic;
       j.valid = cb64 < 2 * g.nb;
@@ -135,8 +149,19 @@ __device__ __forceinline__ Job decode_job(const JobCtx& g, int tile, int init_de
       j.crow = j.rowA; j.ccol = j.rowB;
     } break;
     case M_LAUUM: {  // Kinv[i, c] = sum_{k >= i} U[i, k] U[c, k]^T  (lower tiles, longest K first)
-      const int i = (isqrt_floor(4 * tile + 1) - 1) >> 1;
-      const int c = tile - i * (i + 1);
+      int i, c;
+      if (g.raster) {
+        // L2-aware order: bands of 8 block rows, inside a band cells of 8 x 16 tiles (band b has b + 1 cells, 64 b (b + 1)
+        // tile slots before it); slots beyond the triangle exit.  Grid = lauum_slots(nb).
+        const int ip = (isqrt_floor(4 * (tile >> 6) + 1) - 1) >> 1;
+        const int rem = tile - 64 * ip * (ip + 1);
+        i = ip * 8 + ((rem & 127) >> 4);
+        c = (rem >> 7) * 16 + (rem & 15);
+        j.valid = i < g.nb && c <= 2 * i + 1;
+      } else {
+        i = (isqrt_floor(4 * tile + 1) - 1) >> 1;
+        c = tile - i * (i + 1);
+      }
       j.rowA = i * 128; j.kA = i * 128;
       j.rowB = c * 64; j.kB = i * 128;
       j.nk = (g.nb - i) * 8;
@@ -244,7 +269,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tile = MT == 8 ? blockIdx.x : (blockIdx.x >> 1);
-  JobCtx jc{g.mode, g.step, g.nb, g.aux0, g.aux1, g.aux2};
+  JobCtx jc{g.mode, g.step, g.nb, g.aux0, g.aux1, g.aux2, g.raster};
   int site = -1, npts = g.n;   // site >= 0: batched launch
   double jitter = g.jitter;
   if (bt.count > 0) {
