@@ -82,6 +82,7 @@ struct dgp_handle_s {
   int panel_blocks = 4;              // block columns per panel of the two-level Cholesky
   bool pdl = true;                   // programmatic dependent launch along the panel chain (DGP_PDL=0: off)
   bool chain_half = true;            // 64-row half tiles for the panel chain's small launches (DGP_CHAIN_HALF=0: off)
+  bool inpanel_left = false;         // in-panel updates left-looking (one rank-(128 j) update per column; DGP_INPANEL_LEFT=1)
   struct GraphSlot { cudaGraphExec_t exec = nullptr; double jitter = 0.0; bool seen = false; long long launches = 0; };
   GraphSlot graphs[3];               // per evaluation level (nlml / nlml+grad / factorize)
   bool use_graphs = false;  // opt-in (DGP_GRAPHS=1): replay loses the stream priorities of the look-ahead, measured slower
@@ -282,6 +283,8 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
     if (ch) h->chain_half = atoi(ch) != 0;
     const char* pb = getenv("DGP_PANEL_BLOCKS");
     if (pb && atoi(pb) >= 1 && atoi(pb) <= 64) h->panel_blocks = atoi(pb);
+    const char* il = getenv("DGP_INPANEL_LEFT");
+    if (il) h->inpanel_left = atoi(il) != 0;
   }
   const size_t np = h->max_pad, mc = h->max_m, nbm = np / 128;
   auto A = [&](double** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(double)); };
@@ -629,12 +632,17 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
       h->launches++;
       CK(h, cudaGetLastError());
     }
-    if (s + 1 < pe) {  // in-panel rank-128 update: block columns (s, pe), rows >= s + 1
-      const int w = pe - s - 1;
+    if (s + 1 < pe) {  // in-panel update of the panel's own remaining columns, rows >= s + 1
       const bool waited = (s == pb && mid_wait != nullptr);
       if (waited) CK(h, cudaStreamWaitEvent(P, mid_wait, 0));
-      if ((rc = launch_trail(h, b, M_TRAIL_COL, s, 1, s + 1, w, m * 2 * w, generate && s == 0, jitter, P,
-                             h->chain_half && 4 * m * w <= 2 * h->sms, pdl && !inplace && !fwd && !waited))) return rc;
+      if (h->inpanel_left) {  // left-looking: column s + 1 takes the panel's columns [pb, s] in one rank-(128 (s+1-pb)) update
+        if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, s + 1 - pb, s + 1, 1, m * 2, generate && pb == 0, jitter, P,
+                               h->chain_half && 4 * m <= 2 * h->sms, pdl && !inplace && !fwd && !waited))) return rc;
+      } else {                // right-looking: rank-128 update of block columns (s, pe)
+        const int w = pe - s - 1;
+        if ((rc = launch_trail(h, b, M_TRAIL_COL, s, 1, s + 1, w, m * 2 * w, generate && s == 0, jitter, P,
+                               h->chain_half && 4 * m * w <= 2 * h->sms, pdl && !inplace && !fwd && !waited))) return rc;
+      }
       trace_mark(h, P, "inpanel>", s);
     }
   }

@@ -24,6 +24,7 @@ struct dgp_batch_s {
   std::vector<cudaEvent_t> evs;
   int panel_blocks = 4;
   bool pdl = true, chain_half = true, timing = false;
+  bool inpanel_left = true;  // in-panel updates left-looking (DGP_INPANEL_LEFT=0: right-looking rank-128 updates)
   int max_sites = 0, max_pad = 0, max_n = 0;
   int G = 0, NB = 0;
   long long ld = 0;
@@ -135,7 +136,16 @@ int b_potrf(dgp_batch_t b) {
         const int m = nbi - s - 1;
         trsm.add(i, s, nbi, b->n[i], 0, 1, 0, 2 * m);
         const int lpe = (pe - b->off[i] < nbi) ? pe - b->off[i] : nbi;
-        if (s + 1 < lpe) {
+        if (s + 1 < lpe && b->inpanel_left) {
+          // left-looking inside the panel: block column s + 1 takes the panel's columns [lpb, s] in ONE rank-(128 (s+1-lpb))
+          // update (read and written once per panel instead of once per earlier column).  With a whole batch per launch these
+          // updates are throughput work, and a K = 128 tile spends as long on its C tile as on its products.  Same
+          // products in the same order as the right-looking form: bit-identical.
+          const int lpb = pb - b->off[i];
+          const bool first = (lpb == 0);   // columns of a site's first panel are generated here
+          inp.add(i, lpb, nbi, b->n[i], (s + 1) | (1 << 16), s + 1 - lpb, first ? 0 : 1, m * 2);
+          inp.any_first |= first && m > 0;
+        } else if (s + 1 < lpe) {
           const int w = lpe - s - 1;
           const bool first = (s == 0);
           inp.add(i, s, nbi, b->n[i], (s + 1) | (w << 16), 1, first ? 0 : 1, m * 2 * w);
@@ -326,6 +336,8 @@ int dgp_batch_create(dgp_batch* out, int device, int max_sites, int max_n, void*
   if (ch) b->chain_half = atoi(ch) != 0;
   const char* pbk = getenv("DGP_PANEL_BLOCKS");
   if (pbk && atoi(pbk) >= 1 && atoi(pbk) <= 64) b->panel_blocks = atoi(pbk);
+  const char* il = getenv("DGP_INPANEL_LEFT");
+  if (il) b->inpanel_left = atoi(il) != 0;
   const size_t np = b->max_pad, S = max_sites, nbm = np / 128;
   cudaError_t r = cudaSuccess;
   auto A = [&](double** p, size_t count) { if (r == cudaSuccess) r = cudaMalloc((void**)p, count * sizeof(double)); };

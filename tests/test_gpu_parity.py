@@ -579,3 +579,66 @@ def test_graft_smoke(cuda_device):
     import __graft_entry__ as ge
 
     ge.smoke()
+
+
+def test_set_train_reuses_cleared_buffers_and_reserved_sampling_workspace(cuda_device):
+    """dgp_set_train skips the 2 n^2 memset when the padded size is unchanged (the zero sub-blocks of L / U are only ever
+    written with zeros), and dgp_reserve sizes the sampling workspace ahead of time: a handle that has seen other sites
+    and other grid sizes must return exactly what a fresh handle returns."""
+    th = H.loadest_theta1()
+    spec = models.loadest_spec(2)
+    a = synthetic.loadest_site(700, 91)
+    b = synthetic.loadest_site(690, 92)     # same padded size (768): no memset between the two
+    c = synthetic.loadest_site(300, 93)     # smaller padded size: buffers are cleared again
+    Xs = synthetic.daily_grid(b[0], 500) + np.array([0.0005, 0.0])
+    Z = np.random.default_rng(3).standard_normal((8, 500))
+    fresh = {}
+    for name, site in (("b", b), ("c", c)):
+        e = _engine(spec, *site)
+        fresh[name] = e.nlml_grad(th)
+        if name == "b":
+            e.factorize(th)
+            fresh["Lb"] = e.chol()
+            fresh["draws"] = e.sample(Xs, Z, jitter=1e-7)[0]
+        e.close()
+    eng = capi.Engine(max_n=700, max_m=256)
+    eng.reserve(600, 16)
+    eng.set_train(spec.to_c(), *a)
+    eng.nlml_grad(th)
+    eng.factorize(th)
+    eng.sample(synthetic.daily_grid(a[0], 300), np.zeros((4, 300)), jitter=1e-7)   # a different grid size through the same arena
+    eng.set_train(spec.to_c(), *b)
+    got = eng.nlml_grad(th)
+    assert got[2] == 0 and got[0] == fresh["b"][0] and np.array_equal(got[1], fresh["b"][1])
+    eng.factorize(th)
+    Lb = eng.chol()
+    assert np.array_equal(Lb, fresh["Lb"]) and np.max(np.abs(np.triu(Lb, 1))) == 0.0
+    assert np.array_equal(eng.sample(Xs, Z, jitter=1e-7)[0], fresh["draws"])
+    eng.set_train(spec.to_c(), *c)
+    got = eng.nlml_grad(th)
+    assert got[2] == 0 and got[0] == fresh["c"][0] and np.array_equal(got[1], fresh["c"][1])
+    eng.reserve(0)   # releases the workspace; the next call grows it again
+    eng.set_train(spec.to_c(), *b)
+    eng.factorize(th)
+    assert np.array_equal(eng.sample(Xs, Z, jitter=1e-7)[0], fresh["draws"])
+    eng.close()
+
+
+def test_fit_aborts_on_device_fault_instead_of_counting_nan_iterations(cuda_device):
+    """A bad-argument / CUDA error from libdgp (rc < 0 -> DgpError) must end fit() at once; only numerical failures are
+    skipped like the reference does (engines/gpytorch.py:356-361)."""
+    cov, conc = _loadest_arrays(120, 3)
+    m = models.LoadestGP()
+    m.fit(cov, conc, iterations=2)
+    calls = {"n": 0}
+    real = m._engine.nlml_grad
+
+    def broken(theta, jitter=0.0):
+        calls["n"] += 1
+        raise capi.DgpError("dgp_nlml_grad failed (-2): injected CUDA error")
+
+    m._engine.nlml_grad = broken
+    with pytest.raises(capi.DgpError, match="injected"):
+        m.fit(cov, conc, iterations=5, resume=True)
+    assert calls["n"] == 1
+    m._engine.nlml_grad = real

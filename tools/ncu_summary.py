@@ -7,8 +7,8 @@ def launches(path):
     for row in csv.DictReader(lines):
         t = float(row["Metric Value"].replace(",", ""))
         t = t / 1e3 if row["Metric Unit"] == "ns" else (t * 1e3 if row["Metric Unit"] == "ms" else t)
-        m = re.search(r"k_gemm<(?:\(int\))?(\d), (?:\(int\))?(\d)>", row["Kernel Name"])
-        key = f"k_gemm<INIT={m.group(1)},EPI={m.group(2)}>" if m else row["Kernel Name"].split("(")[0]
+        m = re.search(r"k_gemm<(?:\(int\))?(\d), (?:\(int\))?(\d)(?:, (?:\(int\))?(\d))?>", row["Kernel Name"])
+        key = f"k_gemm<INIT={m.group(1)},EPI={m.group(2)},MT={m.group(3) or 8}>" if m else row["Kernel Name"].split("(")[0]
         a = agg.setdefault(key, [0, 0.0]); a[0] += 1; a[1] += t; tot += t
     out = [f"{'kernel':34s} {'launches':>8s} {'total ms':>10s} {'share':>7s} {'avg us':>10s}"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
