@@ -82,6 +82,10 @@ struct dgp_handle_s {
   int panel_blocks = 4;              // block columns per panel of the two-level Cholesky
   bool pdl = true;                   // programmatic dependent launch along the panel chain (DGP_PDL=0: off)
   bool chain_half = true;            // 64-row half tiles for the panel chain's small launches (DGP_CHAIN_HALF=0: off)
+  cudaStream_t stream_t2 = nullptr;  // second trailing-update stream (same priority as `stream`): column strips alternate
+  int eager_inv = 1;                 // merges of the inverse launched as the factorisation passes them (DGP_EAGER_INV=0: after it)
+  int eager_lag = 0;                 // ... released this many block columns late (DGP_EAGER_LAG)
+  int strip_blocks = 8;              // width of a column strip in block columns (DGP_STRIP_BLOCKS, 0: one stream, no strips)
   bool inpanel_left = false;         // in-panel updates left-looking (one rank-(128 j) update per column; DGP_INPANEL_LEFT=1)
   struct GraphSlot { cudaGraphExec_t exec = nullptr; double jitter = 0.0; bool seen = false; long long launches = 0; };
   GraphSlot graphs[3];               // per evaluation level (nlml / nlml+grad / factorize)
@@ -214,6 +218,14 @@ static int launch_gemm(HT h, const CUtensorMap& a, const CUtensorMap& b, const G
     CK(h, cudaFuncSetAttribute(k_gemm<INIT, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set[dev] = true;
   }
+  static const int stagger = getenv("DGP_STAGGER_NS") ? atoi(getenv("DGP_STAGGER_NS")) : 0;
+  if (stagger > 0 && MT == 8 && g.ntiles > 2 * h->sms) {
+    GemmArgs g2 = g;
+    g2.stagger_ns = stagger; g2.stagger_lo = h->sms;
+    CK(h, launch_ex(k_gemm<INIT, EPI, MT>, g.ntiles, GEMM_THREADS, (size_t)smem_bytes, st, pdl, a, b, h->spec, g2, *bt));
+    h->launches++;
+    return 0;
+  }
   CK(h, launch_ex(k_gemm<INIT, EPI, MT>, g.ntiles * (MT == 8 ? 1 : 2), GEMM_THREADS, (size_t)smem_bytes, st, pdl, a, b, h->spec, g, *bt));
   h->launches++;
   return 0;
@@ -271,6 +283,23 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
       h->own_stream = true;
     }
     cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, hi);
+    {  // second trailing-update stream at the priority of `stream` (whoever created that)
+      int pr = (lo + hi) / 2;
+      if (cudaStreamGetPriority(h->stream, &pr) != cudaSuccess) { cudaGetLastError(); pr = (lo + hi) / 2; }
+      cudaStreamCreateWithPriority(&h->stream_t2, cudaStreamNonBlocking, pr);
+    }
+    if (h->stream_lo == nullptr && (getenv("DGP_PRIO3") == nullptr || atoi(getenv("DGP_PRIO3")) != 0)) {
+      // caller's stream: the phases after the factorisation still get a lowest-priority stream of the handle's own
+      cudaStreamCreateWithPriority(&h->stream_lo, cudaStreamNonBlocking, lo);
+      cudaEventCreateWithFlags(&h->ev_lo[0], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&h->ev_lo[1], cudaEventDisableTiming);
+    }
+    const char* ei = getenv("DGP_EAGER_INV");
+    if (ei) h->eager_inv = atoi(ei);
+    const char* el = getenv("DGP_EAGER_LAG");
+    if (el && atoi(el) >= 0) h->eager_lag = atoi(el) / 8 * 8;
+    const char* sb = getenv("DGP_STRIP_BLOCKS");
+    if (sb && atoi(sb) >= 0 && atoi(sb) <= 4096) h->strip_blocks = atoi(sb);
     const char* la = getenv("DGP_LOOKAHEAD");
     if (la) h->lookahead = atoi(la) != 0;
     const char* ug = getenv("DGP_GRAPHS");
@@ -380,6 +409,8 @@ int dgp_create_partitioned(dgp_handle* out, int device, int max_n, int max_m, in
   dgp_handle h = *out;
   cudaStreamDestroy(h->stream_hi);          // the look-ahead stream must live in the partition as well
   h->stream_hi = (cudaStream_t)st_hi;
+  cudaStreamDestroy(h->stream_t2);          // one trailing-update stream inside a partition (no column strips)
+  h->stream_t2 = nullptr;
   h->own_stream = true;                     // both streams are the handle's to destroy
   h->sms = P.sms;
   return 0;
@@ -391,6 +422,7 @@ int dgp_destroy(dgp_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stream_hi) { cudaStreamSynchronize(h->stream_hi); cudaStreamDestroy(h->stream_hi); }
   if (h->stream_lo) { cudaStreamSynchronize(h->stream_lo); cudaStreamDestroy(h->stream_lo); }
+  if (h->stream_t2) { cudaStreamSynchronize(h->stream_t2); cudaStreamDestroy(h->stream_t2); }
   for (int i = 0; i < 2; i++) if (h->ev_lo[i]) cudaEventDestroy(h->ev_lo[i]);
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   for (auto& gs : h->graphs) if (gs.exec) cudaGraphExecDestroy(gs.exec);
@@ -589,6 +621,8 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
   const long long ld = b.ld;
   int rc;
   const bool pdl = h->pdl && !h->trace_path;  // the trace's events would sit between the kernels
+  // timing experiments only (results are garbage): DGP_SKIP bit 0: no diagonal-block kernel, 1: no panel solve, 2: no in-panel update
+  static const int skip = getenv("DGP_SKIP") ? atoi(getenv("DGP_SKIP")) : 0;
   for (int s = pb; s < pe; s++) {
     const size_t off = (size_t)s * 128 * ld + (size_t)s * 128;
     const bool inplace = (b.L == b.A);
@@ -599,7 +633,8 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
     const bool t_in_a = !potf2_v1 && !inplace && !fwd;
     // the zero sub-blocks of bufL / bufU were cleared by dgp_set_train and only this kernel ever writes them
     const bool lu_clean = !inplace && h->lu_zeroed && b.L == h->bufL && (b.U == nullptr || b.U == h->bufU);
-    if (potf2_v1)
+    if (skip & 1) {}
+    else if (potf2_v1)
       k_potf2<<<1, PF_THREADS, PF_SMEM, P>>>(b.A + off, b.L + off, b.U ? b.U + off : nullptr, ld,
                                              b.DI + (size_t)s * 128 * 128, b.scal, s * 128, inplace ? nullptr : b.A + off);
     else  // dependent launch behind the in-panel update of the previous block column (same stream, nothing in between)
@@ -610,7 +645,7 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
     CK(h, cudaGetLastError());
     trace_mark(h, P, "potf2>", s);
     const int m = nb - s - 1;
-    if (m > 0) {
+    if (m > 0 && !(skip & 2)) {
       GemmArgs g = base_args(h, M_TRSM, s);
       g.nb = nb; g.ldc = ld;
       g.C = b.L; g.ntiles = 2 * m;
@@ -632,7 +667,7 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
       h->launches++;
       CK(h, cudaGetLastError());
     }
-    if (s + 1 < pe) {  // in-panel update of the panel's own remaining columns, rows >= s + 1
+    if (s + 1 < pe && !(skip & 4)) {  // in-panel update of the panel's own remaining columns, rows >= s + 1
       const bool waited = (s == pb && mid_wait != nullptr);
       if (waited) CK(h, cudaStreamWaitEvent(P, mid_wait, 0));
       if (h->inpanel_left) {  // left-looking: column s + 1 takes the panel's columns [pb, s] in one rank-(128 (s+1-pb)) update
@@ -649,13 +684,21 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
   return 0;
 }
 
-static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jitter, bool fwd) {
+// after_panel(p, pe): called once the chain of panel p is enqueued and ev_panel(p) = h->evs[3 p] is recorded (the first pe
+// block columns of L, and the diagonal blocks of T and U up to there, are final behind that event)
+struct PanelHook { int (*fn)(dgp_handle, void*, cudaEvent_t, int) = nullptr; void* ctx = nullptr; };
+
+static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jitter, bool fwd, PanelHook hook = PanelHook()) {
   const int nb = b.nb;
   const long long ld = b.ld;
   int rc;
   cudaStream_t T = h->stream, P = h->lookahead ? h->stream_hi : h->stream;
   const int pw = h->panel_blocks;
   const int npanels = (nb + pw - 1) / pw;
+  // column strips of the trailing updates (see below): width in block columns, a multiple of the panel width
+  const int sw = (h->strip_blocks + pw - 1) / pw * pw;
+  cudaStream_t T2 = (P != T && sw > 0 && h->stream_t2 != nullptr && !h->use_graphs) ? h->stream_t2 : nullptr;
+  bool any2 = false;
   if ((rc = ensure_events(h, 3 * (size_t)npanels + 3))) return rc;
   auto ev_panel = [&](int p) { return h->evs[3 * p]; };
   auto ev_cols = [&](int p) { return h->evs[3 * p + 1]; };   // all columns of panel p have the updates of panels < p
@@ -677,8 +720,44 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
     if (P != T) {
       CK(h, cudaEventRecord(ev_panel(p), P));
       CK(h, cudaStreamWaitEvent(T, ev_panel(p), 0));
+      if (hook.fn && pe < nb && (rc = hook.fn(h, hook.ctx, ev_panel(p), pe))) return rc;
     }
-    if (pe < nb) {  // rank-(128 (pe - pb)) update right of the panel: next panel's columns, then the rest
+    if (pe < nb && T2 != nullptr) {
+      // Column strips on two streams.  The trailing matrix is cut into fixed strips of `sw` block columns; strip j is
+      // always updated on stream j mod 2, so the strips of one stream form their own dependency chain (panel after
+      // panel) and the two streams never wait for each other: while one launch drains its last partial wave, the other
+      // stream's CTAs take the free slots (a single stream loses about half a wave per launch, 3 launches per panel).
+      // The next panel's columns are the head of their strip: first column | its other columns | the rest of the strip.
+      const int ne = (pe + pw < nb) ? pe + pw : nb, w = ne - pe, m = nb - pe;
+      const int slots = 2 * h->sms;
+      const bool first = generate && p == 0;
+      const int j0 = pe / sw;
+      bool used2 = false;
+      auto strip_stream = [&](int j) -> cudaStream_t {
+        if ((j & 1) == 0) return T;
+        if (!used2) { used2 = true; cudaStreamWaitEvent(T2, ev_panel(p), 0); }
+        return T2;
+      };
+      cudaStream_t S0 = strip_stream(j0);
+      trace_mark(h, S0, "cols<", p);
+      if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, pe, 1, m * 2, first, jitter, S0, h->chain_half && m * 2 <= slots))) return rc;
+      CK(h, cudaEventRecord(ev_col0(p + 1), S0));
+      if (w > 1 && (rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, pe + 1, w - 1, (m - 1) * 2 * (w - 1), first, jitter, S0,
+                                      h->chain_half && (m - 1) * 2 * (w - 1) <= slots))) return rc;
+      trace_mark(h, S0, "cols>", p);
+      CK(h, cudaEventRecord(ev_cols(p + 1), S0));
+      const int e0 = ((j0 + 1) * sw < nb) ? (j0 + 1) * sw : nb;
+      if (ne < e0) {
+        const int tiles = (nb - ne) * 2 * (e0 - ne);
+        if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, ne, e0 - ne, tiles, first, jitter, S0, h->chain_half && tiles <= slots))) return rc;
+      }
+      for (int j = j0 + 1; j * sw < nb; j++) {
+        const int o = j * sw, wj = (o + sw < nb) ? sw : nb - o, tiles = (nb - o) * 2 * wj;
+        if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, o, wj, tiles, first, jitter, strip_stream(j), h->chain_half && tiles <= slots))) return rc;
+      }
+      trace_mark(h, T, "rest>", p);
+      if (used2) any2 = true;
+    } else if (pe < nb) {  // rank-(128 (pe - pb)) update right of the panel: next panel's columns, then the rest
       const int ne = (pe + pw < nb) ? pe + pw : nb, w = ne - pe, m = nb - pe;
       // the first column of the next panel is all its diagonal block and panel solve wait for: update it on its own
       trace_mark(h, T, "cols<", p);
@@ -696,12 +775,16 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
       trace_mark(h, T, "rest>", p);
     }
   }
+  if (any2) {  // the caller continues on T
+    CK(h, cudaEventRecord(h->evs[3 * (size_t)npanels], T2));
+    CK(h, cudaStreamWaitEvent(T, h->evs[3 * (size_t)npanels], 0));
+  }
   return 0;
 }
 
-static int run_potrf(dgp_handle h, double jitter, bool fwd) {
+static int run_potrf(dgp_handle h, double jitter, bool fwd, PanelHook hook = PanelHook()) {
   CholBufs b{h->bufA, h->bufL, h->bufU, h->DI, h->scal, &h->tmA, &h->tmL, &h->tmDI, h->nb, h->npad};
-  return potrf_core(h, b, true, jitter, fwd);
+  return potrf_core(h, b, true, jitter, fwd, hook);
 }
 
 // U = L^-T (upper) by recursive doubling: the diagonal 128-blocks come from k_potf2 (U_ss in bufU, T_ss = L_ss^-1 in
@@ -710,33 +793,63 @@ static int run_potrf(dgp_handle h, double jitter, bool fwd) {
 //   U12 = -M' T22'          -> bufU
 //   T21 = U12'              -> lower triangle of bufA (operand of the next level / of the prediction kernels)
 // log2(nb) levels x 3 launches instead of 2 nb launches of rank-128 updates.  want_T: also transpose the last level.
-static int run_trtri(dgp_handle h, bool want_T) {
+// The merges of a level are launched pair by pair as the factorisation passes them (trtri_advance(F): every merge whose
+// block range lies inside the first F block columns and has not been launched yet), on the lowest-priority stream: the
+// inverse of the leading ranges fills the SM slots the factorisation leaves idle (partial last waves, the latency-bound
+// chain of its last panels).  Same products in the same order as one launch per level: bit-identical.
+struct InvProgress {
+  int done[16];       // per level (hb = 1 << l): leading pairs already launched
+  bool want_T;
+  cudaStream_t W;
+  int lag;            // release the merges `lag` block columns late (DGP_EAGER_LAG)
+};
+
+static int trtri_advance(dgp_handle h, InvProgress& ip, int F) {
   const int nb = h->nb;
-  int rc;
-  for (int hb = 1; hb < nb; hb *= 2) {
+  int rc, lv = 0;
+  for (int hb = 1; hb < nb; hb *= 2, lv++) {
     const int npairs = (nb - hb + 2 * hb - 1) / (2 * hb);  // pairs whose second range is non-empty
+    const int avail = F >= nb ? npairs : F / (2 * hb);
+    const int pr0 = ip.done[lv], cnt = avail - pr0;
+    if (cnt <= 0) continue;
     {
-      GemmArgs g = base_args(h, M_INV_M, 0);
+      GemmArgs g = base_args(h, M_INV_M, pr0);
       g.raster = raster_on();
-      g.aux0 = hb; g.aux1 = npairs; g.C = h->bufA; g.ntiles = npairs * hb * 2 * hb;
-      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmU, h->tmL, g))) return rc;
+      g.aux0 = hb; g.aux1 = cnt; g.C = h->bufA; g.ntiles = cnt * hb * 2 * hb;
+      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmU, h->tmL, g, ip.W))) return rc;
     }
     {
-      GemmArgs g = base_args(h, M_INV_U, 0);
+      GemmArgs g = base_args(h, M_INV_U, pr0);
       g.raster = raster_on();
-      g.aux0 = hb; g.aux1 = npairs; g.C = h->bufU; g.ntiles = npairs * hb * 2 * hb; g.sign = -1.0;
-      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmA, h->tmA, g))) return rc;
+      g.aux0 = hb; g.aux1 = cnt; g.C = h->bufU; g.ntiles = cnt * hb * 2 * hb; g.sign = -1.0;
+      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(h, h->tmA, h->tmA, g, ip.W))) return rc;
     }
-    if (want_T || 2 * hb < nb) {
-      k_transpose_pairs<<<npairs * 16 * hb * hb, 256, 0, h->stream>>>(h->bufU, h->bufA, h->npad, hb, h->npad);
+    if (ip.want_T || 2 * hb < nb) {
+      k_transpose_pairs<<<cnt * 16 * hb * hb, 256, 0, ip.W>>>(h->bufU, h->bufA, h->npad, hb, h->npad, pr0);
       h->launches++;
       CK(h, cudaGetLastError());
     }
+    ip.done[lv] = avail;
   }
+  return 0;
+}
+
+static int eager_hook(dgp_handle h, void* ctx, cudaEvent_t ev_panel, int pe) {
+  InvProgress& ip = *(InvProgress*)ctx;
+  const int F = pe - ip.lag;
+  if (F < 2 || (F & 7) != 0) return 0;   // every 8 block columns: 4 / 2 / 1 new pairs at the three lowest levels
+  CK(h, cudaStreamWaitEvent(ip.W, ev_panel, 0));
+  return trtri_advance(h, ip, F);
+}
+
+static int run_trtri(dgp_handle h, InvProgress& ip) {
+  const int nb = h->nb;
+  int rc;
+  if ((rc = trtri_advance(h, ip, nb))) return rc;
   // z = U' r (= L^-1 r), alpha = U z
-  k_upperT_gemv_part<<<dim3(nb, nb), 256, 0, h->stream>>>(h->bufU, h->npad, h->r, h->zpart, h->npad);
-  k_upperT_gemv_sum<<<(h->npad + 255) / 256, 256, 0, h->stream>>>(h->zpart, h->npad, h->z, h->npad);
-  k_upper_gemv<<<h->npad / 8, 256, 0, h->stream>>>(h->bufU, h->npad, h->z, h->alpha, h->npad);
+  k_upperT_gemv_part<<<dim3(nb, nb), 256, 0, ip.W>>>(h->bufU, h->npad, h->r, h->zpart, h->npad);
+  k_upperT_gemv_sum<<<(h->npad + 255) / 256, 256, 0, ip.W>>>(h->zpart, h->npad, h->z, h->npad);
+  k_upper_gemv<<<h->npad / 8, 256, 0, ip.W>>>(h->bufU, h->npad, h->z, h->alpha, h->npad);
   h->launches += 3;
   CK(h, cudaGetLastError());
   return 0;
@@ -777,18 +890,25 @@ static int evaluate_enqueue(dgp_handle h, double jitter, int level) {
   int rc;
   CK(h, cudaMemcpyAsync(h->theta, h->h_theta, sizeof(double) * h->spec.ntheta, cudaMemcpyHostToDevice, h->stream));
   if ((rc = run_features(h))) return rc;
-  if ((rc = run_potrf(h, jitter, level == 0))) return rc;  // level >= 1: z = U'r after the inverse instead
+  // the O(n^3) phases after the factorisation go to the low-priority stream (when the handle has one)
+  cudaStream_t main_stream = h->stream;
+  const bool lo = level >= 1 && h->stream_lo != nullptr && !h->use_graphs;
+  InvProgress ip;
+  memset(&ip, 0, sizeof(ip));
+  ip.want_T = (level == 2); ip.W = lo ? h->stream_lo : main_stream; ip.lag = h->eager_lag;
+  PanelHook hook;
+  // (measured: a gain up to n = 8192 and for batches; at n = 16384 the long low-priority tiles cost the chain of the last
+  // panels as much as they fill, DGP_EAGER_INV=2 forces it on)
+  if (lo && h->lookahead && (h->eager_inv > 1 || (h->eager_inv == 1 && h->nb <= 96))) { hook.fn = eager_hook; hook.ctx = &ip; }
+  if ((rc = run_potrf(h, jitter, level == 0, hook))) return rc;  // level >= 1: z = U'r after the inverse instead
   if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
   if (level >= 1) {
-    // the O(n^3) phases after the factorisation go to the low-priority stream (when the handle has one)
-    cudaStream_t main_stream = h->stream;
-    const bool lo = h->stream_lo != nullptr && !h->use_graphs;
     if (lo) {
       CK(h, cudaEventRecord(h->ev_lo[0], main_stream));
       CK(h, cudaStreamWaitEvent(h->stream_lo, h->ev_lo[0], 0));
       h->stream = h->stream_lo;
     }
-    rc = run_trtri(h, level == 2);
+    rc = run_trtri(h, ip);
     if (!rc && h->timing) { cudaEventRecord(h->ev[2], h->stream); }
     if (!rc && level == 1) rc = run_lauum_grad(h);
     if (!rc && h->timing) { cudaEventRecord(h->ev[3], h->stream); }

@@ -17,14 +17,17 @@
 
 struct dgp_batch_s {
   int device = 0, sms = 148;
-  cudaStream_t stream = nullptr, stream_hi = nullptr, stream_lo = nullptr;
+  cudaStream_t stream = nullptr, stream_hi = nullptr, stream_lo = nullptr, stream_t2 = nullptr;
   bool own_stream = false;
+  bool eager_inv = true;     // merges of the inverse launched as the factorisation passes them (DGP_EAGER_INV=0: after it)
+  int eager_lag = 0;
+  int strip_blocks = 8;      // column strips of the trailing updates on two streams (DGP_STRIP_BLOCKS; 0: one stream)
   cudaEvent_t ev_lo[2] = {nullptr, nullptr};
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> evs;
   int panel_blocks = 4;
   bool pdl = true, chain_half = true, timing = false;
-  bool inpanel_left = true;  // in-panel updates left-looking (DGP_INPANEL_LEFT=0: right-looking rank-128 updates)
+  bool inpanel_left = false; // in-panel updates left-looking (DGP_INPANEL_LEFT=1; default: right-looking rank-128 updates, like the single-site engine -- the two must agree for bit-identical results)
   int max_sites = 0, max_pad = 0, max_n = 0;
   int G = 0, NB = 0;
   long long ld = 0;
@@ -104,12 +107,19 @@ int b_ensure_events(dgp_batch_t b, size_t count) {
 }
 
 // Two-level right-looking Cholesky with look-ahead (potrf_core of dgp_api.cu) over all sites, end-aligned.
-int b_potrf(dgp_batch_t b) {
+struct BInvProgress;
+int b_trtri_advance(dgp_batch_t b, BInvProgress& ip, int Fg);
+int b_eager(dgp_batch_t b, BInvProgress* ip, cudaEvent_t ev_panel, int pe);
+
+int b_potrf(dgp_batch_t b, BInvProgress* eager) {
   const int G = b->G, NB = b->NB, pw = b->panel_blocks;
   const long long ld = b->ld;
   cudaStream_t T = b->stream, P = b->stream_hi;
   const int npanels = (NB + pw - 1) / pw;
   int rc;
+  const int sw = (b->strip_blocks + pw - 1) / pw * pw;
+  cudaStream_t T2 = (sw > 0 && b->stream_t2 != nullptr) ? b->stream_t2 : nullptr;
+  bool any2 = false;
   if ((rc = b_ensure_events(b, 3 * (size_t)npanels + 3))) return rc;
   auto ev_panel = [&](int p) { return b->evs[3 * p]; };
   auto ev_cols = [&](int p) { return b->evs[3 * p + 1]; };
@@ -137,10 +147,11 @@ int b_potrf(dgp_batch_t b) {
         trsm.add(i, s, nbi, b->n[i], 0, 1, 0, 2 * m);
         const int lpe = (pe - b->off[i] < nbi) ? pe - b->off[i] : nbi;
         if (s + 1 < lpe && b->inpanel_left) {
-          // left-looking inside the panel: block column s + 1 takes the panel's columns [lpb, s] in ONE rank-(128 (s+1-lpb))
-          // update (read and written once per panel instead of once per earlier column).  With a whole batch per launch these
-          // updates are throughput work, and a K = 128 tile spends as long on its C tile as on its products.  Same
-          // products in the same order as the right-looking form: bit-identical.
+          // left-looking inside the panel (option): block column s + 1 takes the panel's columns [lpb, s] in ONE
+          // rank-(128 (s+1-lpb)) update (read and written once per panel instead of once per earlier column).  Since the
+          // tile engine adds a tile's old value in its epilogue (out = old + sign * sum, sums started at zero) the two forms
+          // round differently, and with the C tile prefetched they cost the same (measured): the default is right-looking
+          // in both engines, which keeps batch and single-site results bit-identical.
           const int lpb = pb - b->off[i];
           const bool first = (lpb == 0);   // columns of a site's first panel are generated here
           inp.add(i, lpb, nbi, b->n[i], (s + 1) | (1 << 16), s + 1 - lpb, first ? 0 : 1, m * 2);
@@ -170,7 +181,61 @@ int b_potrf(dgp_batch_t b) {
     }
     CK(b, cudaEventRecord(ev_panel(p), P));
     CK(b, cudaStreamWaitEvent(T, ev_panel(p), 0));
-    // ---- rank-(128 pw) update right of the panel, stream T: next panel's first column | its other columns | the rest
+    if (eager != nullptr && pe < NB && (rc = b_eager(b, eager, ev_panel(p), pe))) return rc;
+    // ---- rank-(128 pw) update right of the panel.  Column strips on two streams (potrf_core of dgp_api.cu): fixed strips
+    // of `sw` block columns in the end-aligned (global) column numbering, strip j always on stream j mod 2; the next panel's
+    // columns are the head of their strip: first column | its other columns | the rest of the strip.
+    if (T2 != nullptr) {
+      const int j0 = pe / sw;
+      bool used2 = false;
+      auto strip_stream = [&](int j) -> cudaStream_t {
+        if ((j & 1) == 0) return T;
+        if (!used2) { used2 = true; cudaStreamWaitEvent(T2, ev_panel(p), 0); }
+        return T2;
+      };
+      cudaStream_t S0 = strip_stream(j0);
+      TabBuilder ta(b), tb2(b), tr(b);
+      int jmax = j0;
+      for (int k = 0; k < G; k++) {
+        const int i = b->order[k], nbi = b->nb[i], lpb = pb - b->off[i];
+        if (lpb < 0 || lpb >= nbi) continue;
+        const int lpe = (pe - b->off[i] < nbi) ? pe - b->off[i] : nbi;
+        if (lpe >= nbi) continue;
+        const int kb = lpe - lpb, ne = (lpe + pw < nbi) ? lpe + pw : nbi, w = ne - lpe, m = nbi - lpe;
+        const bool first = (lpb == 0);
+        const int a2 = first ? 0 : 1;
+        ta.add(i, lpb, nbi, b->n[i], lpe | (1 << 16), kb, a2, m * 2);
+        ta.any_first |= first;
+        if (w > 1) { tb2.add(i, lpb, nbi, b->n[i], (lpe + 1) | ((w - 1) << 16), kb, a2, (m - 1) * 2 * (w - 1)); tb2.any_first |= first; }
+        const int e0 = ((j0 + 1) * sw - b->off[i] < nbi) ? (j0 + 1) * sw - b->off[i] : nbi;   // local end of the near strip
+        if (ne < e0) { tr.add(i, lpb, nbi, b->n[i], ne | ((e0 - ne) << 16), kb, a2, (nbi - ne) * 2 * (e0 - ne)); tr.any_first |= first; }
+        const int jl = (b->off[i] + nbi - 1) / sw;   // last global strip this site reaches
+        if (jl > jmax) jmax = jl;
+      }
+      if ((rc = b_launch_trail(b, ta, M_TRAIL_COL, S0, slots, false))) return rc;
+      if (p + 1 < npanels) CK(b, cudaEventRecord(ev_col0(p + 1), S0));
+      if ((rc = b_launch_trail(b, tb2, M_TRAIL_COL, S0, slots, false))) return rc;
+      if (p + 1 < npanels) CK(b, cudaEventRecord(ev_cols(p + 1), S0));
+      if ((rc = b_launch_trail(b, tr, M_TRAIL_COL, S0, slots, false))) return rc;
+      for (int j = j0 + 1; j <= jmax; j++) {
+        TabBuilder ts(b);
+        for (int k = 0; k < G; k++) {
+          const int i = b->order[k], nbi = b->nb[i], lpb = pb - b->off[i];
+          if (lpb < 0 || lpb >= nbi) continue;
+          const int lpe = (pe - b->off[i] < nbi) ? pe - b->off[i] : nbi;
+          const int o = j * sw - b->off[i];
+          if (lpe >= nbi || o >= nbi) continue;
+          const int wj = (o + sw < nbi) ? sw : nbi - o;
+          const bool first = (lpb == 0);
+          ts.add(i, lpb, nbi, b->n[i], o | (wj << 16), lpe - lpb, first ? 0 : 1, (nbi - o) * 2 * wj);
+          ts.any_first |= first;
+        }
+        if (ts.total > 0 && (rc = b_launch_trail(b, ts, M_TRAIL_COL, strip_stream(j), slots, false))) return rc;
+      }
+      if (used2) any2 = true;
+      continue;
+    }
+    // one stream: next panel's first column | its other columns | the rest
     TabBuilder ta(b), tb2(b), tc(b);
     for (int k = 0; k < G; k++) {
       const int i = b->order[k], nbi = b->nb[i], lpb = pb - b->off[i];
@@ -191,38 +256,76 @@ int b_potrf(dgp_batch_t b) {
     if (p + 1 < npanels) CK(b, cudaEventRecord(ev_cols(p + 1), T));
     if ((rc = b_launch_trail(b, tc, M_TRAIL, T, slots, false))) return rc;
   }
+  if (any2) {  // the caller continues on T
+    CK(b, cudaEventRecord(b->evs[3 * (size_t)npanels], T2));
+    CK(b, cudaStreamWaitEvent(T, b->evs[3 * (size_t)npanels], 0));
+  }
   return 0;
 }
 
-// U = L^-T by recursive doubling (run_trtri), z = U'r, alpha = U z; all sites per launch.  Stream W.
-int b_trtri(dgp_batch_t b, cudaStream_t W) {
+// U = L^-T by recursive doubling, all sites per launch, stream W.  b_trtri_advance(Fg): every merge whose block range lies
+// inside the block columns that are final once the global step Fg is reached (site i: its first Fg - off_i columns) and has
+// not been launched yet (trtri_advance of dgp_api.cu); Fg >= NB: everything that is left.
+struct BInvProgress {
+  short done[16][DGP_BATCH_MAX];
+  cudaStream_t W;
+  int lag;
+};
+
+int b_trtri_advance(dgp_batch_t b, BInvProgress& ip, int Fg) {
   const int G = b->G, NB = b->NB;
-  int rc;
-  for (int hb = 1; hb < NB; hb *= 2) {
+  int rc, lv = 0;
+  for (int hb = 1; hb < NB; hb *= 2, lv++) {
     TabBuilder tb(b);
+    PairRange prg;
+    memset(&prg, 0, sizeof(prg));
     int tmax = 0;
     for (int k = 0; k < G; k++) {
       const int i = b->order[k], nbi = b->nb[i];
       if (nbi <= hb) continue;
       const int npairs = (nbi - hb + 2 * hb - 1) / (2 * hb);
-      tb.add(i, 0, nbi, b->n[i], hb, npairs, 0, npairs * hb * 2 * hb);
-      if (2 * hb < nbi && npairs * 16 * hb * hb > tmax) tmax = npairs * 16 * hb * hb;
+      const int F = Fg >= NB ? nbi : Fg - b->off[i];
+      const int avail = F >= nbi ? npairs : (F > 0 ? F / (2 * hb) : 0);
+      const int pr0 = ip.done[lv][i], cnt = avail - pr0;
+      if (cnt <= 0) continue;
+      tb.add(i, pr0, nbi, b->n[i], hb, cnt, 0, cnt * hb * 2 * hb);
+      if (2 * hb < nbi) {
+        prg.pr0[i] = (short)pr0; prg.cnt[i] = (short)cnt;
+        if (cnt * 16 * hb * hb > tmax) tmax = cnt * 16 * hb * hb;
+      }
+      ip.done[lv][i] = (short)avail;
     }
     if (tb.total <= 0) continue;
     {
       GemmArgs g = b_args(b, M_INV_M, b->A, 1.0, tb.total);
-      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(b, b->tmU, b->tmL, g, W, false, &tb.t))) return rc;
+      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(b, b->tmU, b->tmL, g, ip.W, false, &tb.t))) return rc;
     }
     {
       GemmArgs g = b_args(b, M_INV_U, b->U, -1.0, tb.total);
-      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(b, b->tmA, b->tmA, g, W, false, &tb.t))) return rc;
+      if ((rc = launch_gemm<INIT_ZERO, EPI_STORE>(b, b->tmA, b->tmA, g, ip.W, false, &tb.t))) return rc;
     }
     if (tmax > 0) {
-      k_transpose_pairs_b<<<dim3(tmax, G), 256, 0, W>>>(b->sd, b->U, b->A, hb);
+      k_transpose_pairs_b<<<dim3(tmax, G), 256, 0, ip.W>>>(b->sd, prg, b->U, b->A, hb);
       b->launches++;
       CK(b, cudaGetLastError());
     }
   }
+  return 0;
+}
+
+int b_eager(dgp_batch_t b, BInvProgress* ip, cudaEvent_t ev_panel, int pe) {
+  const int F = pe - ip->lag;
+  if (F < 2 || (F & 7) != 0) return 0;
+  CK(b, cudaStreamWaitEvent(ip->W, ev_panel, 0));
+  return b_trtri_advance(b, *ip, F);
+}
+
+// the rest of the inverse, then z = U'r, alpha = U z
+int b_trtri(dgp_batch_t b, BInvProgress& ip) {
+  const int G = b->G, NB = b->NB;
+  cudaStream_t W = ip.W;
+  int rc;
+  if ((rc = b_trtri_advance(b, ip, NB))) return rc;
   k_upperT_gemv_part_b<<<dim3(NB, NB, G), 256, 0, W>>>(b->sd, b->U, b->r, b->zpart);
   k_upperT_gemv_sum_b<<<dim3((unsigned)((b->ld + 255) / 256), G), 256, 0, W>>>(b->sd, b->zpart, b->z);
   k_upper_gemv_b<<<dim3((unsigned)(b->ld / 8), G), 256, 0, W>>>(b->sd, b->U, b->z, b->alpha);
@@ -257,13 +360,16 @@ int b_enqueue(dgp_batch_t b) {
   k_features_b<<<dim3((unsigned)((b->ld + 255) / 256), G), 256, 0, T>>>(b->spec, b->sd, b->theta, b->X, b->y, b->Xw, b->r, b->scal);
   b->launches++;
   CK(b, cudaGetLastError());
-  if ((rc = b_potrf(b))) return rc;
+  BInvProgress ip;
+  memset(&ip, 0, sizeof(ip));
+  ip.W = W; ip.lag = b->eager_lag;
+  if ((rc = b_potrf(b, (b->eager_inv && W != T) ? &ip : nullptr))) return rc;
   if (b->timing) CK(b, cudaEventRecord(b->ev[1], T));
   if (W != T) {
     CK(b, cudaEventRecord(b->ev_lo[0], T));
     CK(b, cudaStreamWaitEvent(W, b->ev_lo[0], 0));
   }
-  if ((rc = b_trtri(b, W))) return rc;
+  if ((rc = b_trtri(b, ip))) return rc;
   if (b->timing) CK(b, cudaEventRecord(b->ev[2], W));
   if ((rc = b_lauum_grad(b, W))) return rc;
   if (b->timing) CK(b, cudaEventRecord(b->ev[3], W));
@@ -293,6 +399,7 @@ int dgp_batch_destroy(dgp_batch b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   if (b->stream_hi) { cudaStreamSynchronize(b->stream_hi); cudaStreamDestroy(b->stream_hi); }
   if (b->stream_lo) { cudaStreamSynchronize(b->stream_lo); cudaStreamDestroy(b->stream_lo); }
+  if (b->stream_t2) { cudaStreamSynchronize(b->stream_t2); cudaStreamDestroy(b->stream_t2); }
   for (int i = 0; i < 2; i++) if (b->ev_lo[i]) cudaEventDestroy(b->ev_lo[i]);
   for (int i = 0; i < 5; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   for (cudaEvent_t e : b->evs) cudaEventDestroy(e);
@@ -326,10 +433,21 @@ int dgp_batch_create(dgp_batch* out, int device, int max_sites, int max_n, void*
   if (stream) b->stream = (cudaStream_t)stream;
   else {
     cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, (lo + hi) / 2);
-    cudaStreamCreateWithPriority(&b->stream_lo, cudaStreamNonBlocking, lo);
     b->own_stream = true;
   }
+  cudaStreamCreateWithPriority(&b->stream_lo, cudaStreamNonBlocking, lo);
+  const char* ei = getenv("DGP_EAGER_INV");
+  if (ei) b->eager_inv = atoi(ei) != 0;
+  const char* el = getenv("DGP_EAGER_LAG");
+  if (el && atoi(el) >= 0) b->eager_lag = atoi(el) / 8 * 8;
   cudaStreamCreateWithPriority(&b->stream_hi, cudaStreamNonBlocking, hi);
+  {
+    int pr = (lo + hi) / 2;
+    if (cudaStreamGetPriority(b->stream, &pr) != cudaSuccess) { cudaGetLastError(); pr = (lo + hi) / 2; }
+    cudaStreamCreateWithPriority(&b->stream_t2, cudaStreamNonBlocking, pr);
+  }
+  const char* sbk = getenv("DGP_STRIP_BLOCKS");
+  if (sbk && atoi(sbk) >= 0 && atoi(sbk) <= 4096) b->strip_blocks = atoi(sbk);
   const char* pd = getenv("DGP_PDL");
   if (pd) b->pdl = atoi(pd) != 0;
   const char* ch = getenv("DGP_CHAIN_HALF");

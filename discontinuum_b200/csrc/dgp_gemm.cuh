@@ -23,7 +23,7 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 8;   // 16 KB
 constexpr int B_BYTES = BN * BK * 8;   //  8 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GEMM_THREADS = 160;      // 4 consumer warps + 1 producer warp
+constexpr int GEMM_THREADS = 256;      // 2 warpgroups: 4 consumer warps | 1 producer warp + 3 warps that only give up their registers
 constexpr int WS = BN + 1;             // padded row stride of the W tile in the grad epilogue
 #ifndef DGP_COV_V
 #define DGP_COV_V 8
@@ -48,6 +48,7 @@ struct GemmArgs {
   double jitter;
   int latent;                   // INIT_COV: add only `jitter` on the diagonal (latent posterior covariance)
   int raster;                   // M_LAUUM / M_INV_M / M_INV_U: tiles enumerated in 8 x 16 super-tiles (see decode_job)
+  int stagger_ns, stagger_lo;   // experiment (DGP_STAGGER_NS): CTAs [lo, 2 lo) of a launch start this many ns late
 };
 
 // Batched launches (dgp_batch_*: several independent sites per launch).  A launch covers the tiles of up to
@@ -125,10 +126,11 @@ __device__ __forceinline__ Job decode_job(const JobCtx& g, int tile, int init_de
     } break;
     case M_INV_M:    // recursive triangular inverse, merge of block ranges [o, o+h) and [o+h, o+2h):
     case M_INV_U: {  //   M' = U11 L21'  (M_INV_M, scratch in the upper triangle of the work matrix)
-                     //   U12 = -M' T22' (M_INV_U), T = L^-1 lower, U = T' upper.  aux0 = h, aux1 = pairs at this level
+                     //   U12 = -M' T22' (M_INV_U), T = L^-1 lower, U = T' upper.  aux0 = h, aux1 = pairs of this launch,
+                     //   step = first pair of this launch (the pairs of a level are launched as their columns of L become final)
       const int hb = g.aux0, np_ = g.aux1;
       const int pr = tile % np_, w = tile / np_;
-      const int o = pr * 2 * hb;
+      const int o = (s + pr) * 2 * hb;
       int jb, ic;
       if (g.raster) {
         // L2-aware order: the hb x 2hb tiles of a pair in cells of R x 2R tiles (R = min(8, hb)), so that the CTAs resident
@@ -236,7 +238,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
@@ -283,7 +285,6 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   }
   // slab offsets of this site (0 for a single-site launch)
   const size_t soff_m = site >= 0 ? (size_t)site * (size_t)bt.ld * (size_t)bt.ld : 0;  // matrices
-  const size_t soff_v = site >= 0 ? (size_t)site * (size_t)bt.ld : 0;                   // per-point vectors
   Job job = decode_job(jc, tile, INIT);
   if (!job.valid) return;
   if (MT == 4) { job.rowA += 64 * (blockIdx.x & 1); job.crow += 64 * (blockIdx.x & 1); }
@@ -291,15 +292,23 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
     fence_mbar_init();
+    if (g.stagger_ns > 0 && (int)blockIdx.x >= g.stagger_lo && (int)blockIdx.x < 2 * g.stagger_lo) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      do { __nanosleep(256); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < (unsigned long long)g.stagger_ns);
+    }
   }
   __syncthreads();
   // dependent launch (panel chain): everything above overlapped the predecessor's tail; no global access before this
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  if (warp == 4) {
+  // Register reallocation between the warpgroups (setmaxnreg): the kernel is compiled for 128 registers per thread
+  // (2 CTAs x 256 threads = the whole register file); the producer warpgroup shrinks to 40 and the consumer warpgroup
+  // grows to 216, which is what lets the accumulators (128), rolling fragments and addresses live without spills.
+  if (warp >= 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp > 4) return;
     // ------------------------------------------------------------ TMA producer
-    // INIT_COV tiles stage the generated covariance tile in the (still idle) ring: wait until it has been consumed
-    if (INIT == INIT_COV && job.init == INIT_COV) asm volatile("bar.sync 2, 160;" ::: "memory");
     if (lane == 0) {
       for (int it = 0; it < job.nk; it++) {
         const int s = it % STAGES;
@@ -322,72 +331,31 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   }
 
   // -------------------------------------------------------------- DMMA consumers
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
   const int g8 = lane >> 2, q = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;
   double acc[MT][4][2];
   constexpr int WROWS = 8 * MT;  // rows per consumer warp
 
-  // ---- accumulator initialisation
-  bool acc_ready = false;
-  if constexpr (INIT == INIT_COV) if (job.init == INIT_COV) {
-    acc_ready = true;
-    // Thread t generates row t of the tile, 8 columns at a time (cov_vals<8>), into a padded tile in the ring;
-    // the fragments are then read back in the DMMA accumulator layout.
-    double* xaT = (double*)(smem + SM_XS);          // [DGP_XS][128] row-point features, column-major
-    double* xb = xaT + DGP_XS * BM;                 // [64][DGP_XS]  column-point features
-    double* W = (double*)(smem + SM_STAGES);
-    const int t = threadIdx.x;  // 0..127
-    const double* Xw_s = g.Xw + soff_v * DGP_XS;
-    const double* noise_s = g.noise + soff_v;
-    cov_compile(cc, spec, g.theta + (site >= 0 ? site * DGP_MAX_THETA : 0), jitter, t, 128);
-    for (int e = t; e < BM * DGP_XS; e += 128) xaT[(e % DGP_XS) * BM + e / DGP_XS] = Xw_s[(size_t)job.crow * DGP_XS + e];
-    for (int e = t; e < BN * DGP_XS; e += 128) xb[e] = Xw_s[(size_t)job.ccol * DGP_XS + e];
-    consumer_bar();
-    {
-      const int gr = job.crow + t;
-      const double dn = (gr < npts) ? (g.latent ? jitter : noise_s[gr] + cc->extra_noise) : 0.0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += COV_V) {
-        double val[COV_V];
-        cov_vals<COV_V>(cc, xaT, BM, t, xb + c0 * DGP_XS, val);
+  // ---- accumulators start at zero in every variant: what the tile starts from (its old value, INIT_LOAD, or the
+  // covariance entries, INIT_COV) is added in the epilogue, out = start + sign * sum.  The main loop is then the same code
+  // for all variants, nothing waits for the start values before the first DMMA, and an INIT_LOAD tile is prefetched to L2
+  // here so that the epilogue's loads do not pay the DRAM latency.
 #pragma unroll
-        for (int v = 0; v < COV_V; v++) {
-          const int gc = job.ccol + c0 + v;
-          double x = val[v];
-          if (gr < npts && gc < npts) { if (gr == gc) x += dn; }
-          else x = (gr == gc) ? 1.0 : 0.0;
-          W[t * WS + c0 + v] = g.sign * x;
-        }
-      }
+  for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+  if constexpr (INIT == INIT_LOAD || INIT == INIT_COV) if (job.init == INIT_LOAD) {
+    const int t = threadIdx.x;   // 0..127: 8 * MT rows x 4 lines of 128 B
+    const int pr = MT == 8 ? t : (t & 63);
+    const char* rowp = reinterpret_cast<const char*>(g.C + soff_m + (size_t)(job.crow + pr) * g.ldc + job.ccol);
+    if (MT == 8) {
+#pragma unroll
+      for (int l = 0; l < 4; l++) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + 128 * l));
+    } else {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + 256 * (t >> 6)));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + 256 * (t >> 6) + 128));
     }
-    consumer_bar();
-#pragma unroll
-    for (int mi = 0; mi < 8; mi++)
-#pragma unroll
-      for (int ni = 0; ni < 4; ni++) {
-        const double* wp = W + (64 * wm + 8 * mi + g8) * WS + 32 * wn + 8 * ni + 2 * q;
-        acc[mi][ni][0] = wp[0];
-        acc[mi][ni][1] = wp[1];
-      }
-    asm volatile("bar.sync 2, 160;" ::: "memory");  // release the ring to the producer
-  }
-  if (acc_ready) {
-  } else if ((INIT == INIT_LOAD || INIT == INIT_COV) && job.init == INIT_LOAD) {
-#pragma unroll
-    for (int mi = 0; mi < MT; mi++) {
-      const double* crow = g.C + soff_m + (size_t)(job.crow + WROWS * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
-#pragma unroll
-      for (int ni = 0; ni < 4; ni++) {
-        const double2 v = *reinterpret_cast<const double2*>(crow + 8 * ni);
-        acc[mi][ni][0] = g.sign * v.x;
-        acc[mi][ni][1] = g.sign * v.y;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int mi = 0; mi < MT; mi++)
-#pragma unroll
-      for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
   }
 
   // ---- main loop.  Fragment addressing: row r of a 64-row box sits at r*128 B; logical 16-byte chunk
@@ -397,48 +365,173 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
   const uint32_t a_off = (uint32_t)((WROWS * wm + g8) * 128 + (q & 1) * 8);
   const uint32_t b_off = (uint32_t)(A_BYTES + (32 * wn + g8) * 128 + (q & 1) * 8);
   const uint32_t chq = (uint32_t)((q >> 1) * 4);
-  const uint32_t sbase = smem_u32(smem + SM_STAGES);
-  for (int it = 0; it < job.nk; it++) {
-    const int s = it % STAGES;
-    mbar_wait(&full[s], (it / STAGES) & 1);
+  uint32_t sbase = smem_u32(smem + SM_STAGES);
+  asm volatile("" : "+r"(sbase));   // one register, not a re-derivation of the shared window base at every use
+  // Fragment loads roll across k4 steps AND across stages, in the 24 registers one step needs: a step issues its DMMAs as
+  // columns {0,1} of every row block, then columns {2,3}; fb[0..1] are reloaded for the next step after the first half,
+  // fa[mi] after row block mi of the second half, fb[2..3] at the end -- each at least 14 DMMAs (> 200 cycles) before its
+  // first use.  The first fragments of stage it + 1 are loaded under the last DMMAs of stage it (its full barrier is
+  // polled one step earlier), so a warp's DMMA issue does not stop at a stage boundary for the barrier round trip plus
+  // a shared-memory load latency, and one CTA alone keeps the tensor pipe busy while its co-resident CTA is in its tile
+  // prologue / epilogue.
+  double fa[MT], fb[4];
+  auto lds = [&](double& dst, uint32_t addr) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dst) : "r"(addr)); };
+  // chunk of k4 step ks: ((chq + ks) ^ g8) << 4 = sw0 ^ (ks << 4)  (chq is 0 or 4, ks < 4); bits 4..6 of a row base are zero
+  const uint32_t pa = a_off + (((chq) ^ (uint32_t)g8) << 4), pb = b_off + (((chq) ^ (uint32_t)g8) << 4);
+  if (job.nk > 0) {
+    mbar_wait(&full[0], 0);
+#pragma unroll
+    for (int mi = 0; mi < MT; mi++) lds(fa[mi], sbase + pa + mi * 1024);
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) lds(fb[ni], sbase + pb + ni * 1024);
+  }
+  const int nk = job.nk;
+  uint32_t st = sbase;
+  int s = 0;
+  uint32_t ph = 0;   // parity of the full barrier of stage s in this round of the ring
+  for (int it = 0; it < nk; it++) {
     // Release the PREVIOUS stage only now.  Its fragment loads are known to have returned: every DMMA of
     // that stage was issued (in order, operands scoreboarded) before the loop back-edge.  Releasing at
     // the end of the stage itself is not safe: the arrive can overtake shared-memory loads still queued
     // behind the co-resident CTA's global-load burst, and the TMA refill then lands under them.
     if (it > 0) {
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[(it - 1) % STAGES]);
+      if (lane == 0) mbar_arrive(&empty[(s + STAGES - 1) % STAGES]);
     }
-    const uint32_t st = sbase + s * STAGE_BYTES;
+    const int s2 = (s + 1 == STAGES) ? 0 : s + 1;
+    const uint32_t ph2 = (s + 1 == STAGES) ? (ph ^ 1u) : ph;
+    const uint32_t st2 = sbase + s2 * STAGE_BYTES;
+    const bool more = it + 1 < nk;
+    bool ready = true;
+    // next step's fragments: this stage, or k4 step 0 of the next one (after the last stage: this stage again, unused)
+    const uint32_t stn = more ? st2 : st;
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
-      const uint32_t sw = ((chq + ks) ^ (uint32_t)g8) << 4;
-      double a[MT], b[4];
+      if (ks == 2 && more) ready = mbar_try_wait(&full[s2], ph2);
+      if (ks == 3 && more && !ready) mbar_wait(&full[s2], ph2);
+      const uint32_t na = (((ks < 3) ? st : stn) + pa) ^ (uint32_t)(((ks + 1) & 3) << 4);
+      const uint32_t nb_ = (((ks < 3) ? st : stn) + pb) ^ (uint32_t)(((ks + 1) & 3) << 4);
 #pragma unroll
-      for (int mi = 0; mi < MT; mi++)
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[mi]) : "r"(st + a_off + mi * 1024 + sw));
+      for (int mi = 0; mi < MT; mi++) {
+        dmma(acc[mi][0], fa[mi], fb[0]);
+        dmma(acc[mi][1], fa[mi], fb[1]);
+      }
+      lds(fb[0], nb_);
+      lds(fb[1], nb_ + 1024);
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++)
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[ni]) : "r"(st + b_off + ni * 1024 + sw));
-#pragma unroll
-      for (int mi = 0; mi < MT; mi++)
-#pragma unroll
-        for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni], a[mi], b[ni]);
+      for (int mi = 0; mi < MT; mi++) {
+        dmma(acc[mi][2], fa[mi], fb[2]);
+        dmma(acc[mi][3], fa[mi], fb[3]);
+        lds(fa[mi], na + mi * 1024);
+      }
+      lds(fb[2], nb_ + 2 * 1024);
+      lds(fb[3], nb_ + 3 * 1024);
     }
+    st = st2; s = s2; ph = ph2;
   }
 
   // ---- epilogue
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if constexpr (EPI == EPI_STORE) {
+    // The output address is recomputed from the block index (through an opaque copy, so that the compiler cannot keep
+    // the values of the prologue alive instead): the main loop needs every register for accumulators and fragments.
+    int bx = blockIdx.x, tx = threadIdx.x;
+    asm volatile("" : "+r"(bx), "+r"(tx));
+    int tile_e = MT == 8 ? bx : (bx >> 1);
+    JobCtx je{g.mode, g.step, g.nb, g.aux0, g.aux1, g.aux2, g.raster};
+    size_t soff_e = 0;
+    int site_e = -1, npts_e = g.n;
+    if (bt.count > 0) {
+      int k = 0;
+#pragma unroll 1
+      for (int i = 1; i < bt.count; i++) if (tile_e >= bt.e[i].tile0) k = i;
+      const BatchEnt& e = bt.e[k];
+      tile_e -= e.tile0; site_e = e.site; npts_e = e.n;
+      je.step = e.step; je.nb = e.nb; je.aux0 = e.aux0; je.aux1 = e.aux1; je.aux2 = e.aux2;
+      soff_e = (size_t)e.site * (size_t)bt.ld * (size_t)bt.ld;
+    }
+    const Job jo = decode_job(je, tile_e, INIT);
+    const int crow_e = jo.crow + (MT == 4 ? 64 * (bx & 1) : 0);
+    const int lane_e = tx & 31, warp_e = tx >> 5;
+    const int g8e = lane_e >> 2, qe = lane_e & 3, wme = warp_e >> 1, wne = warp_e & 1;
+    bool gen = false;
+    if constexpr (INIT == INIT_COV) gen = (jo.init == INIT_COV);
+    if (gen) {
+      if constexpr (INIT == INIT_COV) {
+        // First touch of the tile: out = K + sign * sum.  The accumulators are parked in the (now idle) operand ring as a
+        // padded tile, thread t then generates row t of the covariance tile, 8 columns at a time (cov_vals<8>, with every
+        // register free for it), combines it with the parked sums in place, and the tile leaves in 512-byte rows.
+        const double jit_e = site_e >= 0 ? bt.jitv[site_e] : g.jitter;
+        const size_t soff_ve = site_e >= 0 ? (size_t)site_e * (size_t)bt.ld : 0;
+        double* xaT = (double*)(smem + SM_XS);          // [DGP_XS][128] row-point features, column-major
+        double* xb = xaT + DGP_XS * BM;                 // [64][DGP_XS]  column-point features
+        double* W = (double*)(smem + SM_STAGES);        // [128][WS]
+        const double* Xw_s = g.Xw + soff_ve * DGP_XS;
+        const double* noise_s = g.noise + soff_ve;
+        consumer_bar();                                  // every warp is done reading the ring
 #pragma unroll
-    for (int mi = 0; mi < MT; mi++) {
-      double* crow = g.C + soff_m + (size_t)(job.crow + WROWS * wm + 8 * mi + g8) * g.ldc + job.ccol + 32 * wn + 2 * q;
+        for (int mi = 0; mi < 8; mi++)
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++) {
-        double2 v;
-        v.x = g.sign * acc[mi][ni][0];
-        v.y = g.sign * acc[mi][ni][1];
-        *reinterpret_cast<double2*>(crow + 8 * ni) = v;
+          for (int ni = 0; ni < 4; ni++) {
+            double* wp = W + (64 * wme + 8 * mi + g8e) * WS + 32 * wne + 8 * ni + 2 * qe;
+            wp[0] = g.sign * acc[mi < MT ? mi : 0][ni][0];
+            wp[1] = g.sign * acc[mi < MT ? mi : 0][ni][1];
+          }
+        cov_compile(cc, spec, g.theta + (site_e >= 0 ? site_e * DGP_MAX_THETA : 0), jit_e, tx, 128);
+        for (int e = tx; e < BM * DGP_XS; e += 128) xaT[(e % DGP_XS) * BM + e / DGP_XS] = Xw_s[(size_t)jo.crow * DGP_XS + e];
+        for (int e = tx; e < BN * DGP_XS; e += 128) xb[e] = Xw_s[(size_t)jo.ccol * DGP_XS + e];
+        consumer_bar();
+        {
+          const int gr = jo.crow + tx;
+          const double dn = (gr < npts_e) ? (g.latent ? jit_e : noise_s[gr] + cc->extra_noise) : 0.0;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += COV_V) {
+            double val[COV_V];
+            cov_vals<COV_V>(cc, xaT, BM, tx, xb + c0 * DGP_XS, val);
+#pragma unroll
+            for (int v = 0; v < COV_V; v++) {
+              const int gc = jo.ccol + c0 + v;
+              double x = val[v];
+              if (gr < npts_e && gc < npts_e) { if (gr == gc) x += dn; }
+              else x = (gr == gc) ? 1.0 : 0.0;
+              W[tx * WS + c0 + v] += x;
+            }
+          }
+        }
+        consumer_bar();
+        {  // warp w stores rows 32 w .. 32 w + 31, one 512-byte row per instruction
+          double* cbase = g.C + soff_e + (size_t)jo.crow * g.ldc + jo.ccol + 2 * lane_e;
+#pragma unroll 4
+          for (int r = 32 * warp_e; r < 32 * warp_e + 32; r++) {
+            double2 o;
+            o.x = W[r * WS + 2 * lane_e];
+            o.y = W[r * WS + 2 * lane_e + 1];
+            *reinterpret_cast<double2*>(cbase + (size_t)r * g.ldc) = o;
+          }
+        }
+      }
+    } else {
+      const bool ldc = (INIT == INIT_LOAD || INIT == INIT_COV) && jo.init == INIT_LOAD;
+#pragma unroll
+      for (int mi = 0; mi < MT; mi++) {
+        double* crow = g.C + soff_e + (size_t)(crow_e + WROWS * wme + 8 * mi + g8e) * g.ldc + jo.ccol + 32 * wne + 2 * qe;
+        double2 old[4];
+        if (ldc) {
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) old[ni] = *reinterpret_cast<const double2*>(crow + 8 * ni);
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+          double2 v;
+          if (ldc) {
+            v.x = fma(g.sign, acc[mi][ni][0], old[ni].x);
+            v.y = fma(g.sign, acc[mi][ni][1], old[ni].y);
+          } else {
+            v.x = g.sign * acc[mi][ni][0];
+            v.y = g.sign * acc[mi][ni][1];
+          }
+          *reinterpret_cast<double2*>(crow + 8 * ni) = v;
+        }
       }
     }
   } else if constexpr (EPI == EPI_SUMSQ) {

@@ -430,12 +430,12 @@ k_upperT_gemv_sum_b(const __grid_constant__ SiteDims sd, const double* __restric
 }
 
 // ------------------------------------------------------------------ T21 = U12^T for every pair of one merge level
-// Pair p merges block ranges [o, o+h) and [o+h, o+2h), o = 2 h p.  grid.x = pairs * (4h)^2 tiles of 32x32.
+// Pair p merges block ranges [o, o+h) and [o+h, o+2h), o = 2 h p.  grid.x = pairs * (4h)^2 tiles of 32x32; pr0 = first pair.
 __device__ __forceinline__ void transpose_pairs_body(const double* __restrict__ U, double* __restrict__ T, long long ld, int hb,
-                                                     int npad, int bx) {
+                                                     int npad, int bx, int pr0) {
   __shared__ double tile[32][33];
   const int per = 16 * hb * hb;
-  const int pr = bx / per, rem = bx % per;
+  const int pr = pr0 + bx / per, rem = bx % per;
   const int ty32 = rem / (4 * hb), tx32 = rem % (4 * hb);
   const int r0 = pr * 2 * hb * 128 + ty32 * 32, c0 = (pr * 2 * hb + hb) * 128 + tx32 * 32;
   if (c0 >= npad) return;
@@ -445,18 +445,18 @@ __device__ __forceinline__ void transpose_pairs_body(const double* __restrict__ 
   for (int r = ty; r < 32; r += 8) T[(size_t)(c0 + r) * ld + r0 + tx] = tile[tx][r];
 }
 __global__ void __launch_bounds__(256)
-k_transpose_pairs(const double* __restrict__ U, double* __restrict__ T, long long ld, int hb, int npad) {
-  transpose_pairs_body(U, T, ld, hb, npad, blockIdx.x);
+k_transpose_pairs(const double* __restrict__ U, double* __restrict__ T, long long ld, int hb, int npad, int pr0) {
+  transpose_pairs_body(U, T, ld, hb, npad, blockIdx.x, pr0);
 }
-// grid = (max over sites of pairs * 16 hb^2, sites); a site takes part while the next merge level needs its T21 (2 hb < nb)
+// grid = (max over sites of pairs * 16 hb^2, sites); per site the pairs [pr0, pr0 + cnt) of this launch (cnt = 0: none)
+struct PairRange { short pr0[DGP_BATCH_MAX], cnt[DGP_BATCH_MAX]; };
 __global__ void __launch_bounds__(256)
-k_transpose_pairs_b(const __grid_constant__ SiteDims sd, const double* __restrict__ U, double* __restrict__ T, int hb) {
+k_transpose_pairs_b(const __grid_constant__ SiteDims sd, const __grid_constant__ PairRange pr, const double* __restrict__ U,
+                    double* __restrict__ T, int hb) {
   const int st = blockIdx.y, nb = sd.nb[st];
-  if (2 * hb >= nb) return;
-  const int npairs = (nb - hb + 2 * hb - 1) / (2 * hb);
-  if ((int)blockIdx.x >= npairs * 16 * hb * hb) return;
+  if ((int)blockIdx.x >= pr.cnt[st] * 16 * hb * hb) return;
   const size_t m = (size_t)st * sd.ld * sd.ld;
-  transpose_pairs_body(U + m, T + m, sd.ld, hb, nb * 128, blockIdx.x);
+  transpose_pairs_body(U + m, T + m, sd.ld, hb, nb * 128, blockIdx.x, pr.pr0[st]);
 }
 
 // ------------------------------------------------------------------ final reductions (deterministic order)
