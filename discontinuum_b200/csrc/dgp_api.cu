@@ -411,6 +411,11 @@ int dgp_create_partitioned(dgp_handle* out, int device, int max_n, int max_m, in
   h->stream_hi = (cudaStream_t)st_hi;
   cudaStreamDestroy(h->stream_t2);          // one trailing-update stream inside a partition (no column strips)
   h->stream_t2 = nullptr;
+  if (h->stream_lo) {                       // ... and no helper stream outside it for the inverse / LAUUM phases
+    cudaStreamDestroy(h->stream_lo);
+    h->stream_lo = nullptr;
+    for (int i = 0; i < 2; i++) if (h->ev_lo[i]) { cudaEventDestroy(h->ev_lo[i]); h->ev_lo[i] = nullptr; }
+  }
   h->own_stream = true;                     // both streams are the handle's to destroy
   h->sms = P.sms;
   return 0;
