@@ -696,9 +696,37 @@ k_wgrad(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta,
 // learned-noise slot), wgt = 2 below the diagonal, 1 on it.  Same tiling as the LAUUM launch that wrote Kinv
 // (128 x 64 lower tiles, tile -> (i, c) triangular), one thread per row, 4 columns side by side.  Unlike the fused
 // epilogue this runs with every warp of the SM on FP64 ALU work, so the pipe is not shared with DMMA issue.
+#ifndef DGP_GC_V
+#define DGP_GC_V 4   // entries a thread evaluates side by side in the gradient contraction
+#endif
 #ifndef DGP_GC_BLOCKS
 #define DGP_GC_BLOCKS 4
 #endif
+// one row of a 128 x 64 tile of W = alpha alpha' - Ky^-1 against d(term)/d(parameters), 4 entries side by side
+template <class S>
+__device__ __forceinline__ void grad_row(const TermC& tc, const double* __restrict__ xaT, int t, const double* __restrict__ xb,
+                                         const double* __restrict__ al, const double* __restrict__ krow, double ai, int grow,
+                                         int c0b, bool row_live, double (&sl)[NSLOT]) {
+  if (!row_live) return;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 64; c0 += DGP_GC_V) {
+    if (c0b + c0 > grow) break;  // strictly above the diagonal from here on
+    double w[DGP_GC_V];
+#pragma unroll
+    for (int v2 = 0; v2 < DGP_GC_V; v2 += 2) {
+      const double2 kk = *reinterpret_cast<const double2*>(krow + c0 + v2);
+      const double kv[2] = {kk.x, kk.y};
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int gcol = c0b + c0 + v2 + e;
+        const double wgt = (gcol < grow) ? 2.0 : (gcol == grow ? 1.0 : 0.0);
+        w[v2 + e] = wgt * (ai * al[c0 + v2 + e] - kv[e]);
+      }
+    }
+    term_grad_accum_s<DGP_GC_V, S>(tc, xaT, 128, t, xb + c0 * DGP_XS, w, sl);
+  }
+}
+
 __device__ __forceinline__ void grad_contract_body(const dgp_spec& spec, const double* __restrict__ theta, const double* __restrict__ Xw,
                 const double* __restrict__ alpha, const double* __restrict__ Kinv, long long ld, int n,
                 double* __restrict__ part, int tile) {
@@ -723,27 +751,17 @@ __device__ __forceinline__ void grad_contract_body(const dgp_spec& spec, const d
   const double ai = alpha[grow];
   const double* krow = Kinv + (size_t)grow * ld + c0b;
   double trw = 0.0;
+  const bool row_live = grow < n;
+  // trace of W on the diagonal entries of this row (noise / jitter parameter), once per row
+  if (row_live && grow >= (int)c0b && grow < (int)c0b + 64) trw = ai * al[grow - (int)c0b] - krow[grow - (int)c0b];
   for (int term = 0; term < cc.nterms; term++) {
     double sl[NSLOT];
 #pragma unroll
     for (int k = 0; k < NSLOT; k++) sl[k] = 0.0;
     const TermC& tc = cc.t[term];
-#pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 4) {
-      if (grow >= n || (int)c0b + c0 > grow) continue;  // padding rows / strictly above the diagonal
-      const double2 k01 = *reinterpret_cast<const double2*>(krow + c0);
-      const double2 k23 = *reinterpret_cast<const double2*>(krow + c0 + 2);
-      const double kv[4] = {k01.x, k01.y, k23.x, k23.y};
-      double w[4];
-#pragma unroll
-      for (int v = 0; v < 4; v++) {
-        const int gcol = (int)c0b + c0 + v;
-        const double wgt = (gcol < grow) ? 2.0 : (gcol == grow ? 1.0 : 0.0);
-        w[v] = wgt * (ai * al[c0 + v] - kv[v]);
-        if (term == 0 && gcol == grow) trw += w[v];
-      }
-      term_grad_accum_v<4>(tc, xaT, 128, t, xb + c0 * DGP_XS, w, sl);
-    }
+    // the shape switch is taken once per term and row, around the whole row of the tile: inside a specialisation the
+    // slots the shape does not have stay compile-time zeros instead of 17 live accumulators
+    DGP_SHAPE_SWITCH(tc.shape, (grad_row<S>(tc, xaT, t, xb, al, krow, ai, grow, (int)c0b, row_live, sl)))
 #pragma unroll
     for (int k = 0; k < NSLOT; k++) {
       double v = sl[k];
