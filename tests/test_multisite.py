@@ -231,3 +231,22 @@ def test_sample_sharded_single_rank_matches_engine_sample(cuda_device):
 
 def test_panel_owner_cyclic():
     assert [multisite.panel_owner(p, 4) for p in range(6)] == [0, 1, 2, 3, 0, 1]
+
+
+@pytest.mark.gpu
+def test_sample_sharded_two_ranks_match_single_gpu_draws(cuda_device):
+    """world = 2 over NCCL (one process per GPU, torchrun): the panel-cyclic distributed draws equal single-GPU dgp_sample_ex
+    with the same Philox normals on every rank (tests/dist_sample_check.py).  Needs two visible GPUs; on a one-GPU box the
+    same check runs inside `bench.py --gpus N` (extra.config5.check_sharded_vs_single_gpu_draws_rel)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(here, "dist_sample_check.py"), "900", "2600", "8"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert r.stdout.count(" OK") == 2, r.stdout[-2000:]
