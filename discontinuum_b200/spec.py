@@ -219,8 +219,12 @@ class GPModule(torch.nn.Module):
         """(natural[P], d natural / d raw [P], sum of log priors, d(sum log prior) / d natural [P]) in numpy float64:
         the constraint transforms and priors of `natural()` / `log_prior()` with their
         derivatives in closed form, for the optimiser loop's fast path (no autograd graph per iteration)."""
+        return self.host_chain_raw(np.array([float(r.detach()) for r in self.raw_list()], dtype=np.float64))
+
+    def host_chain_raw(self, raw: np.ndarray):
+        """host_chain at the raw parameter vector `raw` (numpy, [P]) instead of the module's tensors: the optimiser loop's
+        numpy path keeps the raw parameters in one array and touches no tensor per iteration."""
         kind, lb, lo, hi, pk, pa, pb, pc = self._tables()
-        raw = np.array([float(r.detach()) for r in self.raw_list()], dtype=np.float64)
         sig = 1.0 / (1.0 + np.exp(-raw))
         sp = np.where(raw > 20.0, raw, np.log1p(np.exp(np.minimum(raw, 20.0))))  # torch softplus, threshold 20
         nat = np.where(kind == 1, sp + lb, np.where(kind == 2, lo + (hi - lo) * sig, raw))

@@ -303,3 +303,63 @@ def test_checkpoint_keys_follow_the_reference_module_tree():
     model_only = {k: v for k, v in rsd.items() if not k.startswith("likelihood.")}
     checkpoint.load_state(r2, model_only, rlik)   # learned noise taken from the likelihood state dict
     assert all(float(a.detach()) == float(b.detach()) for a, b in zip(r.raw_list(), r2.raw_list()))
+
+
+@pytest.mark.parametrize("model,opt", [("loadest", "adam"), ("loadest", "adamw"), ("rating", "adam")])
+def test_numpy_optimiser_path_matches_torch_path(model, opt, monkeypatch):
+    """MarginalB200.fit's numpy optimiser path (raw parameters, Adam moments and chain rule in numpy vectors, no tensor
+    per iteration) against its torch path (torch.optim.Adam / AdamW fused step on the module's tensors): same objective
+    history, same final raw parameters, same optimiser state for save / resume, also across an interrupted-and-resumed fit.
+    The engine is the CPU oracle stand-in (no GPU needed)."""
+    from discontinuum_b200 import synthetic
+
+    rng = np.random.default_rng(5)
+    n = 40
+    days = np.sort(rng.uniform(0, 3650, n))
+    time = np.datetime64("2005-01-01") + (days * 86400e9).astype("timedelta64[ns]")
+    if model == "loadest":
+        flow = np.exp(1.0 + 0.8 * np.sin(2 * np.pi * days / 365.25) + 0.5 * rng.standard_normal(n))
+        cov = {"time": time, "flow": flow}
+        target = np.exp(0.3 * np.log(flow) + 0.2 * np.cos(2 * np.pi * days / 365.25) + 0.2 * rng.standard_normal(n))
+        kw = {}
+    else:
+        stage = rng.lognormal(1.0, 0.5, n)
+        cov = {"time": time, "stage": stage}
+        target = 3.0 * (stage - 0.5 * stage.min()) ** 1.6 * np.exp(0.03 * rng.standard_normal(n))
+        kw = dict(target_unc=rng.choice(np.array([1.02, 1.05, 1.08]), n))
+
+    def make():
+        m = models.LoadestGP() if model == "loadest" else models.RatingGP()
+        fake = _FakeEngine(model, np.zeros((1, 2)), np.zeros(1), np.zeros(1))
+
+        def bind(self=m):
+            # serve the oracle on what the engine would be given (the data manager has standardised the inputs)
+            fake.X, fake.y = torch.tensor(self.X), torch.tensor(self.y)
+            fake.noise = torch.tensor(np.asarray(self.fixed_noise, dtype=np.float64) * np.ones(self.X.shape[0]))
+            self._engine = fake
+            self._factorized_at = None
+
+        m._bind_engine = bind
+        return m
+
+    out = {}
+    for path in ("torch", "numpy"):
+        monkeypatch.setenv("DGP_HOST_OPT", path)
+        torch.manual_seed(0)   # (rating-gp draws its initial power-law parameters from torch's generator)
+        m = make()
+        m.fit(cov, target, iterations=12, optimizer=opt, learning_rate=0.1, **kw)
+        h1 = list(m.history)
+        m.fit(cov, target, iterations=20, resume=True, **kw)          # interrupted-and-resumed: 8 more iterations
+        raw = np.array([float(p.detach()) for p in m.model.raw_list()])
+        st = m._last_optimizer.state_dict()["state"]
+        out[path] = (np.array(h1 + list(m.history)), raw,
+                     np.array([float(st[k]["exp_avg"].reshape(-1)[0]) for k in sorted(st)]),
+                     np.array([float(st[k]["exp_avg_sq"].reshape(-1)[0]) for k in sorted(st)]),
+                     [float(st[k]["step"]) for k in sorted(st)], m._last_optimizer.param_groups[0]["lr"])
+    a, b = out["torch"], out["numpy"]
+    assert len(a[0]) == len(b[0]) >= 20   # (resume continues from the last started iteration, as the reference does)
+    assert np.max(np.abs(a[0] - b[0]) / np.abs(a[0])) <= 1e-10
+    assert np.max(np.abs(a[1] - b[1])) <= 1e-9 * max(1.0, np.max(np.abs(a[1])))
+    assert np.max(np.abs(a[2] - b[2])) <= 1e-9 * max(1e-3, np.max(np.abs(a[2])))
+    assert np.max(np.abs(a[3] - b[3])) <= 1e-9 * max(1e-6, np.max(np.abs(a[3])))
+    assert a[4] == b[4] and a[5] == b[5]
