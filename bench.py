@@ -302,6 +302,7 @@ def main():
         grids = {k: synthetic.daily_grid(sites[k][0], 10958) for k in mine}
         multisite.fit_sites_local({999: synthetic.loadest_site(512, 7), 998: synthetic.loadest_site(300, 8)}, iterations=3,
                                   device=local, group=2)   # warm-up: kernels loaded, pinned buffers touched
+        multisite.gather_results({-1 - rank: {"warm": True}}, dist)   # ... and the gather's point-to-point channels connected
         barrier()
         stats = {}
         t0 = time.perf_counter()

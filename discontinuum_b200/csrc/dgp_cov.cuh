@@ -293,7 +293,7 @@ __device__ __forceinline__ void term_grad_accum(const TermC& tc, const double* x
 //   Periodic: poly 1, expo 2 sin^2(pi dx / p) / lam   (sinpi: exact range reduction, no slow path)
 // and the V entries are evaluated side by side so that the FP64 pipe sees V independent dependency chains.
 __device__ __forceinline__ double fast_sqrt_nonneg(double d2) {
-  return d2 > 0.0 ? d2 * rsqrt(d2) : 0.0;
+  return d2 > 0.0 ? d2 * rsqrt(d2) : d2;   // d2 = 0 -> 0; a NaN (poisoned length scale) stays a NaN instead of turning into 0
 }
 
 // out[v] += value of term tc for the V entries
