@@ -85,6 +85,7 @@ struct dgp_handle_s {
   cudaStream_t stream_t2 = nullptr;  // second trailing-update stream (same priority as `stream`): column strips alternate
   int eager_inv = 1;                 // merges of the inverse launched as the factorisation passes them (DGP_EAGER_INV=0: after it)
   int eager_lag = 0;                 // ... released this many block columns late (DGP_EAGER_LAG)
+  int eager_max_h = 0;               // above 96 block columns: highest merge level that goes early (DGP_EAGER_MAXH; 0 = none: measured no gain at n = 16384 for 4 / 8 / 16 / 32)
   int strip_blocks = 8;              // width of a column strip in block columns (DGP_STRIP_BLOCKS, 0: one stream, no strips)
   bool inpanel_left = false;         // in-panel updates left-looking (one rank-(128 j) update per column; DGP_INPANEL_LEFT=1)
   struct GraphSlot { cudaGraphExec_t exec = nullptr; double jitter = 0.0; bool seen = false; long long launches = 0; };
@@ -296,6 +297,8 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
     }
     const char* ei = getenv("DGP_EAGER_INV");
     if (ei) h->eager_inv = atoi(ei);
+    const char* em = getenv("DGP_EAGER_MAXH");
+    if (em && atoi(em) >= 0) h->eager_max_h = atoi(em);
     const char* el = getenv("DGP_EAGER_LAG");
     if (el && atoi(el) >= 0) h->eager_lag = atoi(el) / 8 * 8;
     const char* sb = getenv("DGP_STRIP_BLOCKS");
@@ -807,12 +810,14 @@ struct InvProgress {
   bool want_T;
   cudaStream_t W;
   int lag;            // release the merges `lag` block columns late (DGP_EAGER_LAG)
+  int max_h;          // highest level (block count of a merged range) launched before the factorisation is complete
 };
 
 static int trtri_advance(dgp_handle h, InvProgress& ip, int F) {
   const int nb = h->nb;
   int rc, lv = 0;
   for (int hb = 1; hb < nb; hb *= 2, lv++) {
+    if (F < nb && hb > ip.max_h) break;   // while the factorisation runs: only the levels whose tiles are short
     const int npairs = (nb - hb + 2 * hb - 1) / (2 * hb);  // pairs whose second range is non-empty
     const int avail = F >= nb ? npairs : F / (2 * hb);
     const int pr0 = ip.done[lv], cnt = avail - pr0;
@@ -901,10 +906,11 @@ static int evaluate_enqueue(dgp_handle h, double jitter, int level) {
   InvProgress ip;
   memset(&ip, 0, sizeof(ip));
   ip.want_T = (level == 2); ip.W = lo ? h->stream_lo : main_stream; ip.lag = h->eager_lag;
+  // (measured: every level is a gain up to n = 8192 and for batches; at n = 16384 the long low-priority tiles of the high
+  // levels cost the chain of the last panels as much as they fill -- there only the levels up to eager_max_h go early)
+  ip.max_h = (h->eager_inv > 1 || h->nb <= 96) ? (1 << 20) : h->eager_max_h;
   PanelHook hook;
-  // (measured: a gain up to n = 8192 and for batches; at n = 16384 the long low-priority tiles cost the chain of the last
-  // panels as much as they fill, DGP_EAGER_INV=2 forces it on)
-  if (lo && h->lookahead && (h->eager_inv > 1 || (h->eager_inv == 1 && h->nb <= 96))) { hook.fn = eager_hook; hook.ctx = &ip; }
+  if (lo && h->lookahead && h->eager_inv >= 1 && ip.max_h >= 1) { hook.fn = eager_hook; hook.ctx = &ip; }
   if ((rc = run_potrf(h, jitter, level == 0, hook))) return rc;  // level >= 1: z = U'r after the inverse instead
   if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
   if (level >= 1) {
