@@ -5,14 +5,25 @@ hot path when GPyTorch takes the exact-Cholesky branch (n <= max_cholesky_size).
 checker for the CUDA engine: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import it.  The product package never does.
 
-PARITY STATUS: "parity unpinned" at the third-party boundary.  The arithmetic of the reference
-lives in gpytorch / linear_operator (unpinned in /root/reference/pyproject.toml:19-25), which are
-not installed in this image, and the reference's own tests assert no numbers on this path
-(tests/test_loadest_gp.py:77-85, tests/test_rating_gp.py:32-65).  The oracle is therefore pinned
-by (i) 40-digit mpmath known-answer vectors (oracle/make_golden.py -> tests/golden/*.json),
-(ii) analytic n=1 / n=2 closed forms, (iii) autograd-vs-closed-form gradient agreement and (iv) scikit-learn's
-independent exact-GP implementation (covariance formulas, log marginal likelihood, its gradient, predictive mean and
-variance: tests/test_oracle_vs_sklearn.py) -- a third-party implementation of the same mathematics, not the reference.
+PARITY STATUS.  Two layers, pinned differently:
+  * what the REFERENCE owns (which kernels act on which dimensions with which priors, constraints and initial values; the
+    sigmoid gate, its inversion and the log warp of rating_gp/models/kernels.py; PowerLawTransform and its clamps; the noise
+    model; the objective as engines/gpytorch.py:318,353 forms it; the whole optimiser loop of engines/gpytorch.py:162-458;
+    the module tree whose parameter paths are the checkpoint keys) is pinned by OUTPUTS OF THE REFERENCE'S OWN CODE RUN HERE:
+    oracle/make_reference_golden.py imports the unmodified model and engine modules from /root/reference/src, executes
+    them on a small stand-in for the gpytorch API (oracle/gpytorch_standin) and writes tests/golden/ref_models.json
+    (covariance matrices, means, objectives, latent posteriors at two parameter sets per model; 30-iteration objective
+    trajectories of MarginalGPyTorch.fit for loadest Adam / AdamW and rating Adam).  tests/test_reference_golden.py holds
+    this oracle (<= 1e-10 / 1e-8), the checkpoint key mapping and, on the GPU, the CUDA engine and MarginalB200.fit to them.
+  * the THIRD-PARTY layer underneath (gpytorch / linear_operator: unpinned in /root/reference/pyproject.toml:19-25, not
+    installable in this image or on the GPU box; the reference's own tests assert no numbers on this path,
+    tests/test_loadest_gp.py:77-85, tests/test_rating_gp.py:32-65) stays "parity unpinned" in the strict sense: its kernel,
+    constraint, prior and marginal-likelihood formulas are restated from gpytorch's documentation both
+    here and in the stand-in.  They are checked by (i) 40-digit mpmath known-answer vectors (oracle/make_golden.py ->
+    tests/golden/kat_*.json), (ii) analytic n=1 / n=2 closed forms, (iii) autograd-vs-closed-form gradient agreement,
+    (iv) scikit-learn's independent exact-GP implementation (tests/test_oracle_vs_sklearn.py) and (v)
+    tests/test_vs_gpytorch.py, which compares oracle and engine with the real library wherever it is importable (skipped
+    here).
 
 What each function follows (paths relative to /root/reference/src):
   loadest_cov / loadest_mean      loadest_gp/models/gpytorch.py:61-128 (covar_module :71, mean :70)

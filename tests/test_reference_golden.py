@@ -1,0 +1,203 @@
+"""Vectors produced by the REFERENCE's own model-building code (tests/golden/ref_models.json, made by
+oracle/make_reference_golden.py in the build container, where /root/reference is readable): the unmodified `ExactGPModel`
+classes, custom kernels, `PowerLawTransform` and `NoOpMean` of loadest-gp / rating-gp, executed on the gpytorch stand-in of
+oracle/gpytorch_standin.  They pin what the reference owns -- which kernels act on which dimensions with which priors,
+constraints and initial values, the gate and its inversion, the log warp, the power-law mean, the noise model, and the module
+tree whose parameter paths are the checkpoint keys -- for the oracle, for the checkpoint key mapping and (GPU) for the engine.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from helpers import orc
+from discontinuum_b200 import checkpoint, models, spec
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_models.json")
+RTOL = 1e-10
+
+
+def _cases():
+    with open(GOLD) as f:
+        return json.load(f)["cases"]
+
+
+def _module_from_reference_state(case):
+    """GPModule of this repo filled from the reference-named state dicts (checkpoint.load_state = MarginalB200.load's path)."""
+    X = np.array(case["X"])
+    if case["model"] == "loadest":
+        mod = spec.GPModule(models.loadest_spec(X.shape[1]))
+    else:
+        b_lo, b_hi = models.stage_quantile_bounds(X[:, 1])
+        mod = spec.GPModule(models.rating_spec(b_lo, b_hi))
+    sd = {k: torch.tensor(v, dtype=torch.float64) for k, v in case["state_dict"].items()}
+    lik = {k: torch.tensor(v, dtype=torch.float64) for k, v in case["likelihood_state_dict"].items()}
+    checkpoint.load_state(mod, sd, lik)
+    return mod
+
+
+def _oracle_pieces(case, mod):
+    X, y, noise = (torch.tensor(np.array(case[k], dtype=np.float64)) for k in ("X", "y", "noise"))
+    theta = mod.natural().detach().numpy()
+    if case["model"] == "loadest":
+        nat = H.loadest_nat_from_theta(theta, X.shape[1])
+        return X, y, noise, theta, nat, orc.loadest_cov, orc.loadest_mean, None, orc.loadest_log_prior(nat)
+    nat = H.rating_nat_from_theta(theta)
+    return X, y, noise, theta, nat, orc.rating_cov, orc.rating_mean, nat["noise"], orc.rating_log_prior(nat)
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_oracle_matches_reference_model_code(idx):
+    case = _cases()[idx]
+    mod = _module_from_reference_state(case)
+    # every learnable parameter of the reference's module tree is consumed by the key mapping, none is left over
+    table, aliases = checkpoint._table(mod)
+    known = {k for k, _ in table.values()} | {a for v in aliases.values() for a in v}
+    assert set(case["parameter_names"]) <= known, set(case["parameter_names"]) - known
+    X, y, noise, theta, nat, cov, mean, extra, lp = _oracle_pieces(case, mod)
+    K_ref, m_ref = np.array(case["K"]), np.array(case["mean"])
+    K = cov(X, X, nat).numpy()
+    assert np.max(np.abs(K - K_ref)) <= RTOL * np.max(np.abs(K_ref)), case["case"]
+    assert np.max(np.abs(mean(X, nat).numpy() - m_ref)) <= RTOL * max(1.0, np.max(np.abs(m_ref)))
+    n = X.shape[0]
+    val = orc.nlml(cov, mean, nat, X, y, noise, extra_noise=extra)
+    obj = float((val - lp) / n)
+    assert abs(obj - case["objective"]) <= RTOL * abs(case["objective"]), (obj, case["objective"])
+    # the host-side objective of the engine class (constraints + priors of GPModule) says the same
+    assert abs(float(((val - mod.log_prior(mod.natural())) / n).detach()) - case["objective"]) <= RTOL * abs(case["objective"])
+    # latent posterior at new points (engines/gpytorch.py:621: model(x*) in eval mode)
+    Xs = torch.tensor(np.array(case["Xs"]))
+    mu, _, var_lat = orc.predict(cov, mean, nat, X, y, noise, Xs, extra_noise=extra, min_variance=0.0)
+    assert np.max(np.abs(mu.numpy() - np.array(case["post_mean"]))) <= 1e-8 * max(1.0, np.max(np.abs(case["post_mean"])))
+    assert np.max(np.abs(var_lat.numpy() - np.array(case["post_var"]))) <= 1e-8 * max(1e-3, np.max(np.abs(case["post_var"])))
+    if case["model"] == "rating":
+        # constants the reference fixes in code: gate sharpness, switch-point interval from the stage quantiles, noise floor
+        assert case["gate_a"] == 20.0
+        sd = case["state_dict"]
+        b_lo, b_hi = models.stage_quantile_bounds(np.array(case["X"])[:, 1])
+        assert abs(sd["covar_module.kernels.0.kernels.0.raw_b_constraint.lower_bound"] - b_lo) <= 1e-15
+        assert abs(sd["covar_module.kernels.0.kernels.0.raw_b_constraint.upper_bound"] - b_hi) <= 1e-15
+        assert abs(float(nat["noise"]) - case["second_noise"][0]) <= 1e-14
+
+
+def test_reference_state_round_trips_through_the_checkpoint_mapping():
+    """to_reference_state(load_state(reference state)) reproduces every learnable tensor of the reference's state dicts,
+    names and shapes included (what MarginalB200.save writes is what MarginalGPyTorch.load_state_dict reads)."""
+    for case in _cases():
+        mod = _module_from_reference_state(case)
+        sd, lik = checkpoint.to_reference_state(mod)
+        for name in case["parameter_names"]:
+            ref = np.array(case["state_dict"][name])
+            assert name in sd, name
+            got = sd[name].numpy()
+            assert got.shape == ref.shape, (name, got.shape, ref.shape)
+            assert np.max(np.abs(got - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref))), name
+        for name, v in case["likelihood_state_dict"].items():
+            if name.endswith("raw_noise"):
+                assert np.allclose(lik[name].numpy(), np.array(v), rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(4))
+def test_engine_matches_reference_model_code(cuda_device, idx):
+    from discontinuum_b200 import capi
+
+    case = _cases()[idx]
+    mod = _module_from_reference_state(case)
+    X, y, noise = (np.array(case[k], dtype=np.float64) for k in ("X", "y", "noise"))
+    theta = mod.natural().detach().numpy()
+    eng = capi.Engine(max_n=X.shape[0], max_m=128)
+    eng.set_train(mod.spec.to_c(), X, y, noise)
+    K_ref = np.array(case["K"])
+    Kd = eng.covmat(theta)          # K + noise on the diagonal
+    extra = float(theta[mod.spec.index("likelihood.second_noise")]) if case["model"] == "rating" else 0.0
+    assert np.max(np.abs(Kd - K_ref - np.diag(noise + extra))) <= 1e-12 * np.max(np.abs(K_ref))
+    val, info = eng.nlml(theta)
+    n = X.shape[0]
+    obj = (val - float(mod.log_prior(mod.natural()))) / n
+    assert info == 0 and abs(obj - case["objective"]) <= 1e-9 * abs(case["objective"])
+    eng.factorize(theta)
+    mu, var = eng.predict(np.array(case["Xs"]))
+    assert np.max(np.abs(mu - np.array(case["post_mean"]))) <= 1e-8 * max(1.0, np.max(np.abs(case["post_mean"])))
+    assert np.max(np.abs(var - np.array(case["post_var"]))) <= 1e-8 * max(1e-3, np.max(np.abs(case["post_var"])))
+    eng.close()
+
+
+def _fits():
+    with open(GOLD) as f:
+        return json.load(f)["fits"]
+
+
+def _raw_dict_from_state(fit, sd_key, lik_key):
+    """Reference-named state dicts -> (GPModule, the oracle's raw parameter dict) through the checkpoint key mapping."""
+    X = np.array(fit["X"])
+    if fit["model"] == "loadest":
+        mod = spec.GPModule(models.loadest_spec(X.shape[1]))
+    else:
+        mod = spec.GPModule(models.rating_spec(*models.stage_quantile_bounds(X[:, 1])))
+    checkpoint.load_state(mod, {k: torch.tensor(v, dtype=torch.float64) for k, v in fit[sd_key].items()},
+                          {k: torch.tensor(v, dtype=torch.float64) for k, v in fit[lik_key].items()})
+    rawvec = np.array([float(p.detach()) for p in mod.raw_list()])
+    conv = (lambda v: H.loadest_nat_from_theta(v, X.shape[1])) if fit["model"] == "loadest" else H.rating_nat_from_theta
+    return mod, {k: v.clone() for k, v in conv(rawvec).items()}   # (same layout as the natural vector, raw values inside)
+
+
+@pytest.mark.parametrize("idx", range(3))
+def test_oracle_loop_matches_the_reference_fit_loop(idx):
+    """The reference's own `MarginalGPyTorch.fit` (engines/gpytorch.py:162-458: Adam / AdamW settings, global-norm clipping,
+    ReduceLROnPlateau, the rating model's in-forward clamps) run on the stand-in for 30 iterations, against the oracle's
+    restatement of that loop (`fit_adam`, which the GPU tests hold `MarginalB200.fit` to): the objective at every iteration
+    and every parameter at the end."""
+    fit = _fits()[idx]
+    X, y, noise = (torch.tensor(np.array(fit[k], dtype=np.float64)) for k in ("X", "y", "noise"))
+    mod, raw = _raw_dict_from_state(fit, "initial_state_dict", "initial_likelihood_state_dict")
+    kw = {}
+    if fit["model"] == "rating":
+        b_lo, b_hi = models.stage_quantile_bounds(np.array(fit["X"])[:, 1])
+        kw = dict(b_lo=b_lo, b_hi=b_hi, h_min=float(np.array(fit["X"])[:, 1].min()))
+    raw_end, hist = orc.fit_adam(fit["model"], raw, X, y, noise, iterations=fit["iterations"], optimizer=fit["optimizer"], **kw)
+    ref = np.array(fit["history"])
+    assert len(hist) == len(ref) == fit["iterations"]
+    assert np.max(np.abs(np.array(hist) - ref) / np.abs(ref)) <= 1e-8, np.max(np.abs(np.array(hist) - ref) / np.abs(ref))
+    _, raw_ref = _raw_dict_from_state(fit, "final_state_dict", "final_likelihood_state_dict")
+    for k, v in raw_ref.items():
+        got = raw_end[k].detach().numpy()
+        assert np.max(np.abs(got - v.numpy())) <= 1e-7 * max(1.0, np.max(np.abs(v.numpy()))), k
+
+
+class _ModelSpaceDM:
+    """What MarginalB200.fit (like MarginalGPyTorch.fit) reads from its data manager, already in model space."""
+    def __init__(self, X, y, y_unc=None):
+        self.X, self.y, self.y_unc = X, y, y_unc
+
+    def fit(self, **kw):
+        pass
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(3))
+def test_engine_fit_matches_the_reference_fit_loop(cuda_device, idx):
+    """MarginalB200.fit on the GPU, started from the reference's initial parameters, against the objective trajectory of the
+    reference's own fit loop (tests/golden/ref_models.json["fits"]): <= 1e-6 relative at every one of the 30 iterations."""
+    fit = _fits()[idx]
+    X, y = np.array(fit["X"]), np.array(fit["y"])
+    y_unc = np.array(fit["y_unc"]) if fit["model"] == "rating" else None
+    base = models.LoadestGP if fit["model"] == "loadest" else models.RatingGP
+
+    class _FromReferenceState(base):
+        def build_model(self, *a):
+            mod = super().build_model(*a)
+            checkpoint.load_state(mod, {k: torch.tensor(v, dtype=torch.float64) for k, v in fit["initial_state_dict"].items()},
+                                  {k: torch.tensor(v, dtype=torch.float64) for k, v in fit["initial_likelihood_state_dict"].items()})
+            return mod
+
+    m = _FromReferenceState()
+    m.dm = _ModelSpaceDM(X, y, y_unc)
+    m.fit(None, None, target_unc=(True if y_unc is not None else None), iterations=fit["iterations"], optimizer=fit["optimizer"])
+    ref = np.array(fit["history"])
+    got = np.array(m.history)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-6, np.max(np.abs(got - ref) / np.abs(ref))
