@@ -13,7 +13,7 @@ PARITY STATUS.  Two layers, pinned differently:
     oracle/make_reference_golden.py imports the unmodified model and engine modules from /root/reference/src, executes
     them on a small stand-in for the gpytorch API (oracle/gpytorch_standin) and writes tests/golden/ref_models.json
     (covariance matrices, means, objectives, latent posteriors at two parameter sets per model; 30-iteration objective
-    trajectories of MarginalGPyTorch.fit for loadest Adam / AdamW and rating Adam).  tests/test_reference_golden.py holds
+    trajectories of MarginalGPyTorch.fit for loadest Adam / AdamW and rating Adam, one with the monotonic-rating penalty).  tests/test_reference_golden.py holds
     this oracle (<= 1e-10 / 1e-8), the checkpoint key mapping and, on the GPU, the CUDA engine and MarginalB200.fit to them.
   * the THIRD-PARTY layer underneath (gpytorch / linear_operator: unpinned in /root/reference/pyproject.toml:19-25, not
     installable in this image or on the GPU box; the reference's own tests assert no numbers on this path,

@@ -49,6 +49,9 @@ class FixedNoiseGaussianLikelihood(Module):
         n = function_dist.mean.shape[-1]
         fixed = self.noise_covar.noise
         if fixed.shape[0] != n:
-            raise RuntimeError("stand-in: the fixed noise is only defined at the training inputs")
-        diag = fixed + self.second_noise
+            # new points: the fixed noise is only defined at the training inputs, only the learned noise applies (callers in
+            # the reference that reach this, the monotonic-penalty callback, read .mean only)
+            diag = self.second_noise.expand(n)
+        else:
+            diag = fixed + self.second_noise
         return MultivariateNormal(function_dist.mean, function_dist.covariance_matrix + torch.diag(diag))

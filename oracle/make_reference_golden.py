@@ -107,6 +107,7 @@ def run_reference_fit(cls, X, y, y_unc, iterations, seed, **fit_kw):
     def build_and_record(*a):
         m = build(obj, *a)
         rec["initial_state_dict"], rec["initial_likelihood_state_dict"] = state(m), state(obj.likelihood)
+        torch.manual_seed(seed + 1000)   # what the loop draws from here on (penalty grids) starts from a known generator state
         return m
 
     obj.build_model = build_and_record
@@ -194,6 +195,11 @@ def main():
     y_unc = rng.choice(np.array([2.0 ** -10, 2.0 ** -9, 2.0 ** -8]), n)
     rec = run_reference_fit(ref_rating.RatingGPMarginalGPyTorch, X, y, y_unc, 30, seed=5)
     rec.update({"model": "rating", "optimizer": "adam", "y_unc": y_unc.tolist()})
+    fits.append(rec)
+    # ... and with the monotonic-rating penalty of rating_gp/models/gpytorch.py:126-187 (random grids, finite differences)
+    rec = run_reference_fit(ref_rating.RatingGPMarginalGPyTorch, X, y, y_unc, 12, seed=5, monotonic_penalty_weight=0.5, grid_size=16)
+    rec.update({"model": "rating", "optimizer": "adam", "y_unc": y_unc.tolist(), "penalty_weight": 0.5, "grid_size": 16,
+                "loop_seed": 1005})
     fits.append(rec)
     out = os.path.join(os.path.dirname(HERE), "tests", "golden", "ref_models.json")
     with open(out, "w") as f:

@@ -112,12 +112,10 @@ def test_engine_matches_reference_model_code(cuda_device, idx):
     eng = capi.Engine(max_n=X.shape[0], max_m=128)
     eng.set_train(mod.spec.to_c(), X, y, noise)
     K_ref = np.array(case["K"])
-    Kd = eng.covmat(theta)          # K + noise on the diagonal
-    extra = float(theta[mod.spec.index("likelihood.second_noise")]) if case["model"] == "rating" else 0.0
-    assert np.max(np.abs(Kd - K_ref - np.diag(noise + extra))) <= 1e-12 * np.max(np.abs(K_ref))
+    assert np.max(np.abs(eng.covmat(theta) - K_ref)) <= 1e-12 * np.max(np.abs(K_ref))   # covar_module(x), no noise
     val, info = eng.nlml(theta)
     n = X.shape[0]
-    obj = (val - float(mod.log_prior(mod.natural()))) / n
+    obj = (val - float(mod.log_prior(mod.natural()).detach())) / n
     assert info == 0 and abs(obj - case["objective"]) <= 1e-9 * abs(case["objective"])
     eng.factorize(theta)
     mu, var = eng.predict(np.array(case["Xs"]))
@@ -145,7 +143,7 @@ def _raw_dict_from_state(fit, sd_key, lik_key):
     return mod, {k: v.clone() for k, v in conv(rawvec).items()}   # (same layout as the natural vector, raw values inside)
 
 
-@pytest.mark.parametrize("idx", range(3))
+@pytest.mark.parametrize("idx", range(4))
 def test_oracle_loop_matches_the_reference_fit_loop(idx):
     """The reference's own `MarginalGPyTorch.fit` (engines/gpytorch.py:162-458: Adam / AdamW settings, global-norm clipping,
     ReduceLROnPlateau, the rating model's in-forward clamps) run on the stand-in for 30 iterations, against the oracle's
@@ -158,6 +156,9 @@ def test_oracle_loop_matches_the_reference_fit_loop(idx):
     if fit["model"] == "rating":
         b_lo, b_hi = models.stage_quantile_bounds(np.array(fit["X"])[:, 1])
         kw = dict(b_lo=b_lo, b_hi=b_hi, h_min=float(np.array(fit["X"])[:, 1].min()))
+    if "penalty_weight" in fit:   # the monotonic-rating penalty (rating_gp/models/gpytorch.py:126-187) on the same random grids
+        kw.update(penalty_weight=fit["penalty_weight"], grid_size=fit["grid_size"])
+        torch.manual_seed(fit["loop_seed"])
     raw_end, hist = orc.fit_adam(fit["model"], raw, X, y, noise, iterations=fit["iterations"], optimizer=fit["optimizer"], **kw)
     ref = np.array(fit["history"])
     assert len(hist) == len(ref) == fit["iterations"]
@@ -178,7 +179,7 @@ class _ModelSpaceDM:
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("idx", range(3))
+@pytest.mark.parametrize("idx", range(4))
 def test_engine_fit_matches_the_reference_fit_loop(cuda_device, idx):
     """MarginalB200.fit on the GPU, started from the reference's initial parameters, against the objective trajectory of the
     reference's own fit loop (tests/golden/ref_models.json["fits"]): <= 1e-6 relative at every one of the 30 iterations."""
@@ -192,11 +193,15 @@ def test_engine_fit_matches_the_reference_fit_loop(cuda_device, idx):
             mod = super().build_model(*a)
             checkpoint.load_state(mod, {k: torch.tensor(v, dtype=torch.float64) for k, v in fit["initial_state_dict"].items()},
                                   {k: torch.tensor(v, dtype=torch.float64) for k, v in fit["initial_likelihood_state_dict"].items()})
+            if "loop_seed" in fit:
+                torch.manual_seed(fit["loop_seed"])   # the penalty grids are drawn from torch's generator, as in the reference
             return mod
 
     m = _FromReferenceState()
     m.dm = _ModelSpaceDM(X, y, y_unc)
-    m.fit(None, None, target_unc=(True if y_unc is not None else None), iterations=fit["iterations"], optimizer=fit["optimizer"])
+    extra = dict(monotonic_penalty_weight=fit["penalty_weight"], grid_size=fit["grid_size"]) if "penalty_weight" in fit else {}
+    m.fit(None, None, target_unc=(True if y_unc is not None else None), iterations=fit["iterations"], optimizer=fit["optimizer"],
+          **extra)
     ref = np.array(fit["history"])
     got = np.array(m.history)
     assert got.shape == ref.shape
