@@ -34,7 +34,13 @@ def _stub(name):
     return m
 
 
-for name in ["xarray", "matplotlib", "matplotlib.pyplot", "matplotlib.dates", "matplotlib.ticker", "matplotlib.colors",
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
+import fake_xarray as _fx  # noqa: E402  (the slice of xarray's API the reference's data manager and pipelines touch)
+
+_xr = _stub("xarray")
+_xr.DataArray, _xr.Dataset = _fx.DataArray, _fx.Dataset
+sys.modules["xarray"] = _xr
+for name in ["matplotlib", "matplotlib.pyplot", "matplotlib.dates", "matplotlib.ticker", "matplotlib.colors",
              "matplotlib.cm", "dataretrieval", "dataretrieval.nwis"]:
     if name not in sys.modules:
         sys.modules[name] = _stub(name)
@@ -130,6 +136,47 @@ def run_reference_fit(cls, X, y, y_unc, iterations, seed, **fit_kw):
     return rec
 
 
+def run_end_to_end(cls, covariates, target, target_unc, new_covariates, iterations, seed):
+    """The reference model class as a user drives it: constructor (data manager with the package's pipelines,
+    discontinuum/data_manager.py + pipeline.py, on the xarray stand-in), fit(covariates, target[, target_unc]) and
+    predict(new covariates) in data space.  The engine's explicit float32 casts (engines/gpytorch.py:221-222,235,488-491)
+    are turned into float64 for the run, so that the vectors say what the reference's formulas give, not what float32 leaves."""
+    history = []
+    orig_step = torch.optim.lr_scheduler.ReduceLROnPlateau.step
+
+    def step(self, metrics, *a, **k):
+        history.append(float(metrics))
+        return orig_step(self, metrics, *a, **k)
+
+    torch.optim.lr_scheduler.ReduceLROnPlateau.step = step
+    f32 = torch.float32
+    torch.float32 = torch.float64
+    try:
+        torch.manual_seed(seed)
+        m = cls()
+        init = {}
+        build = m.build_model
+
+        def build_and_record(*a):
+            mod = build(*a)
+            init["sd"], init["lik"] = state(mod), state(m.likelihood)
+            return mod
+
+        m.build_model = build_and_record
+        m.fit(covariates=covariates, target=target, target_unc=target_unc, iterations=iterations)
+        pred, se = m.predict(new_covariates)
+    finally:
+        torch.float32 = f32
+        torch.optim.lr_scheduler.ReduceLROnPlateau.step = orig_step
+    rec = {"X_model": m.dm.X.tolist(), "y_model": m.dm.y.tolist(), "Xnew_model": m.dm.Xnew(new_covariates).tolist(),
+           "initial_state_dict": init["sd"], "initial_likelihood_state_dict": init["lik"], "history": history,
+           "iterations": iterations, "predict_target": np.asarray(pred.values).tolist(), "predict_se": np.asarray(se.values).tolist(),
+           "predict_attrs": dict(pred.attrs), "predict_dims": list(pred.dims)}
+    if target_unc is not None:
+        rec["y_unc_model"] = m.dm.y_unc.tolist()
+    return rec
+
+
 def f32_exact(a, bits=10):
     """round to multiples of 2^-bits: exactly representable in float32, so the loop's float32 cast changes nothing."""
     return np.round(np.asarray(a, dtype=np.float64) * 2 ** bits) / 2 ** bits
@@ -201,11 +248,46 @@ def main():
     rec.update({"model": "rating", "optimizer": "adam", "y_unc": y_unc.tolist(), "penalty_weight": 0.5, "grid_size": 16,
                 "loop_seed": 1005})
     fits.append(rec)
+    # ---------------------------------------------------------------- data space, end to end (data manager + pipelines too)
+    e2e = []
+    n, m = 40, 9
+    days = np.sort(rng.uniform(0, 3650, n))
+    time = np.datetime64("2000-01-01") + (days * 86400e9).astype("timedelta64[ns]")
+    flow = np.exp(1.0 + 0.8 * np.sin(2 * np.pi * days / 365.25) + 0.5 * rng.standard_normal(n))
+    conc = np.exp(0.3 * np.log(flow) + 0.2 * np.cos(2 * np.pi * days / 365.25) + 0.2 * rng.standard_normal(n))
+    new_days = np.linspace(30, 3600, m)
+    new_time = np.datetime64("2000-01-01") + (new_days * 86400e9).astype("timedelta64[ns]")
+    new_flow = np.exp(1.0 + 0.8 * np.sin(2 * np.pi * new_days / 365.25))
+    cov = _fx.Dataset({"flow": ("time", flow)}, coords={"time": time})
+    tgt = _fx.DataArray(conc, coords={"time": time}, dims=("time",), attrs={"units": "mg/L"}, name="conc")
+    new = _fx.Dataset({"flow": ("time", new_flow)}, coords={"time": new_time})
+    rec = run_end_to_end(ref_loadest.LoadestGPMarginalGPyTorch, cov, tgt, None, new, 12, seed=2)
+    rec.update({"model": "loadest", "time_ns": time.astype("datetime64[ns]").astype(np.int64).tolist(), "flow": flow.tolist(),
+                "target": conc.tolist(), "new_time_ns": new_time.astype("datetime64[ns]").astype(np.int64).tolist(),
+                "new_flow": new_flow.tolist()})
+    e2e.append(rec)
+    stage = rng.lognormal(1.0, 0.5, n)
+    q = 3.0 * (stage - 0.5 * stage.min()) ** 1.6 * np.exp(0.03 * rng.standard_normal(n))
+    gse = rng.choice(np.array([1.02, 1.05, 1.08]), n)
+    new_stage = np.exp(np.linspace(np.log(stage.min() * 1.05), np.log(stage.max() * 0.95), m))
+    cov = _fx.Dataset({"stage": ("time", stage)}, coords={"time": time})
+    tgt = _fx.DataArray(q, coords={"time": time}, dims=("time",), attrs={"units": "cfs"}, name="discharge")
+    unc = _fx.DataArray(gse, coords={"time": time}, dims=("time",), name="gse")
+    new = _fx.Dataset({"stage": ("time", new_stage)}, coords={"time": new_time})
+    rec = run_end_to_end(ref_rating.RatingGPMarginalGPyTorch, cov, tgt, unc, new, 12, seed=4)
+    rec.update({"model": "rating", "time_ns": time.astype("datetime64[ns]").astype(np.int64).tolist(), "stage": stage.tolist(),
+                "target": q.tolist(), "target_unc": gse.tolist(),
+                "new_time_ns": new_time.astype("datetime64[ns]").astype(np.int64).tolist(), "new_stage": new_stage.tolist()})
+    e2e.append(rec)
     out = os.path.join(os.path.dirname(HERE), "tests", "golden", "ref_models.json")
     with open(out, "w") as f:
         json.dump({"generator": "oracle/make_reference_golden.py", "reference": "thodson-usgs/discontinuum (src/ as found under "
-                   "/root/reference), model and engine code unmodified, third-party layer = oracle/gpytorch_standin",
-                   "cases": cases, "fits": fits}, f)
+                   "/root/reference), model, engine, data-manager and pipeline code unmodified; third-party layers = "
+                   "oracle/gpytorch_standin and tests/fake_xarray.py",
+                   "cases": cases, "fits": fits, "end_to_end": e2e}, f)
+    for r in e2e:
+        print("end to end", r["model"], "objective", r["history"][0], "->", r["history"][-1], "target[:3]", r["predict_target"][:3],
+              "se[:3]", r["predict_se"][:3])
     for r in fits:
         print("fit", r["model"], r["optimizer"], "objective", r["history"][0], "->", r["history"][-1], "final lr", r["final_lr"])
     print("wrote", out, "cases", [(c["model"], c["case"], c["objective"]) for c in cases])

@@ -206,3 +206,60 @@ def test_engine_fit_matches_the_reference_fit_loop(cuda_device, idx):
     got = np.array(m.history)
     assert got.shape == ref.shape
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-6, np.max(np.abs(got - ref) / np.abs(ref))
+
+
+def _e2e():
+    with open(GOLD) as f:
+        return json.load(f)["end_to_end"]
+
+
+def _raw_inputs(rec):
+    time = np.array(rec["time_ns"], dtype="int64").astype("datetime64[ns]")
+    new_time = np.array(rec["new_time_ns"], dtype="int64").astype("datetime64[ns]")
+    key = "flow" if rec["model"] == "loadest" else "stage"
+    cov = {"time": time, key: np.array(rec[key])}
+    new = {"time": new_time, key: np.array(rec["new_" + key])}
+    unc = np.array(rec["target_unc"]) if "target_unc" in rec else None
+    return cov, np.array(rec["target"]), unc, new
+
+
+@pytest.mark.parametrize("idx", range(2))
+def test_data_manager_matches_the_reference_pipelines(idx):
+    """Model-space design matrix, target, target uncertainty and new-point design matrix of the reference's own DataManager
+    and pipelines (discontinuum/data_manager.py, pipeline.py, the packages' data mixins; run on the xarray stand-in) against
+    this repo's array-level data manager on the same raw inputs."""
+    rec = _e2e()[idx]
+    cov, target, unc, new = _raw_inputs(rec)
+    m = models.LoadestGP() if rec["model"] == "loadest" else models.RatingGP()
+    m.dm.fit(target=target, covariates=cov, target_unc=unc)
+    assert np.max(np.abs(m.dm.X - np.array(rec["X_model"]))) <= 1e-11
+    assert np.max(np.abs(m.dm.y - np.array(rec["y_model"]))) <= 1e-12
+    assert np.max(np.abs(m.dm.Xnew(new) - np.array(rec["Xnew_model"]))) <= 1e-11
+    if unc is not None:
+        assert np.max(np.abs(m.dm.y_unc - np.array(rec["y_unc_model"]))) <= 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(2))
+def test_model_classes_match_the_reference_end_to_end(cuda_device, idx):
+    """The user-level flow -- Model().fit(covariates, target[, target_unc], iterations=12) then predict(new covariates), raw
+    data in, data-space prediction and standard error out -- against the reference's own classes run end to end
+    (constructor, data manager, fit loop, predict; engines/gpytorch.py:162-458,460-499), from the same initial parameters."""
+    rec = _e2e()[idx]
+    cov, target, unc, new = _raw_inputs(rec)
+    base = models.LoadestGP if rec["model"] == "loadest" else models.RatingGP
+
+    class _FromReferenceState(base):
+        def build_model(self, *a):
+            mod = super().build_model(*a)
+            checkpoint.load_state(mod, {k: torch.tensor(v, dtype=torch.float64) for k, v in rec["initial_state_dict"].items()},
+                                  {k: torch.tensor(v, dtype=torch.float64) for k, v in rec["initial_likelihood_state_dict"].items()})
+            return mod
+
+    m = _FromReferenceState()
+    m.fit(cov, target, target_unc=unc, iterations=rec["iterations"])
+    ref = np.array(rec["history"])
+    assert np.max(np.abs(np.array(m.history) - ref) / np.abs(ref)) <= 1e-6
+    pred, se = m.predict(new)
+    assert np.max(np.abs(np.asarray(pred) - np.array(rec["predict_target"])) / np.abs(rec["predict_target"])) <= 1e-6
+    assert np.max(np.abs(np.asarray(se) - np.array(rec["predict_se"])) / np.abs(rec["predict_se"])) <= 1e-6
