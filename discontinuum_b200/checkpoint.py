@@ -151,3 +151,79 @@ def load_state(module: GPModule, model_sd: Dict[str, torch.Tensor], likelihood_s
         for base, idx in groups.items():
             for j, i in enumerate(idx):
                 raws[i].fill_(float(vals[base][j]))
+
+
+# ---------------------------------------------------------------- optimiser state
+# torch optimisers index their state by position in `model.parameters()`.  The reference's order is the registration order
+# of its module tree -- gpytorch.models.ExactGP registers the likelihood first, then the model's own sub-modules in the
+# order its __init__ creates them -- and a vector parameter (an ARD length scale) is ONE tensor there, while this engine keeps
+# one scalar parameter per element, in theta order.  tests/test_reference_golden.py holds the two lists below to the
+# reference's own `named_parameters()` (golden vectors written by its unmodified model code).
+_LOADEST_ORDER = ["mean.constant", "seasonal.outputscale", "seasonal.periodic.lengthscale", "seasonal.periodic.period_length",
+                  "seasonal.matern52.lengthscale", "covariates.outputscale", "covariates.rbf.lengthscale", "residual.outputscale",
+                  "residual.matern32.lengthscale"]
+_RATING_ORDER = ["likelihood.second_noise", "powerlaw.a", "powerlaw.b", "powerlaw.c", "sigmoid.b",
+                 "shiftA.outputscale", "shiftA.stage_matern52.lengthscale", "shiftA.time_matern32.lengthscale",
+                 "shiftB.outputscale", "shiftB.stage_matern52.lengthscale", "shiftB.time_matern32.lengthscale",
+                 "bend.outputscale", "bend.stage_matern52.lengthscale", "bend.time_matern52.lengthscale",
+                 "base.outputscale", "base.stage_matern52.lengthscale",
+                 "periodic.outputscale", "periodic.lengthscale", "periodic.period_length", "periodic.time_matern52.lengthscale"]
+
+
+def reference_parameter_order(module: GPModule) -> List[Tuple[str, str, tuple, List[int]]]:
+    """[(base name, reference key, reference shape, indices of this engine's scalar parameters)] in the order of the
+    reference's `model.parameters()`."""
+    table, _ = _table(module)
+    groups = _groups(module)
+    order = _RATING_ORDER if table is _RATING else _LOADEST_ORDER
+    out = []
+    for base in order:
+        key, shape = table[base]
+        idx = groups[base]
+        out.append((base, key, tuple(len(idx) if s == -1 else s for s in shape), idx))
+    return out
+
+
+def optimizer_state_to_reference(module: GPModule, sd: dict) -> dict:
+    """State dict of a torch Adam / AdamW over this engine's scalar parameters (theta order) -> the layout the reference's
+    optimiser over `model.parameters()` loads: its parameter order, one entry per reference tensor, reference shapes."""
+    state = {}
+    order = reference_parameter_order(module)
+    for j, (_base, _key, shape, idx) in enumerate(order):
+        parts = [sd["state"].get(i) for i in idx]
+        if any(p is None for p in parts):
+            continue
+        entry = {"step": parts[0]["step"].clone() if torch.is_tensor(parts[0]["step"]) else parts[0]["step"]}
+        for name in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):
+            if name in parts[0]:
+                entry[name] = torch.cat([p[name].reshape(1) for p in parts]).reshape(shape).clone()
+        state[j] = entry
+    groups = [dict(g, params=list(range(len(order)))) for g in sd["param_groups"]]
+    return {"state": state, "param_groups": groups}
+
+
+def optimizer_state_from_reference(module: GPModule, sd: dict) -> dict:
+    """The inverse: a reference-layout optimiser state dict (written by MarginalGPyTorch.save or by MarginalB200.save) ->
+    one entry per scalar parameter of this engine, theta order."""
+    order = reference_parameter_order(module)
+    if len(sd["param_groups"]) != 1 or len(sd["param_groups"][0]["params"]) != len(order):
+        raise ValueError(f"optimiser state holds {[len(g['params']) for g in sd['param_groups']]} parameters, the reference's "
+                         f"module tree of this model has {len(order)}")
+    ref_ids = sd["param_groups"][0]["params"]
+    nparam = sum(len(idx) for _, _, _, idx in order)
+    state = {}
+    for j, (_base, key, _shape, idx) in enumerate(order):
+        entry = sd["state"].get(ref_ids[j])
+        if entry is None:
+            continue
+        for k, i in enumerate(idx):
+            e = {"step": entry["step"].clone().to(torch.float32) if torch.is_tensor(entry["step"]) else torch.tensor(float(entry["step"]))}
+            for name in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):
+                if name in entry:
+                    flat = entry[name].reshape(-1)
+                    if flat.numel() != len(idx):
+                        raise ValueError(f"optimiser state of '{key}' has {flat.numel()} elements, the model expects {len(idx)}")
+                    e[name] = flat[k].reshape(1).to(torch.float64).clone()
+            state[i] = e
+    groups = [dict(g, params=list(range(nparam))) for g in sd["param_groups"]]
+    return {"state": state, "param_groups": groups}

@@ -30,6 +30,14 @@ JITTERS = (0.0, 1e-8, 1e-7, 1e-6)  # psd_safe_cholesky retry ladder in float64 (
 _FUSED = {"fused": True}
 
 
+def _reference_model_config_shim():
+    """A dataclass that unpickles as `discontinuum.engines.base.ModelConfig` (same fields), for weights_only loading of
+    checkpoints written by the reference."""
+    shim = dataclasses.make_dataclass("ModelConfig", [("transform", str, dataclasses.field(default="log"))])
+    shim.__module__, shim.__qualname__ = "discontinuum.engines.base", "ModelConfig"
+    return shim
+
+
 def _push_raw(params, raw_np) -> None:
     """numpy raw parameter vector -> the module's one-element tensors."""
     with torch.no_grad():
@@ -219,7 +227,10 @@ class MarginalB200:
             "model_class": f"{self.__class__.__module__}.{self.__class__.__name__}",
             "model_state_dict": sd,
             "likelihood_state_dict": lik,
-            "optimizer_state_dict": optimizer_obj.state_dict() if optimizer_obj is not None else None,
+            # the reference's layout (its parameter order, vector parameters as one tensor), so that either engine resumes it
+            "optimizer_state_dict": (checkpoint.optimizer_state_to_reference(self.model, optimizer_obj.state_dict())
+                                     if optimizer_obj is not None else None),
+            "optimizer_layout": "reference",
             "optimizer_name": _get_optimizer_name(optimizer_obj) if optimizer_obj is not None else None,
             "optimizer_lr": optimizer_obj.param_groups[0].get("lr") if optimizer_obj is not None else None,
             "scheduler_state_dict": scheduler.state_dict() if scheduler is not None else None,
@@ -232,8 +243,13 @@ class MarginalB200:
 
     @classmethod
     def load(cls, f, covariates, target, target_unc=None):
-        ckpt = torch.load(f, map_location="cpu", weights_only=True)  # tensors, numbers, strings and dicts only: no pickled code
+        # tensors, numbers, strings and dicts only, no pickled code -- plus the one object the reference's save() pickles, its
+        # ModelConfig dataclass (discontinuum/engines/base.py:22-26), resolved to a field-for-field stand-in by name
+        with torch.serialization.safe_globals([_reference_model_config_shim()]):
+            ckpt = torch.load(f, map_location="cpu", weights_only=True)
         cfg = ckpt.get("model_config")
+        if dataclasses.is_dataclass(cfg) and not isinstance(cfg, type):
+            cfg = dataclasses.asdict(cfg)
         model = cls(ModelConfig(**cfg)) if isinstance(cfg, dict) and cfg else cls()
         model.dm.fit(target=target, covariates=covariates, target_unc=target_unc)
         model.X, model.y = model.dm.X, model.dm.y
@@ -247,6 +263,10 @@ class MarginalB200:
         model._resume_info = {k: ckpt.get(k) for k in ("optimizer_state_dict", "optimizer_name", "optimizer_lr",
                                                        "scheduler_state_dict", "scheduler_name")}
         model._resume_info["current_iteration"] = ckpt.get("current_iteration", 0)
+        # checkpoints of the reference (no marker, model_class in its packages) and of this engine since round 2 hold the
+        # optimiser state in the reference's layout; round-1 checkpoints of this engine in theta order
+        native_class = str(ckpt.get("model_class", "")).startswith("discontinuum_b200")
+        model._resume_info["optimizer_layout"] = ckpt.get("optimizer_layout", "native" if native_class else "reference")
         model._current_iteration = ckpt.get("current_iteration", 0)
         model._bind_engine()
         model.is_fitted = True
@@ -292,7 +312,10 @@ class MarginalB200:
             raise ValueError(f"Unsupported optimizer: {opt_choice!r}. Supported optimizers are 'adam' and 'adamw'.")
         if can_restore and resume_info.get("optimizer_state_dict") is not None:
             try:
-                optimizer_obj.load_state_dict(resume_info["optimizer_state_dict"])
+                osd = resume_info["optimizer_state_dict"]
+                if resume_info.get("optimizer_layout") == "reference":
+                    osd = checkpoint.optimizer_state_from_reference(self.model, osd)
+                optimizer_obj.load_state_dict(osd)
             except Exception:  # noqa: BLE001, S110
                 pass
         scheduler_obj = None

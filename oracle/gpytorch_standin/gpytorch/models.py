@@ -17,6 +17,14 @@ class ExactGP(Module):
     def forward(self, x):
         raise NotImplementedError
 
+    def set_train_data(self, inputs=None, targets=None, strict=True):
+        if inputs is not None:
+            if torch.is_tensor(inputs):
+                inputs = (inputs,)
+            self.train_inputs = tuple(t.unsqueeze(-1) if t.ndim == 1 else t for t in inputs)
+        if targets is not None:
+            self.train_targets = targets
+
     def __call__(self, *args, **kwargs):
         x = args[0]
         if x.ndim == 1:

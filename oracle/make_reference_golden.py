@@ -279,9 +279,43 @@ def main():
                 "target": q.tolist(), "target_unc": gse.tolist(),
                 "new_time_ns": new_time.astype("datetime64[ns]").astype(np.int64).tolist(), "new_stage": new_stage.tolist()})
     e2e.append(rec)
+    # ---------------------------------------------------------------- a checkpoint written by the reference's own save()
+    ckpt_path = os.path.join(os.path.dirname(HERE), "tests", "golden", "ref_checkpoint_loadest.pt")
+    cov = _fx.Dataset({"flow": ("time", flow)}, coords={"time": time})
+    tgt = _fx.DataArray(conc, coords={"time": time}, dims=("time",), attrs={"units": "mg/L"}, name="conc")
+    history = []
+    orig_step = torch.optim.lr_scheduler.ReduceLROnPlateau.step
+
+    def step(self, metrics, *a, **k):
+        history.append(float(metrics))
+        return orig_step(self, metrics, *a, **k)
+
+    torch.optim.lr_scheduler.ReduceLROnPlateau.step = step
+    f32 = torch.float32
+    torch.float32 = torch.float64
+    try:
+        torch.manual_seed(6)
+        m1 = ref_loadest.LoadestGPMarginalGPyTorch()
+        m1.fit(covariates=cov, target=tgt, iterations=8)
+        m1.save(ckpt_path)                                        # engines/gpytorch.py:107-160
+        first = list(history)
+        del history[:]
+        # (the reference's load() calls torch.load with the defaults, which on torch >= 2.6 refuse the pickled ModelConfig
+        # dataclass the reference's save() puts into the file: allow-list it, as the error message asks)
+        import discontinuum.engines.base as ref_base
+        torch.serialization.add_safe_globals([ref_base.ModelConfig])
+        m2 = ref_loadest.LoadestGPMarginalGPyTorch.load(ckpt_path, cov, tgt)   # engines/gpytorch.py:47-105
+        m2.fit(covariates=cov, target=tgt, iterations=18, resume=True)
+    finally:
+        torch.float32 = f32
+        torch.optim.lr_scheduler.ReduceLROnPlateau.step = orig_step
+    ckpt_rec = {"file": "ref_checkpoint_loadest.pt", "first_history": first, "resumed_history": list(history),
+                "time_ns": time.astype("datetime64[ns]").astype(np.int64).tolist(), "flow": flow.tolist(), "target": conc.tolist(),
+                "total_iterations": 18}
+    print("checkpoint: first", len(first), "iterations, resumed", len(history), "more:", history[0], "->", history[-1])
     out = os.path.join(os.path.dirname(HERE), "tests", "golden", "ref_models.json")
     with open(out, "w") as f:
-        json.dump({"generator": "oracle/make_reference_golden.py", "reference": "thodson-usgs/discontinuum (src/ as found under "
+        json.dump({"generator": "oracle/make_reference_golden.py", "checkpoint": ckpt_rec, "reference": "thodson-usgs/discontinuum (src/ as found under "
                    "/root/reference), model, engine, data-manager and pipeline code unmodified; third-party layers = "
                    "oracle/gpytorch_standin and tests/fake_xarray.py",
                    "cases": cases, "fits": fits, "end_to_end": e2e}, f)

@@ -263,3 +263,63 @@ def test_model_classes_match_the_reference_end_to_end(cuda_device, idx):
     pred, se = m.predict(new)
     assert np.max(np.abs(np.asarray(pred) - np.array(rec["predict_target"])) / np.abs(rec["predict_target"])) <= 1e-6
     assert np.max(np.abs(np.asarray(se) - np.array(rec["predict_se"])) / np.abs(rec["predict_se"])) <= 1e-6
+
+
+def test_reference_parameter_order_and_optimizer_state_layout():
+    """The order in which the reference's optimiser sees the parameters (`model.parameters()` of its own module tree) and the
+    conversion of an Adam state between that layout and this engine's scalar parameters, both directions."""
+    for case in _cases():
+        mod = _module_from_reference_state(case)
+        order = checkpoint.reference_parameter_order(mod)
+        assert [key for _, key, _, _ in order] == case["parameter_names"]
+        for _, key, shape, idx in order:
+            assert tuple(np.array(case["state_dict"][key]).shape) == shape and int(np.prod(shape, dtype=int)) == len(idx)
+        params = mod.raw_list()
+        opt = torch.optim.Adam(params, lr=0.05)
+        for k, p in enumerate(params):
+            p.grad = torch.tensor([0.1 * (k + 1)], dtype=torch.float64)
+        opt.step()
+        native = opt.state_dict()
+        ref = checkpoint.optimizer_state_to_reference(mod, native)
+        assert ref["param_groups"][0]["params"] == list(range(len(order)))
+        for j, (_, key, shape, idx) in enumerate(order):
+            assert tuple(ref["state"][j]["exp_avg"].shape) == shape
+            assert [float(v) for v in ref["state"][j]["exp_avg"].reshape(-1)] == [float(native["state"][i]["exp_avg"]) for i in idx]
+        back = checkpoint.optimizer_state_from_reference(mod, ref)
+        for i in range(len(params)):
+            for name in ("exp_avg", "exp_avg_sq"):
+                assert float(back["state"][i][name]) == float(native["state"][i][name])
+        opt2 = torch.optim.Adam(params, lr=0.05)
+        opt2.load_state_dict(back)   # loads into an optimiser over the engine's parameters
+
+
+def test_reference_written_checkpoint_loads_without_pickled_code():
+    """tests/golden/ref_checkpoint_loadest.pt was written by the reference's own `save()` (engines/gpytorch.py:107-160, run on
+    the stand-in): weights_only loading works, the state dicts map onto this engine's parameters, the optimiser state converts."""
+    from discontinuum_b200 import engine
+
+    path = os.path.join(os.path.dirname(GOLD), "ref_checkpoint_loadest.pt")
+    with torch.serialization.safe_globals([engine._reference_model_config_shim()]):
+        ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    assert ckpt["model_class"] == "loadest_gp.models.gpytorch.LoadestGPMarginalGPyTorch" and ckpt["optimizer_name"] == "adam"
+    mod = spec.GPModule(models.loadest_spec(2))
+    checkpoint.load_state(mod, ckpt["model_state_dict"], ckpt["likelihood_state_dict"])
+    osd = checkpoint.optimizer_state_from_reference(mod, ckpt["optimizer_state_dict"])
+    assert len(osd["state"]) == 10 and all(float(v["step"]) == 8.0 for v in osd["state"].values())
+    torch.optim.Adam(mod.raw_list(), lr=0.05).load_state_dict(osd)
+
+
+@pytest.mark.gpu
+def test_resume_from_a_reference_written_checkpoint(cuda_device):
+    """LoadestGP.load(<checkpoint written by the reference's save()>) + fit(resume=True): the same objective trajectory as the
+    reference's own load() + fit(resume=True) -- parameters, Adam moments, step count and scheduler state all carried over."""
+    with open(GOLD) as f:
+        rec = json.load(f)["checkpoint"]
+    time = np.array(rec["time_ns"], dtype="int64").astype("datetime64[ns]")
+    cov, target = {"time": time, "flow": np.array(rec["flow"])}, np.array(rec["target"])
+    m = models.LoadestGP.load(os.path.join(os.path.dirname(GOLD), rec["file"]), cov, target)
+    m.fit(cov, target, iterations=rec["total_iterations"], resume=True)
+    ref = np.array(rec["resumed_history"])
+    got = np.array(m.history)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-6, np.max(np.abs(got - ref) / np.abs(ref))
