@@ -136,7 +136,7 @@ def run_reference_fit(cls, X, y, y_unc, iterations, seed, **fit_kw):
     return rec
 
 
-def run_end_to_end(cls, covariates, target, target_unc, new_covariates, iterations, seed):
+def run_end_to_end(cls, covariates, target, target_unc, new_covariates, iterations, seed, grid_covariate):
     """The reference model class as a user drives it: constructor (data manager with the package's pipelines,
     discontinuum/data_manager.py + pipeline.py, on the xarray stand-in), fit(covariates, target[, target_unc]) and
     predict(new covariates) in data space.  The engine's explicit float32 casts (engines/gpytorch.py:221-222,235,488-491)
@@ -165,13 +165,17 @@ def run_end_to_end(cls, covariates, target, target_unc, new_covariates, iteratio
         m.build_model = build_and_record
         m.fit(covariates=covariates, target=target, target_unc=target_unc, iterations=iterations)
         pred, se = m.predict(new_covariates)
+        grid = m.predict_grid(grid_covariate)          # engines/gpytorch.py:500-549
     finally:
         torch.float32 = f32
         torch.optim.lr_scheduler.ReduceLROnPlateau.step = orig_step
     rec = {"X_model": m.dm.X.tolist(), "y_model": m.dm.y.tolist(), "Xnew_model": m.dm.Xnew(new_covariates).tolist(),
            "initial_state_dict": init["sd"], "initial_likelihood_state_dict": init["lik"], "history": history,
            "iterations": iterations, "predict_target": np.asarray(pred.values).tolist(), "predict_se": np.asarray(se.values).tolist(),
-           "predict_attrs": dict(pred.attrs), "predict_dims": list(pred.dims)}
+           "predict_attrs": dict(pred.attrs), "predict_dims": list(pred.dims),
+           "grid_covariate": grid_covariate, "grid_values": np.asarray(grid.values).tolist(), "grid_dims": list(grid.dims),
+           "grid_index_ns": np.asarray(grid.coords[grid.dims[0]].values).astype("datetime64[ns]").astype(np.int64).tolist(),
+           "grid_covariate_values": np.asarray(grid.coords[grid.dims[1]].values, dtype=np.float64).tolist()}
     if target_unc is not None:
         rec["y_unc_model"] = m.dm.y_unc.tolist()
     return rec
@@ -261,7 +265,7 @@ def main():
     cov = _fx.Dataset({"flow": ("time", flow)}, coords={"time": time})
     tgt = _fx.DataArray(conc, coords={"time": time}, dims=("time",), attrs={"units": "mg/L"}, name="conc")
     new = _fx.Dataset({"flow": ("time", new_flow)}, coords={"time": new_time})
-    rec = run_end_to_end(ref_loadest.LoadestGPMarginalGPyTorch, cov, tgt, None, new, 12, seed=2)
+    rec = run_end_to_end(ref_loadest.LoadestGPMarginalGPyTorch, cov, tgt, None, new, 12, seed=2, grid_covariate="flow")
     rec.update({"model": "loadest", "time_ns": time.astype("datetime64[ns]").astype(np.int64).tolist(), "flow": flow.tolist(),
                 "target": conc.tolist(), "new_time_ns": new_time.astype("datetime64[ns]").astype(np.int64).tolist(),
                 "new_flow": new_flow.tolist()})
@@ -274,7 +278,7 @@ def main():
     tgt = _fx.DataArray(q, coords={"time": time}, dims=("time",), attrs={"units": "cfs"}, name="discharge")
     unc = _fx.DataArray(gse, coords={"time": time}, dims=("time",), name="gse")
     new = _fx.Dataset({"stage": ("time", new_stage)}, coords={"time": new_time})
-    rec = run_end_to_end(ref_rating.RatingGPMarginalGPyTorch, cov, tgt, unc, new, 12, seed=4)
+    rec = run_end_to_end(ref_rating.RatingGPMarginalGPyTorch, cov, tgt, unc, new, 12, seed=4, grid_covariate="stage")
     rec.update({"model": "rating", "time_ns": time.astype("datetime64[ns]").astype(np.int64).tolist(), "stage": stage.tolist(),
                 "target": q.tolist(), "target_unc": gse.tolist(),
                 "new_time_ns": new_time.astype("datetime64[ns]").astype(np.int64).tolist(), "new_stage": new_stage.tolist()})

@@ -24,6 +24,10 @@ class DataArray:
         return self.values.ndim
 
     @property
+    def data(self):
+        return self.values
+
+    @property
     def shape(self):
         return self.values.shape
 
@@ -48,3 +52,9 @@ class Dataset:
 
     def __getitem__(self, key):
         return self.data_vars[key] if key in self.data_vars else self.coords[key]
+
+    def __iter__(self):          # a Dataset iterates over the names of its data variables
+        return iter(self.data_vars)
+
+    def __len__(self):
+        return len(self.data_vars)

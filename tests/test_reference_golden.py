@@ -263,6 +263,15 @@ def test_model_classes_match_the_reference_end_to_end(cuda_device, idx):
     pred, se = m.predict(new)
     assert np.max(np.abs(np.asarray(pred) - np.array(rec["predict_target"])) / np.abs(rec["predict_target"])) <= 1e-6
     assert np.max(np.abs(np.asarray(se) - np.array(rec["predict_se"])) / np.abs(rec["predict_se"])) <= 1e-6
+    # predict_grid (engines/gpytorch.py:500-549): 18 covariate columns x round(12 * time range) rows, data-space coordinates
+    grid, index, covs = m.predict_grid(rec["grid_covariate"])
+    ref_grid = np.array(rec["grid_values"])
+    assert grid.shape == ref_grid.shape
+    assert np.max(np.abs(grid - ref_grid) / np.abs(ref_grid)) <= 1e-6
+    assert np.max(np.abs(np.asarray(covs, dtype=np.float64) - np.array(rec["grid_covariate_values"]))) <= 1e-9 * np.max(rec["grid_covariate_values"])
+    ref_index = np.array(rec["grid_index_ns"], dtype="int64")
+    got_index = np.asarray(index).astype("datetime64[ns]").astype("int64")
+    assert np.max(np.abs(got_index - ref_index)) <= 2_000_000_000   # the reference rounds the grid times to the second
 
 
 def test_reference_parameter_order_and_optimizer_state_layout():
