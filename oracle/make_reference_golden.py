@@ -55,6 +55,7 @@ import gpytorch  # noqa: E402  (the stand-in)
 
 assert "gpytorch_standin" in gpytorch.__file__
 import loadest_gp.models.gpytorch as ref_loadest  # noqa: E402
+import loadest_gp.models.pymc as ref_loadest_pymc  # noqa: E402  (on the pymc stand-in)
 import rating_gp.models.gpytorch as ref_rating  # noqa: E402
 
 
@@ -317,9 +318,26 @@ def main():
                 "time_ns": time.astype("datetime64[ns]").astype(np.int64).tolist(), "flow": flow.tolist(), "target": conc.tolist(),
                 "total_iterations": 18}
     print("checkpoint: first", len(first), "iterations, resumed", len(history), "more:", history[0], "->", history[-1])
+    # ---------------------------------------------------------------- the PyMC model (loadest_gp/models/pymc.py:30-88)
+    pymc_cases = []
+    for nd in (2, 3):
+        n = 13
+        Xp = np.concatenate([np.sort(rng.uniform(-1.5, 1.5, n))[:, None], rng.standard_normal((n, nd - 1))], axis=1)
+        yp = rng.standard_normal(n)
+        owner = types.SimpleNamespace()
+        pm_model = ref_loadest_pymc.LoadestGPMarginalPyMC.build_model(owner, Xp, yp)
+        table = [{"name": k, "prior": v.kind, "params": v.params, "size": 1 if v.shape is None else int(np.prod(v.shape)),
+                  "initval": None if v.initval is None else np.atleast_1d(np.asarray(v.initval, dtype=np.float64)).tolist()}
+                 for k, v in pm_model.vars.items()]
+        for tag in ("a", "b"):
+            vals = {t["name"]: (0.3 + 1.2 * rng.uniform(size=t["size"])).tolist() for t in table}
+            nl = float(pm_model.neg_logp(vals))
+            pymc_cases.append({"ndim": nd, "case": tag, "X": Xp.tolist(), "y": yp.tolist(), "variables": table, "values": vals,
+                               "neg_logp": nl, "K": tolist(owner.gp.cov_func(torch.tensor(Xp)))})
+    print("pymc", [(c["ndim"], c["case"], c["neg_logp"]) for c in pymc_cases])
     out = os.path.join(os.path.dirname(HERE), "tests", "golden", "ref_models.json")
     with open(out, "w") as f:
-        json.dump({"generator": "oracle/make_reference_golden.py", "checkpoint": ckpt_rec, "reference": "thodson-usgs/discontinuum (src/ as found under "
+        json.dump({"generator": "oracle/make_reference_golden.py", "checkpoint": ckpt_rec, "pymc": pymc_cases, "reference": "thodson-usgs/discontinuum (src/ as found under "
                    "/root/reference), model, engine, data-manager and pipeline code unmodified; third-party layers = "
                    "oracle/gpytorch_standin and tests/fake_xarray.py",
                    "cases": cases, "fits": fits, "end_to_end": e2e}, f)

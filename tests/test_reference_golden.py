@@ -332,3 +332,52 @@ def test_resume_from_a_reference_written_checkpoint(cuda_device):
     got = np.array(m.history)
     assert got.shape == ref.shape
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-6, np.max(np.abs(got - ref) / np.abs(ref))
+
+
+def _pymc_cases():
+    with open(GOLD) as f:
+        return json.load(f)["pymc"]
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_pymc_variant_matches_the_reference_pymc_model(idx):
+    """The reference's PyMC model definition (loadest_gp/models/pymc.py:30-88: variables, priors, shapes, initial values,
+    eta**2-scaled covariance terms on their dimensions, WhiteNoise(0.1)), run on the pymc stand-in, against the variable table
+    of discontinuum_b200/pymc_variant.py and the oracle's restatement of the covariance and of the MAP objective."""
+    from discontinuum_b200 import pymc_variant as pv
+
+    c = _pymc_cases()[idx]
+    vars_ = pv.loadest_pymc_vars(c["ndim"])
+    assert [v.name for v in vars_] == [t["name"] for t in c["variables"]]
+    for v, t in zip(vars_, c["variables"]):
+        assert v.prior[0] == t["prior"] and v.size == t["size"], t["name"]
+        want = {"halfnormal": [t["params"].get("sigma")], "normal": [t["params"].get("mu"), t["params"].get("sigma")],
+                "gamma": [t["params"].get("alpha"), t["params"].get("beta")], "exponential": [t["params"].get("scale")]}[t["prior"]]
+        assert [float(x) for x in v.prior[1:]] == [float(x) for x in want], t["name"]
+        if t["initval"] is not None:     # explicit initval in the reference (eta_per = 1, ls_covariates = 0.5)
+            assert np.allclose(v.init, np.broadcast_to(np.array(t["initval"]), v.init.shape)), t["name"]
+    X, y = torch.tensor(np.array(c["X"])), torch.tensor(np.array(c["y"]))
+    v = {k: torch.tensor(np.array(val, dtype=np.float64)) for k, val in c["values"].items()}
+    K_ref = np.array(c["K"])
+    assert np.max(np.abs(orc.pymc_loadest_cov(X, X, v).numpy() - K_ref)) <= 1e-12 * np.max(np.abs(K_ref))
+    assert abs(float(orc.pymc_loadest_neg_logp(v, X, y)) - c["neg_logp"]) <= 1e-11 * abs(c["neg_logp"])
+    # the engine's covariance spec at the reparameterised theta describes the same matrix (checked on the GPU elsewhere);
+    # here: the log density of every variable of the table equals the stand-in's prior term
+    Ky = torch.tensor(K_ref) + (0.1 ** 2 + 1e-6) * torch.eye(len(c["y"]), dtype=torch.float64)
+    prior_sum = float(sum(x.logp(v[x.name]) for x in vars_))
+    assert abs(-prior_sum + float(orc.nlml_from_K(Ky, y)[0]) - c["neg_logp"]) <= 1e-10 * abs(c["neg_logp"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(4))
+def test_engine_covariance_matches_the_reference_pymc_model(cuda_device, idx):
+    from discontinuum_b200 import capi, pymc_variant as pv
+
+    c = _pymc_cases()[idx]
+    X, y = np.array(c["X"]), np.array(c["y"])
+    v = {k: torch.tensor(np.array(val, dtype=np.float64)) for k, val in c["values"].items()}
+    eng = capi.Engine(max_n=X.shape[0], max_m=128)
+    eng.set_train(pv.loadest_pymc_spec(c["ndim"]).to_c(), X, y, np.full(X.shape[0], 0.1 ** 2 + 1e-6))
+    K = eng.covmat(pv.pymc_to_natural(v).numpy())
+    assert np.max(np.abs(K - np.array(c["K"]))) <= 1e-12 * np.max(np.abs(c["K"]))
+    eng.close()
