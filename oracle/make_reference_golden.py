@@ -207,6 +207,20 @@ def main():
         rec.update({"model": "loadest", "case": tag, "X": X.tolist(), "y": y.tolist(), "Xs": Xs.tolist(),
                     "noise": tolist(owner.likelihood.noise)})
         cases.append(rec)
+    # ... and with three covariate columns (ARD length scales are vectors: (1, 2) and (1, 3) tensors in the state dict)
+    n = 12
+    t = np.sort(rng.uniform(-1.5, 1.5, n))
+    X = np.concatenate([t[:, None], rng.standard_normal((n, 2))], axis=1)
+    y = 0.4 * np.sin(2 * np.pi * t) + 0.3 * X[:, 1] - 0.2 * X[:, 2] + 0.1 * rng.standard_normal(n)
+    Xs = np.concatenate([np.linspace(-1.4, 1.6, m)[:, None], rng.standard_normal((m, 2))], axis=1)
+    x_t, y_t, xs_t = torch.tensor(X), torch.tensor(y), torch.tensor(Xs)
+    owner = types.SimpleNamespace()
+    model = ref_loadest.LoadestGPMarginalGPyTorch.build_model(owner, x_t, y_t)
+    perturb(model, 13)
+    rec = evaluate(owner, model, x_t, y_t, xs_t)
+    rec.update({"model": "loadest", "case": "moved, 3 input columns", "X": X.tolist(), "y": y.tolist(), "Xs": Xs.tolist(),
+                "noise": tolist(owner.likelihood.noise)})
+    cases.append(rec)
     # ---------------------------------------------------------------- rating-gp
     n = 16
     t = np.sort(rng.uniform(-1.5, 1.5, n))

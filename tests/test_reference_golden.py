@@ -49,7 +49,7 @@ def _oracle_pieces(case, mod):
     return X, y, noise, theta, nat, orc.rating_cov, orc.rating_mean, nat["noise"], orc.rating_log_prior(nat)
 
 
-@pytest.mark.parametrize("idx", range(4))
+@pytest.mark.parametrize("idx", range(5))
 def test_oracle_matches_reference_model_code(idx):
     case = _cases()[idx]
     mod = _module_from_reference_state(case)
@@ -101,7 +101,7 @@ def test_reference_state_round_trips_through_the_checkpoint_mapping():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("idx", range(4))
+@pytest.mark.parametrize("idx", range(5))
 def test_engine_matches_reference_model_code(cuda_device, idx):
     from discontinuum_b200 import capi
 
