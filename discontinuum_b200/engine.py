@@ -479,7 +479,9 @@ class MarginalB200:
         """(target, se) in original units; diag / pred_noise are accepted and ignored like the reference (gpytorch.py:460-501)."""
         mu, var = self._model_space_predict(self.dm.Xnew(covariates))
         target = _assign_coords(self.dm.y_t(mu), covariates)
-        se = _assign_coords(self.dm.se_t(var), covariates)
+        # (this repo's data manager wraps the result itself; the reference's has no se_t: engines/gpytorch.py:497)
+        se_t = getattr(self.dm, "se_t", None)
+        se = _assign_coords(se_t(var) if se_t is not None else self.dm.error_pipeline.inverse_transform(var), covariates)
         return target, se
 
     @is_fitted

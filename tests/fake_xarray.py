@@ -10,6 +10,8 @@ import numpy as np
 class DataArray:
     def __init__(self, data, coords=None, dims=None, attrs=None, name=None):
         self.values = np.asarray(data)
+        if self.values.dtype == object and self.values.size and hasattr(self.values.flat[0], "to_datetime64"):
+            self.values = np.array([v.to_datetime64() for v in self.values.flat], dtype="datetime64[ns]").reshape(self.values.shape)
         self.attrs = dict(attrs or {})
         self.name = name
         if dims is None:
@@ -34,6 +36,48 @@ class DataArray:
     def __array__(self, dtype=None, copy=None):
         return self.values if dtype is None else self.values.astype(dtype)
 
+    # -- what the reference's plot mixins touch beyond the adapter: element-wise arithmetic, da["coord"], da.plot.<kind>(...)
+    def _binary(self, other, op):
+        o = other.values if isinstance(other, DataArray) else other
+        return DataArray(op(self.values, o), coords=dict(self.coords), dims=self.dims, attrs=self.attrs, name=self.name)
+
+    def __add__(self, o): return self._binary(o, np.add)
+    def __sub__(self, o): return self._binary(o, np.subtract)
+    def __mul__(self, o): return self._binary(o, np.multiply)
+    def __truediv__(self, o): return self._binary(o, np.divide)
+    def __pow__(self, o): return self._binary(o, np.power)
+    def __radd__(self, o): return self._binary(o, lambda a, b: b + a)
+    def __rmul__(self, o): return self._binary(o, lambda a, b: b * a)
+    def __rsub__(self, o): return self._binary(o, lambda a, b: b - a)
+    def __rtruediv__(self, o): return self._binary(o, lambda a, b: b / a)
+
+    def __getitem__(self, key):
+        return self.coords[key]
+
+    def __getattr__(self, name):  # da.time: attribute-style access to a coordinate
+        coords = self.__dict__.get("coords", {})
+        if name in coords:
+            return coords[name]
+        raise AttributeError(name)
+
+    def min(self):
+        import types
+        return types.SimpleNamespace(values=self.values.min())   # (.values of a reduced array: a numpy scalar)
+
+    def max(self):
+        import types
+        return types.SimpleNamespace(values=self.values.max())
+
+    def __len__(self):
+        return len(self.values)
+
+    @property
+    def plot(self):
+        from unittest.mock import MagicMock
+        if self.__dict__.get("_plot") is None:
+            self.__dict__["_plot"] = MagicMock(name="DataArray.plot")
+        return self.__dict__["_plot"]
+
     def assign_coords(self, coords):
         out = DataArray(self.values, coords=dict(self.coords), dims=self.dims, attrs=self.attrs, name=self.name)
         out.coords.update({k: (v if isinstance(v, DataArray) else DataArray(v, dims=(k,))) for k, v in dict(coords).items()})
@@ -52,6 +96,20 @@ class Dataset:
 
     def __getitem__(self, key):
         return self.data_vars[key] if key in self.data_vars else self.coords[key]
+
+    def __getattr__(self, name):  # ds.time, ds.stage: attribute-style access to coordinates and variables
+        d = self.__dict__
+        for table in ("data_vars", "coords"):
+            if table in d and name in d[table]:
+                return d[table][name]
+        raise AttributeError(name)
+
+    @property
+    def plot(self):
+        from unittest.mock import MagicMock
+        if self.__dict__.get("_plot") is None:
+            self.__dict__["_plot"] = MagicMock(name="Dataset.plot")
+        return self.__dict__["_plot"]
 
     def __iter__(self):          # a Dataset iterates over the names of its data variables
         return iter(self.data_vars)
