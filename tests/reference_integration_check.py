@@ -92,6 +92,12 @@ class CpuEngine:
         mu, _, var = orc.predict(cov, mean, nat, self.X, self.y, self.noise, torch.tensor(Xs), extra_noise=extra, min_variance=0.0)
         return mu.numpy(), var.numpy()
 
+    def sample(self, Xs, Z, jitter=0.0):
+        nat, cov, mean, extra = self._pieces(self.theta)
+        sim, _ = orc.sample(cov, mean, nat, self.X, self.y, self.noise, torch.tensor(Xs), torch.tensor(Z), extra_noise=extra,
+                            jitter=max(float(jitter), 1e-8))
+        return sim.numpy(), 0
+
     def close(self):
         pass
 
@@ -151,11 +157,14 @@ def main():
     assert target.values.shape == (n,) and np.all(target.values > 0) and np.all(se.values >= 1.0) and "time" in target.coords
     grid = m.predict_grid("flow")
     assert isinstance(grid, fx.DataArray) and grid.values.shape[1] == 18 and list(grid.dims) == ["time", "flow"]
+    draws = m.sample(cov, n=6, seed=0)                                 # engines/gpytorch.py:551-593: [draw, time] in data space
+    assert isinstance(draws, fx.DataArray) and draws.values.shape == (6, n) and list(draws.dims) == ["draw", "time"]
+    assert np.all(draws.values > 0) and list(draws.coords["draw"].values) == list(range(6)) and draws.attrs["units"] == "mg/L"
     ax = MagicMock(name="Axes")
     assert m.plot(cov, ax=ax) is ax and ax.fill_between.called          # discontinuum/plot.py:68-119
     m.plot_observations(ax)                                            # discontinuum/plot.py:42-66
     assert m.contourf(levels=5, y_scale="log", ax=ax) is ax            # loadest_gp/plot.py:51-86 (as tests/test_loadest_gp.py:84)
-    print("loadest: fit / predict / predict_grid / plot / plot_observations / contourf ok; objective", m.history[0], "->", m.history[-1])
+    print("loadest: fit / predict / predict_grid / sample / plot / plot_observations / contourf ok; objective", m.history[0], "->", m.history[-1])
 
     stage = rng.lognormal(1.0, 0.5, n)
     q = 3.0 * (stage - 0.5 * stage.min()) ** 1.6 * np.exp(0.03 * rng.standard_normal(n))
