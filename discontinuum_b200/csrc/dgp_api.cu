@@ -1,18 +1,20 @@
 // libdgp.so -- C ABI (include/dgp.h) and host-side schedule of the B200 exact-GP engine.
 //
-// Per evaluation, on three streams of decreasing priority (P: panel chain, T: trailing updates,
-// W: everything after the factorisation):
+// Per evaluation, on four streams (P: panel chain, highest priority; T and T2: trailing updates;
+// W: everything after the factorisation, lowest priority):
 //   features/residual -> [block-column 0 covariance panel] ->
 //   two-level right-looking Cholesky, panels of 4 block columns:
 //     P: for s in panel: k_potf2_v2(s) -> panel solve(s) (GEMM against T_ss) -> rank-128 update of the panel's columns
 //        (programmatic dependent launches; 64-row half tiles while a launch is smaller than the GPU)
-//     T: rank-512 update right of the panel: next panel's first column | its other columns | the rest   (n^3/3, DMMA)
-//   W: U = L^-T by recursive doubling (two long-K products and a transpose per level)                   (n^3/3, DMMA)
-//      z = U'r, alpha = U z, LAUUM -> Ky^-1 (lower tiles), gradient contraction W (.) dK/dtheta          (n^3/3, DMMA)
+//     T / T2: rank-512 update right of the panel in fixed column strips, strip j on stream j mod 2; the next panel's
+//        columns are the head of their strip: first column | its other columns | the rest of the strip       (n^3/3, DMMA)
+//   W: U = L^-T by recursive doubling (two long-K products and a transpose per level; up to 96 block columns and in batches
+//      the merges are launched as the factorisation passes them)                                            (n^3/3, DMMA)
+//      z = U'r, alpha = U z, LAUUM -> Ky^-1 (lower tiles), gradient contraction W (.) dK/dtheta              (n^3/3, DMMA)
 //   deterministic reductions -> {nlml, info, grad} -> pinned host buffer.
 // Three padded n x n panels: bufA (work matrix, then T = L^-1 and scratch, then Ky^-1), bufL (L, lower), bufU (U = L^-T,
-// upper).  The covariance matrix itself is never stored: tiles are generated in registers as accumulator initial values
-// at their first trailing update.
+// upper).  The covariance matrix itself is never stored: a tile is generated in shared memory in the epilogue of its first
+// trailing update (out = K - sum).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>

@@ -1,15 +1,16 @@
 // FP64 tensor-pipe tile engine: C(128x64 tile) = init -/+ sum_k A[rows, k] * B[rows', k]^T  ("NT" form,
 // both operands K-contiguous), DMMA.8x8x4 (mma.sync.m8n8k4.f64) fed from a TMA + mbarrier ring.
 //
-// One CTA = one 128x64 output tile: warps 0-3 are DMMA consumers (2x2, 64x32 per warp, 128 accumulator
-// registers), warp 4 is the TMA producer.  Two CTAs are co-resident per SM so that one CTA's tile
-// prologue/epilogue overlaps the other's main loop.  Operand tiles are 64-row x 16-col (128 B) TMA boxes
-// with the 128-byte swizzle; the k-index permutation kperm() makes every fragment load conflict free.
+// One CTA = one 128x64 output tile, 256 threads in two warpgroups: warps 0-3 are DMMA consumers (2x2, 64x32 per warp, 128
+// accumulator registers), warp 4 is the TMA producer, warps 5-7 only hand their registers over (setmaxnreg: producer
+// warpgroup 40 registers per thread, consumers 216).  Two CTAs are co-resident per SM so that one CTA's tile
+// prologue/epilogue overlaps the other's main loop.  Operand tiles are 64-row x 16-col (128 B) TMA boxes with the
+// 128-byte swizzle; the k-index permutation kperm() makes every fragment load conflict free.
 //
 // The same kernel runs every O(n^3) phase of the marginal-likelihood evaluation; `mode` selects how a
-// tile index maps to operand panels (decode_job) and the template flags select the accumulator
-// initialisation (zero / load C / generate covariance tile) and the epilogue (store / fused
-// W (.) dK/dtheta contraction / row sum of squares).
+// tile index maps to operand panels (decode_job) and the template flags select what the tile starts from
+// (nothing / its old value / a generated covariance tile -- added in the epilogue, the accumulators always start at
+// zero) and the epilogue (store / fused W (.) dK/dtheta contraction / row sum of squares).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
