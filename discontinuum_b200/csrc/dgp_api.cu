@@ -221,6 +221,16 @@ static int launch_gemm(HT h, const CUtensorMap& a, const CUtensorMap& b, const G
     CK(h, cudaFuncSetAttribute(k_gemm<INIT, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set[dev] = true;
   }
+  if (INIT == INIT_COV) {   // first-touch tiles: alternate "generate first" / "generate last" by wave-sized groups of CTAs
+    static const int gen_first = getenv("DGP_GEN_FIRST") ? atoi(getenv("DGP_GEN_FIRST")) : 0;   // measured: no gain
+    if (gen_first > 0 && g.ntiles > h->sms) {
+      GemmArgs g2 = g;
+      g2.gen_first_mod = h->sms * gen_first;
+      CK(h, launch_ex(k_gemm<INIT, EPI, MT>, g.ntiles, GEMM_THREADS, (size_t)smem_bytes, st, pdl, a, b, h->spec, g2, *bt));
+      h->launches++;
+      return 0;
+    }
+  }
   static const int stagger = getenv("DGP_STAGGER_NS") ? atoi(getenv("DGP_STAGGER_NS")) : 0;
   if (stagger > 0 && MT == 8 && g.ntiles > 2 * h->sms) {
     GemmArgs g2 = g;

@@ -50,6 +50,7 @@ struct GemmArgs {
   int latent;                   // INIT_COV: add only `jitter` on the diagonal (latent posterior covariance)
   int raster;                   // M_LAUUM / M_INV_M / M_INV_U: tiles enumerated in 8 x 16 super-tiles (see decode_job)
   int stagger_ns, stagger_lo;   // experiment (DGP_STAGGER_NS): CTAs [lo, 2 lo) of a launch start this many ns late
+  int gen_first_mod;            // INIT_COV: CTAs with (blockIdx / gen_first_mod) odd generate their tile BEFORE the main loop (0: none)
 };
 
 // Batched launches (dgp_batch_*: several independent sites per launch).  A launch covers the tiles of up to
@@ -359,6 +360,46 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
     }
   }
 
+  // First-touch tiles come in two kinds (INIT_COV launches).  Generating the covariance tile is a long chain of FP64 ALU work
+  // that shares its datapath with the neighbour CTA's DMMAs; if both CTAs of an SM reach it at the same time the tensor pipe
+  // idles.  So every other wave-sized group of CTAs generates its tile FIRST -- row per thread, straight into the output tile
+  // in global memory (it stays in L2) -- and adds it back in the epilogue like an old tile, while the others generate in the
+  // epilogue: the two CTAs of an SM then tend to be in opposite phases.  Same operands, one rounding: bit-identical.
+  if constexpr (INIT == INIT_COV) {
+    if (job.init == INIT_COV && g.gen_first_mod > 0 && (((int)blockIdx.x / g.gen_first_mod) & 1)) {
+      const int t = threadIdx.x;
+      double* xaT = (double*)(smem + SM_XS);
+      double* xb = xaT + DGP_XS * BM;
+      const size_t soff_v = site >= 0 ? (size_t)site * (size_t)bt.ld : 0;
+      const double* Xw_s = g.Xw + soff_v * DGP_XS;
+      const double* noise_s = g.noise + soff_v;
+      cov_compile(cc, spec, g.theta + (site >= 0 ? site * DGP_MAX_THETA : 0), jitter, t, 128);
+      for (int e = t; e < BM * DGP_XS; e += 128) xaT[(e % DGP_XS) * BM + e / DGP_XS] = Xw_s[(size_t)job.crow * DGP_XS + e];
+      for (int e = t; e < BN * DGP_XS; e += 128) xb[e] = Xw_s[(size_t)job.ccol * DGP_XS + e];
+      consumer_bar();
+      const int gr = job.crow + t;
+      const double dn = (gr < npts) ? (g.latent ? jitter : noise_s[gr] + cc->extra_noise) : 0.0;
+      double* crow = g.C + soff_m + (size_t)gr * g.ldc + job.ccol;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += COV_V) {
+        double val[COV_V];
+        cov_vals<COV_V>(cc, xaT, BM, t, xb + c0 * DGP_XS, val);
+#pragma unroll
+        for (int v = 0; v < COV_V; v++) {
+          const int gc = job.ccol + c0 + v;
+          if (gr < npts && gc < npts) { if (gr == gc) val[v] += dn; }
+          else val[v] = (gr == gc) ? 1.0 : 0.0;
+        }
+#pragma unroll
+        for (int v = 0; v < COV_V; v += 2) {
+          double2 o; o.x = val[v]; o.y = val[v + 1];
+          *reinterpret_cast<double2*>(crow + c0 + v) = o;
+        }
+      }
+      consumer_bar();   // the tile is read back in the accumulator layout by other threads of this CTA
+    }
+  }
+
   // ---- main loop.  Fragment addressing: row r of a 64-row box sits at r*128 B; logical 16-byte chunk
   // ch of that row is stored at chunk (ch ^ (r & 7)) (TMA 128B swizzle).  Lane (g8, q) takes, for the
   // s-th k4 step of a stage, k = (q>>1)*8 + 2s + (q&1), i.e. chunk (q>>1)*4 + s, word q&1: the 16
@@ -455,8 +496,11 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
     const int crow_e = jo.crow + (MT == 4 ? 64 * (bx & 1) : 0);
     const int lane_e = tx & 31, warp_e = tx >> 5;
     const int g8e = lane_e >> 2, qe = lane_e & 3, wme = warp_e >> 1, wne = warp_e & 1;
-    bool gen = false;
-    if constexpr (INIT == INIT_COV) gen = (jo.init == INIT_COV);
+    bool gen = false, gen_done = false;   // gen_done: this CTA generated its tile before the main loop (see there)
+    if constexpr (INIT == INIT_COV) {
+      gen_done = jo.init == INIT_COV && g.gen_first_mod > 0 && ((bx / g.gen_first_mod) & 1);
+      gen = (jo.init == INIT_COV) && !gen_done;
+    }
     if (gen) {
       if constexpr (INIT == INIT_COV) {
         // First touch of the tile: out = K + sign * sum.  The accumulators are parked in the (now idle) operand ring as a
@@ -512,7 +556,7 @@ k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensor
         }
       }
     } else {
-      const bool ldc = (INIT == INIT_LOAD || INIT == INIT_COV) && jo.init == INIT_LOAD;
+      const bool ldc = ((INIT == INIT_LOAD || INIT == INIT_COV) && jo.init == INIT_LOAD) || gen_done;
 #pragma unroll
       for (int mi = 0; mi < MT; mi++) {
         double* crow = g.C + soff_e + (size_t)(crow_e + WROWS * wme + 8 * mi + g8e) * g.ldc + jo.ccol + 32 * wne + 2 * qe;
