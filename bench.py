@@ -317,7 +317,7 @@ def main():
         if bad or (rank == 0 and sorted(merged) != keys):
             raise RuntimeError(f"site fits failed: {bad}")
         flop_local = float(sum(float(ns_all[k]) ** 3 * args.site_iterations for k in mine))
-        per_rank = torch.tensor([t_local, stats["gpu_eval_ms"] * 1e-3, stats["predict_s"], stats["host_step_s"], flop_local, float(len(mine))],
+        per_rank = torch.tensor([t_local, stats["fit_wall_s"], stats["predict_s"], stats["host_step_s"], flop_local, float(len(mine))],
                                 dtype=torch.float64, device="cuda")
         all_ranks = [torch.zeros_like(per_rank) for _ in range(world)]
         if dist is not None:
@@ -335,8 +335,8 @@ def main():
             "iterations": args.site_iterations, "predict_grid": 10958, "group": args.site_group,
             "fit_tflops": flop_total / t_sites_max / 1e12, "fit_tflops_per_gpu": flop_total / t_sites_max / 1e12 / world,
             "n_range": {"n_min": int(ns_all[keys].min()), "n_max": int(ns_all[keys].max())},
-            "per_rank": [{"sites": int(r[5]), "wall_s": r[0], "gpu_busy_s": r[1], "gpu_idle_s": r[0] - r[1] - r[2],
-                          "predict_s": r[2], "host_step_s": r[3], "fit_tflops_while_busy": (r[4] / r[1] / 1e12) if r[1] > 0 else None}
+            "per_rank": [{"sites": int(r[5]), "wall_s": r[0], "fit_loop_s": r[1], "other_s": r[0] - r[1] - r[2],
+                          "predict_s": r[2], "host_step_s": r[3], "fit_tflops_in_fit_loop": (r[4] / r[1] / 1e12) if r[1] > 0 else None}
                          for r in rows],
             "what": "BASELINE config 4: the fixed 128-site NWQN-style batch (SURVEY 8d sizes, n = 2000 + 6000 u, seed 42), fit (100 Adam "
                     "iterations) + daily-grid prediction per site, host arrays in / host results out, sites assigned to ranks by cost (LPT), "

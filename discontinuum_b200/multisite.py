@@ -234,27 +234,104 @@ def _predict_site(eng: capi.Engine, s: _Site, theta: np.ndarray, Xs: np.ndarray,
     res["var"] = observed_variance(s.module.spec, theta, var, s.noise, Xs.shape[0])
 
 
+class _GroupRun:
+    """One group of sites on one batch handle: `launch()` enqueues the next optimiser iteration's NLML + gradient evaluation of
+    the whole group, `finish()` collects it and takes the host step.  Two of these in flight on one GPU fill each other's
+    latency-bound stretches (measured: +1 % for two groups of n ~ 7k sites, +8 % for two groups of n ~ 2-3k sites)."""
+
+    def __init__(self, grp, batch, kind, iterations, lr, scheduler, patience, st, timed):
+        self.grp, self.batch, self.kind, self.left, self.st = grp, batch, kind, int(iterations), st
+        self.G = len(grp)
+        batch.set_train(grp[0].module.spec.to_c(), [(s.X, s.y, s.noise) for s in grp])
+        batch.set_timing(timed)
+        self.timed = timed
+        self.opt = GroupOptimizer([s.module for s in grp], lr=lr, scheduler=scheduler, patience=patience)
+        self.ns = np.array([s.X.shape[0] for s in grp], dtype=np.float64)
+        self.inflight = False
+
+    @property
+    def done(self):
+        return self.left <= 0 and not self.inflight
+
+    def launch(self):
+        if self.left <= 0:
+            return False
+        self.alive = np.array([s.failed is None for s in self.grp])
+        if not self.alive.any():
+            self.left = 0
+            return False
+        self.kind.project_raw(self.opt.raw, self.opt.modules, [s.X for s in self.grp])
+        self.nat, self.dnat, self.lp, self.dlp = self.opt.chain()
+        self.theta = np.ascontiguousarray(self.nat)
+        self.batch.nlml_grad_launch(self.theta)
+        self.inflight = True
+        return True
+
+    def finish(self):
+        st, grp, G, alive, theta = self.st, self.grp, self.G, self.alive, self.theta
+        val, grad, info = self.batch.nlml_grad_wait()
+        self.inflight = False
+        self.left -= 1
+        st["evals"] += 1
+        if self.timed:
+            st["gpu_eval_ms"] += sum(self.batch.last_timing())
+        bad = alive & ((info != 0) | ~np.isfinite(val))
+        if bad.any():   # jitter ladder, per site; the others are re-evaluated unchanged and keep their numbers
+            jit = np.zeros(G)
+            for j in JITTERS[1:]:
+                jit[bad] = j
+                v2, g2, i2 = self.batch.nlml_grad(theta, jit)
+                st["retries"] += 1
+                fixed = bad & (i2 == 0) & np.isfinite(v2)
+                val[fixed], grad[fixed], info[fixed] = v2[fixed], g2[fixed], 0
+                bad &= ~fixed
+                if not bad.any():
+                    break
+        t0 = time.perf_counter()
+        obj = (val - self.lp) / self.ns
+        graw = (grad - self.dlp) * self.dnat / self.ns[:, None]
+        ok = alive & ~bad & np.isfinite(obj)
+        for k, s in enumerate(grp):
+            if not alive[k]:
+                continue
+            if ok[k]:
+                s.bad_streak = 0
+                s.history.append(float(obj[k]))
+            else:
+                s.bad_streak += 1
+                if s.bad_streak > 10:
+                    s.failed = f"more than 10 consecutive bad objectives (info={int(info[k])})"
+        self.opt.step(np.where(ok[:, None], graw, 0.0), obj, ok)
+        st["host_step_s"] += time.perf_counter() - t0
+        if self.left <= 0:
+            self.opt.push()
+
+
 def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int = 0, group: int = 16,
                     predict: Optional[Dict[int, np.ndarray]] = None, lr: float = 0.05, scheduler: bool = True,
                     patience: int = 60, model="loadest", stats: Optional[dict] = None, concurrency: Optional[int] = None,
-                    partitions: Optional[int] = None) -> Dict[int, dict]:
+                    partitions: Optional[int] = None, lanes: int = 2) -> Dict[int, dict]:
     """Fit one GP per site on this rank.  sites: {index: (X, y[, noise])} in model space; model: "loadest", "rating" or a
     kind object (see LoadestKind).  Returns {index: {"theta", "objective", "history", "failed", "n", "mu", "var",
     "var_latent"}} ("var" follows `likelihood(model(x))` like MarginalB200.predict).
 
-    Sites are sorted by size and fitted in groups of up to `group` on ONE batch handle (capi.BatchEngine): every
-    iteration is a single launch sequence that evaluates NLML + gradient of the whole group (dgp_batch_nlml_grad), one
+    Sites are sorted by size and fitted in groups of up to `group` on batch handles (capi.BatchEngine): every iteration of a
+    group is a single launch sequence that evaluates NLML + gradient of the whole group (dgp_batch_nlml_grad), one
     device-to-host copy of the G results, and one vectorised host step (GroupOptimizer).  The latency-bound panel chain,
-    which dominated when every site ran its own launch sequence, is paid once per block step for the group.  Evaluations
-    that fail (info != 0 or a non-finite value) climb psd_safe_cholesky's jitter ladder per site; a site whose objective
-    stays bad for more than 10 consecutive iterations is marked failed, as MarginalB200.fit gives up.
+    which dominated when every site ran its own launch sequence, is paid once per block step for the group.  `lanes` groups
+    are in flight at a time, each on its own handle (the largest remaining group next to the smallest, so that memory stays
+    bounded and the pair finishes together); a rank with a single group's worth of sites splits it.  Results do not depend on
+    `lanes`: every site sees the same sequence of evaluations.  Evaluations that fail (info != 0 or a non-finite value) climb
+    psd_safe_cholesky's jitter ladder per site; a site whose objective stays bad for more than 10 consecutive iterations is
+    marked failed, as MarginalB200.fit gives up.
     `concurrency` / `partitions` select the round-1 per-handle pipelines instead (fit_sites_local_per_handle)."""
     if concurrency is not None or partitions is not None:
         return fit_sites_local_per_handle(sites, iterations=iterations, device=device, concurrency=concurrency or 4,
                                           predict=predict, lr=lr, scheduler=scheduler, patience=patience, partitions=partitions)
     kind = _kind(model)
     t_start = time.perf_counter()
-    st = {"groups": 0, "evals": 0, "gpu_eval_ms": 0.0, "predict_s": 0.0, "host_step_s": 0.0, "retries": 0}
+    st = {"groups": 0, "evals": 0, "gpu_eval_ms": 0.0, "fit_wall_s": 0.0, "predict_s": 0.0, "host_step_s": 0.0, "retries": 0,
+          "lanes": 1}
     results: Dict[int, dict] = {}
     if not sites:
         if stats is not None:
@@ -268,78 +345,77 @@ def fit_sites_local(sites: Dict[int, tuple], iterations: int = 100, device: int 
         state[idx] = _Site(idx, X, y, noise, kind.module(X, y, noise))
     order = sorted(state, key=lambda i: (-state[i].X.shape[0], i))
     group = max(1, min(int(group), capi.BATCH_MAX_SITES))
+    lanes = max(1, int(lanes))
+    if lanes > 1 and len(order) >= 2 * lanes:   # enough sites for `lanes` groups at a time: never leave a lane empty
+        group = min(group, -(-len(order) // lanes))
+    pending = _groups(order, group)              # largest sites first
+    lanes = min(lanes, len(pending)) if iterations > 0 else 1
+    st["lanes"] = lanes
     n_max = state[order[0]].X.shape[0]
-    batch = capi.BatchEngine(max_sites=min(group, len(order)), max_n=n_max, device=device) if iterations > 0 else None
+    handles: List[capi.BatchEngine] = []
     single: Optional[capi.Engine] = None
-    try:
-        for members in _groups(order, group):
-            grp = [state[i] for i in members]
-            G = len(grp)
-            st["groups"] += 1
-            if iterations > 0:
-                batch.set_train(grp[0].module.spec.to_c(), [(s.X, s.y, s.noise) for s in grp])
-                batch.set_timing(stats is not None)
-                opt = GroupOptimizer([s.module for s in grp], lr=lr, scheduler=scheduler, patience=patience)
-                ns = np.array([s.X.shape[0] for s in grp], dtype=np.float64)
-                for _ in range(iterations):
-                    alive = np.array([s.failed is None for s in grp])
-                    if not alive.any():
-                        break
-                    kind.project_raw(opt.raw, opt.modules, [s.X for s in grp])
-                    nat, dnat, lp, dlp = opt.chain()
-                    theta = np.ascontiguousarray(nat)
-                    val, grad, info = batch.nlml_grad(theta)
-                    st["evals"] += 1
-                    if stats is not None:
-                        st["gpu_eval_ms"] += sum(batch.last_timing())
-                    bad = alive & ((info != 0) | ~np.isfinite(val))
-                    if bad.any():   # jitter ladder, per site; the others are re-evaluated unchanged and keep their numbers
-                        jit = np.zeros(G)
-                        for j in JITTERS[1:]:
-                            jit[bad] = j
-                            v2, g2, i2 = batch.nlml_grad(theta, jit)
-                            st["retries"] += 1
-                            fixed = bad & (i2 == 0) & np.isfinite(v2)
-                            val[fixed], grad[fixed], info[fixed] = v2[fixed], g2[fixed], 0
-                            bad &= ~fixed
-                            if not bad.any():
-                                break
-                    t0 = time.perf_counter()
-                    obj = (val - lp) / ns
-                    graw = (grad - dlp) * dnat / ns[:, None]
-                    ok = alive & ~bad & np.isfinite(obj)
-                    for k, s in enumerate(grp):
-                        if not alive[k]:
-                            continue
-                        if ok[k]:
-                            s.bad_streak = 0
-                            s.history.append(float(obj[k]))
-                        else:
-                            s.bad_streak += 1
-                            if s.bad_streak > 10:
-                                s.failed = f"more than 10 consecutive bad objectives (info={int(info[k])})"
-                    opt.step(np.where(ok[:, None], graw, 0.0), obj, ok)
-                    st["host_step_s"] += time.perf_counter() - t0
-                opt.push()
-            t0 = time.perf_counter()
-            for s in grp:
+
+    def close_group(grp):
+        nonlocal single
+        t0 = time.perf_counter()
+        for s in grp:
+            with torch.no_grad():
+                theta = s.module.natural().numpy().astype(np.float64)
+            res = {"theta": theta, "history": s.history, "objective": s.history[-1] if s.history else None,
+                   "failed": s.failed, "n": int(s.X.shape[0])}
+            if predict is not None and s.idx in predict and s.failed is None:
+                if single is None:
+                    single = capi.Engine(max_n=n_max, max_m=2048, device=device)
+                kind.project(s.module, np.concatenate([s.X, predict[s.idx]], axis=0))
                 with torch.no_grad():
                     theta = s.module.natural().numpy().astype(np.float64)
-                res = {"theta": theta, "history": s.history, "objective": s.history[-1] if s.history else None,
-                       "failed": s.failed, "n": int(s.X.shape[0])}
-                if predict is not None and s.idx in predict and s.failed is None:
-                    if single is None:
-                        single = capi.Engine(max_n=n_max, max_m=2048, device=device)
-                    kind.project(s.module, np.concatenate([s.X, predict[s.idx]], axis=0))
-                    with torch.no_grad():
-                        theta = s.module.natural().numpy().astype(np.float64)
-                    res["theta"] = theta
-                    _predict_site(single, s, theta, np.ascontiguousarray(predict[s.idx], dtype=np.float64), res)
-                results[s.idx] = res
-            st["predict_s"] += time.perf_counter() - t0
+                res["theta"] = theta
+                _predict_site(single, s, theta, np.ascontiguousarray(predict[s.idx], dtype=np.float64), res)
+            results[s.idx] = res
+        st["predict_s"] += time.perf_counter() - t0
+
+    try:
+        if iterations <= 0:
+            for members in pending:
+                st["groups"] += 1
+                close_group([state[i] for i in members])
+        else:
+            for _ in range(lanes):
+                handles.append(capi.BatchEngine(max_sites=min(group, len(order)), max_n=n_max, device=device))
+            runs: List[Optional[_GroupRun]] = [None] * lanes
+
+            def next_group(lane):
+                if not pending:
+                    return None
+                members = pending.pop(0) if lane == 0 else pending.pop()   # lane 0 from the large end, the others from the small end
+                st["groups"] += 1
+                return _GroupRun([state[i] for i in members], handles[lane], kind, iterations, lr, scheduler, patience, st,
+                                 stats is not None)
+
+            # rolling: every lane always has an evaluation in flight (wait -> host step -> launch the next one), so the GPU
+            # works on one group while the host steps the other
+            t_loop, p_before = time.perf_counter(), st["predict_s"]
+            for lane in range(lanes):
+                runs[lane] = next_group(lane)
+                if runs[lane] is not None:
+                    runs[lane].launch()
+            while any(r is not None for r in runs):
+                for lane, r in enumerate(runs):
+                    if r is None:
+                        continue
+                    if r.inflight:
+                        r.finish()
+                    if r.left > 0 and not r.launch() and r.left <= 0:
+                        r.opt.push()             # (every site of the group has failed: nothing left to evaluate)
+                    if r.done:
+                        close_group(r.grp)
+                        runs[lane] = next_group(lane)
+                        if runs[lane] is not None:
+                            runs[lane].launch()
+            st["fit_wall_s"] = (time.perf_counter() - t_loop) - (st["predict_s"] - p_before)
     finally:
-        if batch is not None:
-            batch.close()
+        for b in handles:
+            b.close()
         if single is not None:
             single.close()
     if stats is not None:
@@ -501,7 +577,7 @@ def fit_sites_local_per_handle(sites: Dict[int, tuple], iterations: int = 100, d
 
 def fit_sites(sites: Dict[int, tuple], iterations: int = 100, predict: Optional[Dict[int, np.ndarray]] = None,
               group: int = 16, dist=None, device: int = 0, model="loadest", stats: Optional[dict] = None,
-              concurrency: Optional[int] = None) -> Optional[Dict[int, dict]]:
+              concurrency: Optional[int] = None, lanes: int = 2) -> Optional[Dict[int, dict]]:
     """Shard `sites` (every rank holds the same dict, or at least the same keys and sizes) over the ranks of
     `dist`, fit this rank's share, gather everything on rank 0."""
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
@@ -511,7 +587,7 @@ def fit_sites(sites: Dict[int, tuple], iterations: int = 100, predict: Optional[
     mine = [keys[i] for i in assign_sites(costs, world)[rank]]
     local = fit_sites_local({k: sites[k] for k in mine}, iterations=iterations, device=device, group=group,
                             predict={k: predict[k] for k in mine} if predict else None, model=model, stats=stats,
-                            concurrency=concurrency)
+                            concurrency=concurrency, lanes=lanes)
     return gather_results(local, dist)
 
 

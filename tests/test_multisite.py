@@ -155,7 +155,12 @@ def test_concurrent_sites_match_single_site_fits(cuda_device):
     stats = {}
     resb = multisite.fit_sites(sites, iterations=8, predict=grid, group=2, stats=stats)  # batched groups: (700, 450), (300)
     assert sorted(res) == [0, 1, 2] and sorted(resb) == [0, 1, 2]
-    assert stats["groups"] == 2 and stats["evals"] == 16 and stats["gpu_eval_ms"] > 0
+    assert stats["groups"] == 2 and stats["evals"] == 16 and stats["gpu_eval_ms"] > 0 and stats["lanes"] == 2
+    # two groups in flight (default) or one after the other: every site sees the same evaluations
+    resb1 = multisite.fit_sites(sites, iterations=8, predict=grid, group=2, lanes=1)
+    for i in sites:
+        assert resb1[i]["history"] == resb[i]["history"] and np.array_equal(resb1[i]["theta"], resb[i]["theta"])
+        assert np.array_equal(resb1[i]["mu"], resb[i]["mu"])
     for i, (X, y) in sites.items():
         raw = orc.loadest_init_raw()
         _, hist = orc.fit_adam("loadest", raw, torch.tensor(X), torch.tensor(y), orc.loadest_noise(X.shape[0]), iterations=8)
