@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--sites", type=int, default=128, help="sites of the NWQN-style batch (BASELINE config 4: 128), sharded over the ranks")
     ap.add_argument("--site-iterations", type=int, default=100)
     ap.add_argument("--site-group", type=int, default=16, help="sites per batched launch sequence")
+    ap.add_argument("--site-lanes", type=int, default=2, help="groups in flight per GPU (each on its own batch handle)")
     ap.add_argument("--c5-n", type=int, default=32768)
     ap.add_argument("--c5-m", type=int, default=100000)
     ap.add_argument("--c5-draws", type=int, default=1000)
@@ -307,7 +308,7 @@ def main():
         stats = {}
         t0 = time.perf_counter()
         res = multisite.fit_sites_local(sites, iterations=args.site_iterations, device=local, group=args.site_group,
-                                        predict=grids, stats=stats)
+                                        predict=grids, stats=stats, lanes=args.site_lanes)
         t_local = time.perf_counter() - t0
         summary = {k: {"theta": r["theta"], "objective": r["objective"], "failed": r["failed"]} for k, r in res.items()}
         merged = multisite.gather_results(summary, dist)   # the only collective: final gather on rank 0
@@ -332,7 +333,7 @@ def main():
         flop_total = sum(r[4] for r in rows)
         extra["sites"] = {
             "metric": "sites_per_sec", "value": len(keys) / t_sites_max, "unit": "sites/s", "sites": len(keys), "scaling": "strong",
-            "iterations": args.site_iterations, "predict_grid": 10958, "group": args.site_group,
+            "iterations": args.site_iterations, "predict_grid": 10958, "group": args.site_group, "lanes": args.site_lanes,
             "fit_tflops": flop_total / t_sites_max / 1e12, "fit_tflops_per_gpu": flop_total / t_sites_max / 1e12 / world,
             "n_range": {"n_min": int(ns_all[keys].min()), "n_max": int(ns_all[keys].max())},
             "per_rank": [{"sites": int(r[5]), "wall_s": r[0], "fit_loop_s": r[1], "other_s": r[0] - r[1] - r[2],
