@@ -245,6 +245,17 @@ def main():
                     "noise": tolist(owner.likelihood.noise), "second_noise": tolist(owner.likelihood.second_noise),
                     "gate_a": float(model.covar_module.kernels[0].kernels[0].a)})
         cases.append(rec)
+    # ... and without a target uncertainty: the default noise of build_model (rating_gp/models/gpytorch.py:69-70)
+    owner = types.SimpleNamespace()
+    torch.manual_seed(8)
+    model = ref_rating.RatingGPMarginalGPyTorch.build_model(owner, x_t, y_t)
+    with torch.no_grad():
+        model.powerlaw.b.fill_(1.9); model.powerlaw.c.fill_(0.2)
+    rec = evaluate(owner, model, x_t, y_t, xs_t)
+    rec.update({"model": "rating", "case": "initial, default noise", "X": X.tolist(), "y": y.tolist(), "Xs": Xs.tolist(),
+                "noise": tolist(owner.likelihood.noise), "second_noise": tolist(owner.likelihood.second_noise),
+                "gate_a": float(model.covar_module.kernels[0].kernels[0].a)})
+    cases.append(rec)
     # ---------------------------------------------------------------- the reference's own optimiser loop
     fits = []
     n = 24

@@ -49,7 +49,7 @@ def _oracle_pieces(case, mod):
     return X, y, noise, theta, nat, orc.rating_cov, orc.rating_mean, nat["noise"], orc.rating_log_prior(nat)
 
 
-@pytest.mark.parametrize("idx", range(5))
+@pytest.mark.parametrize("idx", range(6))
 def test_oracle_matches_reference_model_code(idx):
     case = _cases()[idx]
     mod = _module_from_reference_state(case)
@@ -81,6 +81,8 @@ def test_oracle_matches_reference_model_code(idx):
         assert abs(sd["covar_module.kernels.0.kernels.0.raw_b_constraint.lower_bound"] - b_lo) <= 1e-15
         assert abs(sd["covar_module.kernels.0.kernels.0.raw_b_constraint.upper_bound"] - b_hi) <= 1e-15
         assert abs(float(nat["noise"]) - case["second_noise"][0]) <= 1e-14
+        if "default noise" in case["case"]:
+            assert np.allclose(np.array(case["noise"]), models.RATING_DEFAULT_NOISE, rtol=0, atol=1e-18)
 
 
 def test_reference_state_round_trips_through_the_checkpoint_mapping():
@@ -101,7 +103,7 @@ def test_reference_state_round_trips_through_the_checkpoint_mapping():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("idx", range(5))
+@pytest.mark.parametrize("idx", range(6))
 def test_engine_matches_reference_model_code(cuda_device, idx):
     from discontinuum_b200 import capi
 
