@@ -255,3 +255,73 @@ def test_sample_sharded_two_ranks_match_single_gpu_draws(cuda_device):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     assert r.stdout.count(" OK") == 2, r.stdout[-2000:]
+
+
+class _OracleBatch:
+    """capi.BatchEngine's surface as fit_sites_local drives it, served by the CPU oracle (loadest sites)."""
+    created = 0
+
+    def __init__(self, max_sites, max_n, device=0):
+        type(self).created += 1
+        self.inflight = None
+
+    def set_train(self, spec_c, sites):
+        self.sites = [(torch.tensor(X), torch.tensor(y), torch.tensor(nz)) for X, y, nz in sites]
+
+    def set_timing(self, on):
+        pass
+
+    def last_timing(self):
+        return [0.0, 0.0, 0.0, 0.0]
+
+    def _eval(self, theta):
+        import helpers as H
+        from helpers import orc
+
+        G = len(self.sites)
+        val, grad, info = np.zeros(G), np.zeros((G, theta.shape[1])), np.zeros(G, dtype=np.int32)
+        for k, (X, y, nz) in enumerate(self.sites):
+            nat = H.loadest_nat_from_theta(theta[k], X.shape[1])
+            with torch.enable_grad():
+                v, g, _, _ = orc.nlml_grad_closed_form(orc.loadest_cov, orc.loadest_mean, nat, X, y, nz)
+            val[k], grad[k] = float(v), H.loadest_theta_from_nat({n: t.numpy() for n, t in g.items()})
+        return val, grad, info
+
+    def nlml_grad_launch(self, theta, jitter=None):
+        assert self.inflight is None, "one evaluation in flight per handle"
+        self.inflight = np.array(theta)
+
+    def nlml_grad_wait(self):
+        theta, self.inflight = self.inflight, None
+        return self._eval(theta)
+
+    def nlml_grad(self, theta, jitter=None):
+        return self._eval(np.array(theta))
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize("nsites,group", [(5, 2), (4, 16), (1, 16), (7, 3)])
+def test_groups_in_flight_schedule_is_result_neutral(monkeypatch, nsites, group):
+    """fit_sites_local with 1, 2 or 3 groups in flight (the pairing of large and small groups, a rank whose sites fit one group
+    being split, odd group counts, a single site): every site ends with the same history and parameters.  CPU stand-in for the
+    batch handle; the same property is checked on the GPU with the real one."""
+    from discontinuum_b200 import capi, synthetic
+
+    monkeypatch.setattr(capi, "BatchEngine", _OracleBatch)
+    sites = {i: synthetic.loadest_site(24 + 5 * i, 300 + i)[:2] for i in range(nsites)}
+    out = {}
+    for lanes in (1, 2, 3):
+        stats = {}
+        _OracleBatch.created = 0
+        res = multisite.fit_sites_local(sites, iterations=4, group=group, lanes=lanes, stats=stats)
+        assert sorted(res) == list(range(nsites)) and all(r["failed"] is None and len(r["history"]) == 4 for r in res.values())
+        assert stats["lanes"] == _OracleBatch.created <= lanes and stats["evals"] == 4 * stats["groups"]
+        if nsites >= 2 * lanes:
+            assert stats["lanes"] == lanes      # enough sites: no lane stays empty (one group's worth of sites is split)
+        out[lanes] = res
+    for i in range(nsites):
+        for lanes in (2, 3):
+            assert out[lanes][i]["history"] == out[1][i]["history"]
+            assert np.array_equal(out[lanes][i]["theta"], out[1][i]["theta"])
