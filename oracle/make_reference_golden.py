@@ -343,6 +343,30 @@ def main():
                 "time_ns": time.astype("datetime64[ns]").astype(np.int64).tolist(), "flow": flow.tolist(), "target": conc.tolist(),
                 "total_iterations": 18}
     print("checkpoint: first", len(first), "iterations, resumed", len(history), "more:", history[0], "->", history[-1])
+    # ... and for rating-gp, whose optimiser sees the parameters in a different order than this engine's theta (likelihood first)
+    ckpt_path_r = os.path.join(os.path.dirname(HERE), "tests", "golden", "ref_checkpoint_rating.pt")
+    cov_r = _fx.Dataset({"stage": ("time", stage)}, coords={"time": time})
+    tgt_r = _fx.DataArray(q, coords={"time": time}, dims=("time",), attrs={"units": "cfs"}, name="discharge")
+    unc_r = _fx.DataArray(gse, coords={"time": time}, dims=("time",), name="gse")
+    del history[:]
+    torch.optim.lr_scheduler.ReduceLROnPlateau.step = step
+    torch.float32 = torch.float64
+    try:
+        torch.manual_seed(9)
+        r1 = ref_rating.RatingGPMarginalGPyTorch()
+        r1.fit(covariates=cov_r, target=tgt_r, target_unc=unc_r, iterations=8)
+        r1.save(ckpt_path_r)
+        first_r = list(history)
+        del history[:]
+        r2 = ref_rating.RatingGPMarginalGPyTorch.load(ckpt_path_r, cov_r, tgt_r, unc_r)
+        r2.fit(covariates=cov_r, target=tgt_r, target_unc=unc_r, iterations=18, resume=True)
+    finally:
+        torch.float32 = f32
+        torch.optim.lr_scheduler.ReduceLROnPlateau.step = orig_step
+    ckpt_rating = {"file": "ref_checkpoint_rating.pt", "first_history": first_r, "resumed_history": list(history),
+                   "time_ns": time.astype("datetime64[ns]").astype(np.int64).tolist(), "stage": stage.tolist(), "target": q.tolist(),
+                   "target_unc": gse.tolist(), "total_iterations": 18}
+    print("rating checkpoint: first", len(first_r), "iterations, resumed", len(history), "more:", history[0], "->", history[-1])
     # ---------------------------------------------------------------- the PyMC model (loadest_gp/models/pymc.py:30-88)
     pymc_cases = []
     for nd in (2, 3):
@@ -362,7 +386,8 @@ def main():
     print("pymc", [(c["ndim"], c["case"], c["neg_logp"]) for c in pymc_cases])
     out = os.path.join(os.path.dirname(HERE), "tests", "golden", "ref_models.json")
     with open(out, "w") as f:
-        json.dump({"generator": "oracle/make_reference_golden.py", "checkpoint": ckpt_rec, "pymc": pymc_cases, "reference": "thodson-usgs/discontinuum (src/ as found under "
+        json.dump({"generator": "oracle/make_reference_golden.py", "checkpoint": ckpt_rec, "checkpoint_rating": ckpt_rating,
+                   "pymc": pymc_cases, "reference": "thodson-usgs/discontinuum (src/ as found under "
                    "/root/reference), model, engine, data-manager and pipeline code unmodified; third-party layers = "
                    "oracle/gpytorch_standin and tests/fake_xarray.py",
                    "cases": cases, "fits": fits, "end_to_end": e2e}, f)

@@ -336,6 +336,44 @@ def test_resume_from_a_reference_written_checkpoint(cuda_device):
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-6, np.max(np.abs(got - ref) / np.abs(ref))
 
 
+def test_reference_written_rating_checkpoint_loads_without_pickled_code():
+    """The same for rating-gp (tests/golden/ref_checkpoint_rating.pt, written by RatingGPMarginalGPyTorch.save()): the
+    reference's optimiser holds the likelihood's noise first and the power-law / sigmoid parameters in its own module order
+    (checkpoint._RATING_ORDER), so this is the layout where a wrong order would load silently into the wrong moments."""
+    from discontinuum_b200 import engine
+
+    path = os.path.join(os.path.dirname(GOLD), "ref_checkpoint_rating.pt")
+    with torch.serialization.safe_globals([engine._reference_model_config_shim()]):
+        ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    assert ckpt["model_class"].endswith("RatingGPMarginalGPyTorch")
+    mod = spec.GPModule(models.rating_spec(1.1, 1.9))   # (bounds: any; only the parameter layout is checked here)
+    checkpoint.load_state(mod, ckpt["model_state_dict"], ckpt["likelihood_state_dict"])
+    order = checkpoint.reference_parameter_order(mod)
+    ref_state = ckpt["optimizer_state_dict"]["state"]
+    assert len(ref_state) == len(order)
+    for j, (_, key, shape, idx) in enumerate(order):
+        assert tuple(ref_state[j]["exp_avg"].shape) == shape, key
+    osd = checkpoint.optimizer_state_from_reference(mod, ckpt["optimizer_state_dict"])
+    assert len(osd["state"]) == len(mod.raw_list()) and all(float(v["step"]) == 8.0 for v in osd["state"].values())
+    torch.optim.Adam(mod.raw_list(), lr=0.05).load_state_dict(osd)
+
+
+@pytest.mark.gpu
+def test_resume_from_a_reference_written_rating_checkpoint(cuda_device):
+    """RatingGP.load(<checkpoint written by the reference's save()>) + fit(resume=True) follows the reference's own resumed
+    trajectory (fixed per-observation noise, monotonicity penalty, likelihood-first parameter order)."""
+    with open(GOLD) as f:
+        rec = json.load(f)["checkpoint_rating"]
+    time = np.array(rec["time_ns"], dtype="int64").astype("datetime64[ns]")
+    cov, target, unc = {"time": time, "stage": np.array(rec["stage"])}, np.array(rec["target"]), np.array(rec["target_unc"])
+    m = models.RatingGP.load(os.path.join(os.path.dirname(GOLD), rec["file"]), cov, target, unc)
+    m.fit(cov, target, target_unc=unc, iterations=rec["total_iterations"], resume=True)
+    ref = np.array(rec["resumed_history"])
+    got = np.array(m.history)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-6, np.max(np.abs(got - ref) / np.abs(ref))
+
+
 def _pymc_cases():
     with open(GOLD) as f:
         return json.load(f)["pymc"]
