@@ -641,8 +641,13 @@ static int factor_panel(dgp_handle h, const CholBufs& b, int pb, int pe, bool ge
   const long long ld = b.ld;
   int rc;
   const bool pdl = h->pdl && !h->trace_path;  // the trace's events would sit between the kernels
-  // timing experiments only (results are garbage): DGP_SKIP bit 0: no diagonal-block kernel, 1: no panel solve, 2: no in-panel update
+  // timing experiments only (results are garbage), compiled in with -DDGP_EXPERIMENTS and never in the shipped library:
+  // DGP_SKIP bit 0: no diagonal-block kernel, 1: no panel solve, 2: no in-panel update
+#ifdef DGP_EXPERIMENTS
   static const int skip = getenv("DGP_SKIP") ? atoi(getenv("DGP_SKIP")) : 0;
+#else
+  constexpr int skip = 0;
+#endif
   for (int s = pb; s < pe; s++) {
     const size_t off = (size_t)s * 128 * ld + (size_t)s * 128;
     const bool inplace = (b.L == b.A);
