@@ -90,6 +90,7 @@ struct dgp_handle_s {
   int eager_max_h = 0;               // above 96 block columns: highest merge level that goes early (DGP_EAGER_MAXH; 0 = none: measured no gain at n = 16384 for 4 / 8 / 16 / 32)
   int strip_blocks = 8;              // width of a column strip in block columns (DGP_STRIP_BLOCKS, 0: one stream, no strips)
   bool inpanel_left = false;         // in-panel updates left-looking (one rank-(128 j) update per column; DGP_INPANEL_LEFT=1)
+  bool pregen = true;                // standalone covariance generator ahead of the factorisation (DGP_PREGEN=0: first-touch generation)
   struct GraphSlot { cudaGraphExec_t exec = nullptr; double jitter = 0.0; bool seen = false; long long launches = 0; };
   GraphSlot graphs[3];               // per evaluation level (nlml / nlml+grad / factorize)
   bool use_graphs = false;  // opt-in (DGP_GRAPHS=1): replay loses the stream priorities of the look-ahead, measured slower
@@ -327,6 +328,8 @@ int dgp_create(dgp_handle* out, int device, int max_n, int max_m, void* stream) 
     if (ch) h->chain_half = atoi(ch) != 0;
     const char* pb = getenv("DGP_PANEL_BLOCKS");
     if (pb && atoi(pb) >= 1 && atoi(pb) <= 64) h->panel_blocks = atoi(pb);
+    const char* pg = getenv("DGP_PREGEN");
+    if (pg) h->pregen = atoi(pg) != 0;
     const char* il = getenv("DGP_INPANEL_LEFT");
     if (il) h->inpanel_left = atoi(il) != 0;
   }
@@ -724,11 +727,35 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
   const int sw = (h->strip_blocks + pw - 1) / pw * pw;
   cudaStream_t T2 = (P != T && sw > 0 && h->stream_t2 != nullptr && !h->use_graphs) ? h->stream_t2 : nullptr;
   bool any2 = false;
-  if ((rc = ensure_events(h, 3 * (size_t)npanels + 3))) return rc;
+  const int nstrips = sw > 0 ? (nb + sw - 1) / sw : 0;
+  // DGP_PREGEN (default on): the covariance matrix is written by a standalone generator, strip by strip on the
+  // low-priority stream while the first panel is factored, and the first trailing update reads it like any later one
+  const bool pregen = generate && h->pregen && nb > DGP_PREGEN_MIN_NB;
+  const bool pregen_strips = pregen && T2 != nullptr && h->stream_lo != nullptr && nstrips > 1;
+  if ((rc = ensure_events(h, 3 * (size_t)npanels + 3 + (size_t)nstrips))) return rc;
+  auto ev_gen = [&](int j) { return h->evs[3 * (size_t)npanels + 2 + j]; };
   auto ev_panel = [&](int p) { return h->evs[3 * p]; };
   auto ev_cols = [&](int p) { return h->evs[3 * p + 1]; };   // all columns of panel p have the updates of panels < p
   auto ev_col0 = [&](int p) { return h->evs[3 * p + 2]; };   // ... its first block column has them
-  if (generate) {
+  if (pregen && !pregen_strips) {   // one trailing stream: everything up front, in stream order
+    k_cov_lower<<<dim3(nb * 4, nb), 256, 0, T>>>(h->spec, h->theta, h->Xw, h->noise, jitter, b.A, ld, h->n, 0);
+    h->launches++;
+    CK(h, cudaGetLastError());
+  } else if (pregen) {
+    k_cov_lower<<<dim3(nb * 4, sw), 256, 0, T>>>(h->spec, h->theta, h->Xw, h->noise, jitter, b.A, ld, h->n, 0);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    CK(h, cudaEventRecord(h->evs[3 * (size_t)npanels + 1], T));
+    cudaStream_t G = h->stream_lo;
+    CK(h, cudaStreamWaitEvent(G, h->evs[3 * (size_t)npanels + 1], 0));
+    for (int j = 1; j < nstrips; j++) {
+      const int o = j * sw, wj = (o + sw < nb) ? sw : nb - o;
+      k_cov_lower<<<dim3((nb - o) * 4, wj), 256, 0, G>>>(h->spec, h->theta, h->Xw, h->noise, jitter, b.A, ld, h->n, o);
+      h->launches++;
+      CK(h, cudaGetLastError());
+      CK(h, cudaEventRecord(ev_gen(j), G));
+    }
+  } else if (generate) {
     k_cov_rect<<<dim3(nb * 4, 1), 256, 0, T>>>(h->spec, h->theta, h->Xw, h->Xw, h->noise, jitter, b.A, ld, h->n,
                                                h->n, 1, 1, nullptr, nullptr, 0);
     h->launches++;
@@ -741,7 +768,7 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
   for (int p = 0; p < npanels; p++) {
     const int pb = p * pw, pe = (pb + pw < nb) ? pb + pw : nb;
     if (P != T && p > 0) CK(h, cudaStreamWaitEvent(P, ev_col0(p), 0));
-    if ((rc = factor_panel(h, b, pb, pe, generate, jitter, fwd, P, (P != T && p > 0) ? ev_cols(p) : nullptr))) return rc;
+    if ((rc = factor_panel(h, b, pb, pe, generate && !pregen, jitter, fwd, P, (P != T && p > 0) ? ev_cols(p) : nullptr))) return rc;
     if (P != T) {
       CK(h, cudaEventRecord(ev_panel(p), P));
       CK(h, cudaStreamWaitEvent(T, ev_panel(p), 0));
@@ -755,13 +782,17 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
       // The next panel's columns are the head of their strip: first column | its other columns | the rest of the strip.
       const int ne = (pe + pw < nb) ? pe + pw : nb, w = ne - pe, m = nb - pe;
       const int slots = 2 * h->sms;
-      const bool first = generate && p == 0;
+      const bool first = generate && p == 0 && !pregen;
       const int j0 = pe / sw;
       bool used2 = false;
       auto strip_stream = [&](int j) -> cudaStream_t {
-        if ((j & 1) == 0) return T;
-        if (!used2) { used2 = true; cudaStreamWaitEvent(T2, ev_panel(p), 0); }
-        return T2;
+        cudaStream_t S = T;
+        if (j & 1) {
+          if (!used2) { used2 = true; cudaStreamWaitEvent(T2, ev_panel(p), 0); }
+          S = T2;
+        }
+        if (pregen_strips && p == 0 && j > 0) cudaStreamWaitEvent(S, ev_gen(j), 0);
+        return S;
       };
       cudaStream_t S0 = strip_stream(j0);
       trace_mark(h, S0, "cols<", p);
@@ -788,14 +819,14 @@ static int potrf_core(dgp_handle h, const CholBufs& b, bool generate, double jit
       trace_mark(h, T, "cols<", p);
       // (half tiles while a launch has fewer tiles than the GPU has CTA slots: a K = 512 tile is 34 us on its own)
       const int slots = 2 * h->sms;
-      if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, pe, 1, m * 2, generate && p == 0, jitter, T, h->chain_half && m * 2 <= slots))) return rc;
+      if ((rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, pe, 1, m * 2, generate && p == 0 && !pregen, jitter, T, h->chain_half && m * 2 <= slots))) return rc;
       if (P != T) CK(h, cudaEventRecord(ev_col0(p + 1), T));
-      if (w > 1 && (rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, pe + 1, w - 1, (m - 1) * 2 * (w - 1), generate && p == 0, jitter, T,
+      if (w > 1 && (rc = launch_trail(h, b, M_TRAIL_COL, pb, pe - pb, pe + 1, w - 1, (m - 1) * 2 * (w - 1), generate && p == 0 && !pregen, jitter, T,
                                       h->chain_half && (m - 1) * 2 * (w - 1) <= slots))) return rc;
       trace_mark(h, T, "cols>", p);
       if (P != T) CK(h, cudaEventRecord(ev_cols(p + 1), T));
       const int m2 = nb - ne;
-      if (m2 > 0 && (rc = launch_trail(h, b, M_TRAIL, pb, pe - pb, ne, 0, m2 * (m2 + 1), generate && p == 0, jitter, T,
+      if (m2 > 0 && (rc = launch_trail(h, b, M_TRAIL, pb, pe - pb, ne, 0, m2 * (m2 + 1), generate && p == 0 && !pregen, jitter, T,
                                        h->chain_half && m2 * (m2 + 1) <= slots))) return rc;
       trace_mark(h, T, "rest>", p);
     }

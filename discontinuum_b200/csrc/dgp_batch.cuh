@@ -27,6 +27,7 @@ struct dgp_batch_s {
   std::vector<cudaEvent_t> evs;
   int panel_blocks = 4;
   bool pdl = true, chain_half = true, timing = false;
+  bool pregen = true;        // standalone covariance generator ahead of the factorisation (DGP_PREGEN=0: first-touch generation)
   bool inpanel_left = false; // in-panel updates left-looking (DGP_INPANEL_LEFT=1; default: right-looking rank-128 updates, like the single-site engine -- the two must agree for bit-identical results)
   int max_sites = 0, max_pad = 0, max_n = 0;
   int G = 0, NB = 0;
@@ -129,6 +130,24 @@ int b_potrf(dgp_batch_t b, BInvProgress* eager) {
   CK(b, cudaGetLastError());
   CK(b, cudaEventRecord(ev_cols(0), T));
   CK(b, cudaStreamWaitEvent(P, ev_cols(0), 0));
+  // standalone generator (potrf_core's DGP_PREGEN schedule): the sites with more than DGP_PREGEN_MIN_NB block columns get their
+  // whole lower triangle written on the low-priority stream while the first diagonal blocks are factored, and their first
+  // updates read it like any later one.  The same sites by the same rule as the single-site engine: bit-identical results.
+  bool pre[DGP_BATCH_MAX];
+  bool any_pre = false, wP = false, wT = false, w2 = false;
+  for (int i = 0; i < G; i++) {
+    pre[i] = b->pregen && b->nb[i] > DGP_PREGEN_MIN_NB;
+    any_pre |= pre[i];
+  }
+  cudaEvent_t ev_gen = b->evs[3 * (size_t)npanels + 1];
+  if (any_pre) {
+    CK(b, cudaStreamWaitEvent(b->stream_lo, ev_cols(0), 0));
+    k_cov_lower_b<<<dim3(4 * NB, NB - 1, G), 256, 0, b->stream_lo>>>(b->spec, b->sd, b->theta, b->Xw, b->noise, b->jitv, b->A,
+                                                                            DGP_PREGEN_MIN_NB);
+    b->launches++;
+    CK(b, cudaGetLastError());
+    CK(b, cudaEventRecord(ev_gen, b->stream_lo));
+  }
   const int slots = 2 * b->sms;
   for (int p = 0; p < npanels; p++) {
     const int pb = p * pw, pe = (pb + pw < NB) ? pb + pw : NB;
@@ -153,12 +172,12 @@ int b_potrf(dgp_batch_t b, BInvProgress* eager) {
           // round differently, and with the C tile prefetched they cost the same (measured): the default is right-looking
           // in both engines, which keeps batch and single-site results bit-identical.
           const int lpb = pb - b->off[i];
-          const bool first = (lpb == 0);   // columns of a site's first panel are generated here
+          const bool first = (lpb == 0) && !pre[i];   // columns of a site's first panel are generated here
           inp.add(i, lpb, nbi, b->n[i], (s + 1) | (1 << 16), s + 1 - lpb, first ? 0 : 1, m * 2);
           inp.any_first |= first && m > 0;
         } else if (s + 1 < lpe) {
           const int w = lpe - s - 1;
-          const bool first = (s == 0);
+          const bool first = (s == 0) && !pre[i];
           inp.add(i, s, nbi, b->n[i], (s + 1) | (w << 16), 1, first ? 0 : 1, m * 2 * w);
           inp.any_first |= first && m > 0;
         }
@@ -176,11 +195,14 @@ int b_potrf(dgp_batch_t b, BInvProgress* eager) {
       if (inp.total > 0) {   // rank-128 update of the panel's own remaining columns
         const bool waited = (t == pb && p > 0);
         if (waited) CK(b, cudaStreamWaitEvent(P, ev_cols(p), 0));
-        if ((rc = b_launch_trail(b, inp, M_TRAIL_COL, P, b->sms, b->pdl && !waited))) return rc;
+        const bool gen_wait = any_pre && !wP;
+        if (gen_wait) { wP = true; CK(b, cudaStreamWaitEvent(P, ev_gen, 0)); }
+        if ((rc = b_launch_trail(b, inp, M_TRAIL_COL, P, b->sms, b->pdl && !waited && !gen_wait))) return rc;
       }
     }
     CK(b, cudaEventRecord(ev_panel(p), P));
     CK(b, cudaStreamWaitEvent(T, ev_panel(p), 0));
+    if (any_pre && !wT) { wT = true; CK(b, cudaStreamWaitEvent(T, ev_gen, 0)); }
     if (eager != nullptr && pe < NB && (rc = b_eager(b, eager, ev_panel(p), pe))) return rc;
     // ---- rank-(128 pw) update right of the panel.  Column strips on two streams (potrf_core of dgp_api.cu): fixed strips
     // of `sw` block columns in the end-aligned (global) column numbering, strip j always on stream j mod 2; the next panel's
@@ -191,6 +213,7 @@ int b_potrf(dgp_batch_t b, BInvProgress* eager) {
       auto strip_stream = [&](int j) -> cudaStream_t {
         if ((j & 1) == 0) return T;
         if (!used2) { used2 = true; cudaStreamWaitEvent(T2, ev_panel(p), 0); }
+        if (any_pre && !w2) { w2 = true; cudaStreamWaitEvent(T2, ev_gen, 0); }
         return T2;
       };
       cudaStream_t S0 = strip_stream(j0);
@@ -202,7 +225,7 @@ int b_potrf(dgp_batch_t b, BInvProgress* eager) {
         const int lpe = (pe - b->off[i] < nbi) ? pe - b->off[i] : nbi;
         if (lpe >= nbi) continue;
         const int kb = lpe - lpb, ne = (lpe + pw < nbi) ? lpe + pw : nbi, w = ne - lpe, m = nbi - lpe;
-        const bool first = (lpb == 0);
+        const bool first = (lpb == 0) && !pre[i];
         const int a2 = first ? 0 : 1;
         ta.add(i, lpb, nbi, b->n[i], lpe | (1 << 16), kb, a2, m * 2);
         ta.any_first |= first;
@@ -226,7 +249,7 @@ int b_potrf(dgp_batch_t b, BInvProgress* eager) {
           const int o = j * sw - b->off[i];
           if (lpe >= nbi || o >= nbi) continue;
           const int wj = (o + sw < nbi) ? sw : nbi - o;
-          const bool first = (lpb == 0);
+          const bool first = (lpb == 0) && !pre[i];
           ts.add(i, lpb, nbi, b->n[i], o | (wj << 16), lpe - lpb, first ? 0 : 1, (nbi - o) * 2 * wj);
           ts.any_first |= first;
         }
@@ -243,7 +266,7 @@ int b_potrf(dgp_batch_t b, BInvProgress* eager) {
       const int lpe = (pe - b->off[i] < nbi) ? pe - b->off[i] : nbi;
       if (lpe >= nbi) continue;
       const int kb = lpe - lpb, ne = (lpe + pw < nbi) ? lpe + pw : nbi, w = ne - lpe, m = nbi - lpe, m2 = nbi - ne;
-      const bool first = (lpb == 0);
+      const bool first = (lpb == 0) && !pre[i];
       const int a2 = first ? 0 : 1;
       ta.add(i, lpb, nbi, b->n[i], lpe | (1 << 16), kb, a2, m * 2);
       ta.any_first |= first;
@@ -454,6 +477,8 @@ int dgp_batch_create(dgp_batch* out, int device, int max_sites, int max_n, void*
   if (ch) b->chain_half = atoi(ch) != 0;
   const char* pbk = getenv("DGP_PANEL_BLOCKS");
   if (pbk && atoi(pbk) >= 1 && atoi(pbk) <= 64) b->panel_blocks = atoi(pbk);
+  const char* pg = getenv("DGP_PREGEN");
+  if (pg) b->pregen = atoi(pg) != 0;
   const char* il = getenv("DGP_INPANEL_LEFT");
   if (il) b->inpanel_left = atoi(il) != 0;
   const size_t np = b->max_pad, S = max_sites, nbm = np / 128;

@@ -133,6 +133,21 @@ k_cov_rect(const __grid_constant__ dgp_spec spec, const double* __restrict__ the
                 blockIdx.y);
 }
 
+// Matrices of more than this many block columns are written by the standalone generator ahead of the factorisation
+// (both engines, whatever the stream layout: which kernel generates a tile decides how its first update rounds).
+constexpr int DGP_PREGEN_MIN_NB = 8;
+
+// lower-triangle blocks of block columns [ob, ob + gridDim.y) of the work matrix (noise on the diagonal, identity padding),
+// rows from block ob down: grid = (4 (nb - ob), width).  The standalone generator of the pre-generation schedule (DGP_PREGEN).
+__global__ void __launch_bounds__(256)
+k_cov_lower(const __grid_constant__ dgp_spec spec, const double* __restrict__ theta, const double* __restrict__ Xw,
+            const double* __restrict__ noise, double jitter, double* __restrict__ A, long long ld, int n, int ob) {
+  if ((int)blockIdx.x / 4 < (int)blockIdx.y) return;   // above the diagonal block
+  const size_t o = (size_t)ob * 128;
+  cov_rect_body(spec, theta, Xw + o * DGP_XS, Xw + o * DGP_XS, noise + o, jitter, A + o * ld + o, ld, n - (int)o, n - (int)o, 1, 1,
+                nullptr, nullptr, 0, blockIdx.x, blockIdx.y);
+}
+
 // block column 0 of every site's work matrix (noise on the diagonal, identity padding): grid = (4 nbmax, 1, sites)
 __global__ void __launch_bounds__(256)
 k_cov_col0_b(const __grid_constant__ dgp_spec spec, const __grid_constant__ SiteDims sd, const double* __restrict__ theta,
@@ -143,6 +158,18 @@ k_cov_col0_b(const __grid_constant__ dgp_spec spec, const __grid_constant__ Site
   const size_t v = (size_t)st * sd.ld;
   cov_rect_body(spec, theta + st * DGP_MAX_THETA, Xw + v * DGP_XS, Xw + v * DGP_XS, noise + v, jitv[st], A + v * sd.ld, sd.ld,
                 sd.n[st], sd.n[st], 1, 1, nullptr, nullptr, 0, blockIdx.x, 0);
+}
+
+// ... and the lower-triangle blocks of block columns >= 1 of the sites with more than `min_nb` block columns (DGP_PREGEN_MIN_NB): grid = (4 nbmax, nbmax - 1, sites)
+__global__ void __launch_bounds__(256)
+k_cov_lower_b(const __grid_constant__ dgp_spec spec, const __grid_constant__ SiteDims sd, const double* __restrict__ theta,
+              const double* __restrict__ Xw, const double* __restrict__ noise, const double* __restrict__ jitv,
+              double* __restrict__ A, int min_nb) {
+  const int st = blockIdx.z, nbi = sd.nb[st], col = 1 + (int)blockIdx.y;
+  if (nbi <= min_nb || col >= nbi || (int)blockIdx.x >= 4 * nbi || (int)blockIdx.x / 4 < col) return;
+  const size_t v = (size_t)st * sd.ld;
+  cov_rect_body(spec, theta + st * DGP_MAX_THETA, Xw + v * DGP_XS, Xw + v * DGP_XS, noise + v, jitv[st], A + v * sd.ld, sd.ld,
+                sd.n[st], sd.n[st], 1, 1, nullptr, nullptr, 0, blockIdx.x, col);
 }
 
 // ------------------------------------------------------------------ diagonal block: L, L^-1, L^-T

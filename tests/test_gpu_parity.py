@@ -537,11 +537,13 @@ def test_schedule_switches_agree(cuda_device):
                 os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     out = {}
     # round 2: one trailing stream instead of column strips / narrower strips, the inverse strictly after the factorisation /
-    # always interleaved with it (same operations per tile: bit-identical), left-looking in-panel updates (rounds differently)
+    # always interleaved with it (same operations per tile: bit-identical), left-looking in-panel updates and covariance tiles
+    # generated in the epilogue of their first update instead of by the standalone generator (round differently)
     exact = {"one_trailing_stream": {"DGP_STRIP_BLOCKS": "0"}, "strips4": {"DGP_STRIP_BLOCKS": "4"},
              "inverse_after": {"DGP_EAGER_INV": "0"}, "inverse_eager_lag8": {"DGP_EAGER_INV": "2", "DGP_EAGER_LAG": "8"}}
     for name, env in {"default": {}, "potf2_v1": {"DGP_POTF2_V1": "1"}, "plain": {"DGP_PDL": "0", "DGP_CHAIN_HALF": "0", "DGP_PRIO3": "0"},
-                      "one_stream": {"DGP_LOOKAHEAD": "0"}, "inpanel_left": {"DGP_INPANEL_LEFT": "1"}, **exact}.items():
+                      "one_stream": {"DGP_LOOKAHEAD": "0"}, "inpanel_left": {"DGP_INPANEL_LEFT": "1"},
+                      "first_touch_generation": {"DGP_PREGEN": "0"}, **exact}.items():
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         out[name] = json.loads(r.stdout.strip().splitlines()[-1])
