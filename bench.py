@@ -423,8 +423,8 @@ def main():
                 "peak_source": "measured in this run (MEASURED_PEAKS.json has no FP64 entry, B200_PROFILING.md states no FP64 fallback): "
                                + peak["how"] + "; dmma_pipe_peak = tensor-pipe rate implied by ncu (profiles/ncu_lauum_n16384_r01d.txt)",
                 "peak_clocks": peak["clocks"],
-                "traffic": 61.7e9 if n == N_TRAIN else None,
-                "traffic_note": "dram__bytes_read+write summed over the launches of one evaluation (ncu, profiles/dram_n16384_r02b_summary.txt; working set 3 n^2 x 8 B = 6.4 GB, operand panels re-read through L2)",
+                "traffic": 62.7e9 if n == N_TRAIN else None,
+                "traffic_note": "dram__bytes_read+write summed over the launches of one evaluation (ncu, profiles/dram_n16384_r02d_summary.txt; working set 3 n^2 x 8 B = 6.4 GB, operand panels re-read through L2)",
                 "kernel": "dgp::k_gemm (FP64 DMMA tile engine): every launch of one evaluation",
                 "algorithmic_flop_per_eval": flop,
                 "phases_ms": {"potrf": phase[0], "trtri": phase[1], "lauum_grad": phase[2], "rest": phase[3]},

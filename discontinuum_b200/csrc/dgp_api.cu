@@ -13,8 +13,12 @@
 //      z = U'r, alpha = U z, LAUUM -> Ky^-1 (lower tiles), gradient contraction W (.) dK/dtheta              (n^3/3, DMMA)
 //   deterministic reductions -> {nlml, info, grad} -> pinned host buffer.
 // Three padded n x n panels: bufA (work matrix, then T = L^-1 and scratch, then Ky^-1), bufL (L, lower), bufU (U = L^-T,
-// upper).  The covariance matrix itself is never stored: a tile is generated in shared memory in the epilogue of its first
-// trailing update (out = K - sum).
+// upper).  Covariance tiles come from one of two generators with the same per-entry arithmetic (dgp_cov.cuh): up to
+// DGP_PREGEN_MIN_NB block columns, for the prediction / sampling matrices and with DGP_PREGEN=0 a tile is generated in shared
+// memory in the epilogue of its first trailing update (out = K - sum) and K itself is never stored; for larger training
+// matrices a standalone generator writes the lower tiles of K into the work matrix strip by strip on the low-priority stream
+// while the first panel is factored (measured faster: the generator's FP64 arithmetic shares the datapath with DMMA and is
+// latency-bound inside a GEMM epilogue; the extra 2 x 8 n^2 bytes are 3 % of the evaluation's DRAM traffic).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
